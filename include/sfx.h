@@ -1,0 +1,127 @@
+/* sfx.h -- C ABI of the sm_100a batched speech feature extractor (libsfx_b200.so).
+ *
+ * The reference has no FFI/plugin layer for this path: the boundary is the Python module
+ * preprocessing/audio_preprocessing.py (reference :12-46), whose per-clip functions call librosa.
+ * These entry points are what a maintainer binds (ctypes) to replace, in one
+ * batched device pass, the four calls the reference makes per clip:
+ *
+ *   sfx_extract / sfx_extract_host  <->  extract_mfcc             (audio_preprocessing.py:22-24)
+ *                                        extract_chroma           (audio_preprocessing.py:27-29)
+ *                                        extract_spectral_features(audio_preprocessing.py:32-37)
+ *                                        np.concatenate -> f32[56] (audio_preprocessing.py:45-46)
+ *   lengths[] / n_default            <->  the pad/trim of load_audio (audio_preprocessing.py:14-18):
+ *                                        a clip shorter than the row is read up to lengths[i] only.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every function returns 0 on success
+ * or a negative sfx_status; sfx_last_error() gives the text.  Nothing here falls back to the CPU:
+ * without a CUDA device every compute entry point fails with SFX_ERR_CUDA.
+ * Device entry points are stream-ordered (no host sync inside) and re-entrant across streams given
+ * distinct workspaces.  The caller owns every buffer.
+ */
+#ifndef SFX_B200_H
+#define SFX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFX_ABI_VERSION 1
+#define SFX_N_CHROMA    12
+#define SFX_N_SPECTRAL  4      /* [zcr, spectral_centroid, spectral_rolloff, rms] (reference :33-37) */
+#define SFX_N_FFT       2048
+#define SFX_HOP         512
+#define SFX_N_BINS      1025
+#define SFX_N_MELS      128
+#define SFX_P_STRIDE    1056   /* padded bin row */
+#define SFX_N_TUNINGS   100
+
+typedef enum {
+    SFX_OK              =  0,
+    SFX_ERR_ARG         = -1,  /* bad argument (null pointer, negative size, n_mfcc out of range ...) */
+    SFX_ERR_CUDA        = -2,  /* CUDA runtime error (including "no device") */
+    SFX_ERR_NOT_INIT    = -3,  /* sfx_init_tables has not been called for this device */
+    SFX_ERR_WORKSPACE   = -4,  /* workspace too small */
+    SFX_ERR_BAD_CLIP    = -5   /* a clip has length <= 0 or a non-finite sample (sfx_extract_host only) */
+} sfx_status;
+
+/* Host-side constant tables (generated in float64 by sfx_b200/tables.py; see that file for layouts). */
+typedef struct {
+    int32_t       sr;            /* sample rate the banks were built for (reference config.py:57) */
+    int32_t       pip_kmin;      /* first/last rFFT bin with 150 Hz <= f < 4000 Hz (librosa.piptrack) */
+    int32_t       pip_kmax;
+    int32_t       mel_rows;      /* rows of melw */
+    const float  *hann;          /* [2048] */
+    const float  *tw1;           /* [32][32][2] */
+    const float  *tw2;           /* [32][32][2] */
+    const float  *melw;          /* [mel_rows][32] */
+    const int32_t*mel_lo;        /* [128] */
+    const int32_t*mel_off;       /* [4] */
+    const int32_t*mel_len;       /* [4] */
+    const float  *chroma;        /* [100][12][1056] */
+    const double *dct;           /* [128][128] */
+    const double *edges;         /* [101] */
+} sfx_tables_host;
+
+/* Optional per-clip / per-frame intermediates for parity triage (device pointers, any may be NULL). */
+typedef struct {
+    float   *P;          /* [B][T_dbg][1056] power spectrum |X|^2 */
+    float   *logmel;     /* [B][T_dbg][128]  10*log10(max(1e-10, mel)) before the top_db clamp */
+    float   *frame_feat; /* [B][T_dbg][4]    per-frame centroid(Hz), rolloff(Hz), rms, zc-count of the frame's hop */
+    float   *clip_info;  /* [B][8]           tuning, gmax, n_peaks, median threshold, n_selected, T, 0, 0 */
+    int32_t  T_dbg;      /* frames allocated per clip in the arrays above */
+} sfx_debug_out;
+
+int         sfx_abi_version(void);
+const char *sfx_last_error(void);
+
+/* Number of CUDA devices visible (<0 on error; 0 = none: compute calls will fail). */
+int         sfx_device_count(void);
+
+/* Upload the constant tables to `device` (idempotent per (device, sr); replaces earlier tables). */
+int         sfx_init_tables(int device, const sfx_tables_host *tables);
+
+/* Bytes of device workspace sfx_extract needs for clips of at most max_samples samples.
+ * Independent of the batch size (persistent CTAs each own a fixed scratch slice).  0 on error. */
+size_t      sfx_workspace_bytes(int device, int64_t max_samples);
+
+/* Number of kernels one sfx_extract call launches (for launch accounting). */
+int         sfx_launches_per_extract(void);
+
+/* Batched extraction, device buffers.
+ *   wave        [B] rows of float32 samples, row i at wave + i*row_stride (device)
+ *   lengths     [B] int32 sample counts (device) or NULL = every clip has n_default samples
+ *   out         [B] rows of (n_mfcc + 12 + 4) float32 at out + i*out_stride (device):
+ *               [mfcc_0..n_mfcc-1 | chroma C..B | zcr, centroid_Hz, rolloff_Hz, rms]
+ *   workspace   >= sfx_workspace_bytes(device, max length in the batch)
+ *   stream      cudaStream_t (NULL = legacy default stream)
+ * A clip with length <= 0 yields a row of NaN (the host wrapper raises, as librosa would).
+ */
+int         sfx_extract(int device, const float *wave, int64_t row_stride, const int32_t *lengths,
+                        int64_t n_default, int64_t max_samples, int32_t B, int32_t n_mfcc,
+                        float *out, int64_t out_stride, void *workspace, size_t workspace_bytes,
+                        void *stream);
+
+/* Same, additionally filling `dbg`. */
+int         sfx_extract_debug(int device, const float *wave, int64_t row_stride, const int32_t *lengths,
+                              int64_t n_default, int64_t max_samples, int32_t B, int32_t n_mfcc,
+                              float *out, int64_t out_stride, void *workspace, size_t workspace_bytes,
+                              void *stream, const sfx_debug_out *dbg);
+
+/* Batched extraction, HOST buffers (the reference-facing plugin path): pinned staging, chunked
+ * H2D copy overlapped with the kernel on two streams, D2H of the feature rows, then a stream sync.
+ * host_wave rows must hold finite float32 samples; host_lengths may be NULL.  Allocates and caches
+ * its own device buffers per device.  chunk_clips <= 0 selects the default chunk. */
+int         sfx_extract_host(int device, const float *host_wave, int64_t row_stride,
+                             const int32_t *host_lengths, int64_t n_default, int32_t B, int32_t n_mfcc,
+                             float *host_out, int64_t out_stride, int32_t chunk_clips);
+
+/* Release cached device buffers/tables of `device` (tests; process exit does it implicitly). */
+int         sfx_release(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFX_B200_H */

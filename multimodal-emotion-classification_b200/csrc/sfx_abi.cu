@@ -1,0 +1,308 @@
+// sfx_abi.cu -- extern "C" boundary of libsfx_b200.so (declared in include/sfx.h).
+// Host-only logic: per-device table upload, workspace sizing, launch, and the host-buffer pipeline.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "sfx_internal.h"
+
+namespace {
+
+constexpr int kMaxDev = 16;
+constexpr int kHostStreams = 2;
+
+struct HostPath {               // cached buffers of sfx_extract_host
+    cudaStream_t stream[kHostStreams] = {nullptr, nullptr};
+    float* d_wave[kHostStreams] = {nullptr, nullptr};
+    int* d_len[kHostStreams] = {nullptr, nullptr};
+    float* d_out[kHostStreams] = {nullptr, nullptr};
+    void* d_ws[kHostStreams] = {nullptr, nullptr};
+    float* h_stage[kHostStreams] = {nullptr, nullptr};   // pinned staging for pageable input
+    float* h_out[kHostStreams] = {nullptr, nullptr};     // pinned staging for pageable output
+    cudaEvent_t ev_done[kHostStreams] = {nullptr, nullptr};
+    size_t wave_elems = 0, ws_bytes = 0, out_elems = 0;
+    int chunk = 0;
+};
+
+struct DevCtx {
+    bool ready = false;
+    int sm_count = 0, blocks_per_sm = 0, grid_max = 0;
+    sfx::DevTables tb{};
+    std::vector<void*> allocs;
+    HostPath hp;
+};
+
+DevCtx g_ctx[kMaxDev];
+std::mutex g_mu;
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(SFX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+template <class T>
+int upload(DevCtx& c, const T* host, size_t count, const T** dev) {
+    void* d = nullptr;
+    CK(cudaMalloc(&d, count * sizeof(T)));
+    c.allocs.push_back(d);
+    CK(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = static_cast<const T*>(d);
+    return SFX_OK;
+}
+
+void free_host_path(HostPath& hp) {
+    for (int s = 0; s < kHostStreams; ++s) {
+        if (hp.d_wave[s]) cudaFree(hp.d_wave[s]);
+        if (hp.d_len[s]) cudaFree(hp.d_len[s]);
+        if (hp.d_out[s]) cudaFree(hp.d_out[s]);
+        if (hp.d_ws[s]) cudaFree(hp.d_ws[s]);
+        if (hp.h_stage[s]) cudaFreeHost(hp.h_stage[s]);
+        if (hp.h_out[s]) cudaFreeHost(hp.h_out[s]);
+        if (hp.ev_done[s]) cudaEventDestroy(hp.ev_done[s]);
+        if (hp.stream[s]) cudaStreamDestroy(hp.stream[s]);
+    }
+    hp = HostPath{};
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int do_extract(int device, const float* wave, int64_t row_stride, const int32_t* lengths, int64_t n_default,
+               int64_t max_samples, int32_t B, int32_t n_mfcc, float* out, int64_t out_stride, void* ws,
+               size_t ws_bytes, void* stream, const sfx_debug_out* dbg) {
+    if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
+    if (B < 0 || n_mfcc < 1 || n_mfcc > sfx::kMels) return fail(SFX_ERR_ARG, "B < 0 or n_mfcc outside [1,128]");
+    if (B == 0) return SFX_OK;
+    if (!wave || !out || !ws) return fail(SFX_ERR_ARG, "null wave/out/workspace pointer");
+    if (row_stride < 0 || out_stride < n_mfcc + 16) return fail(SFX_ERR_ARG, "bad row_stride/out_stride");
+    if (max_samples < 1) return fail(SFX_ERR_ARG, "max_samples < 1");
+    if (!lengths && (n_default < 1 || n_default > max_samples)) return fail(SFX_ERR_ARG, "n_default outside [1,max_samples]");
+    DevCtx& c = g_ctx[device];
+    if (!c.ready) return fail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this device");
+    CK(cudaSetDevice(device));
+    const int Tmax = 1 + static_cast<int>(max_samples / sfx::kHop);
+    const size_t slice = sfx::cta_scratch_bytes(Tmax);
+    const int grid = std::min<int64_t>(B, c.grid_max);
+    if (ws_bytes < sfx::kWsHeader + slice * static_cast<size_t>(grid))
+        return fail(SFX_ERR_WORKSPACE, "workspace smaller than sfx_workspace_bytes(device, max_samples)");
+    sfx::Params p{};
+    p.wave = wave; p.row_stride = row_stride; p.lengths = lengths; p.n_default = n_default;
+    p.B = B; p.n_mfcc = n_mfcc; p.out = out; p.out_stride = out_stride;
+    p.ws = static_cast<unsigned char*>(ws); p.cta_scratch_bytes = static_cast<long long>(slice); p.Tmax = Tmax;
+    p.aligned8 = ((reinterpret_cast<uintptr_t>(wave) & 7u) == 0 && (row_stride & 1) == 0) ? 1 : 0;
+    p.tb = c.tb;
+    if (dbg) p.dbg = *dbg;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaMemsetAsync(ws, 0, sfx::kWsHeader, st));
+    CK(sfx::launch_extract(p, grid, dbg != nullptr, st));
+    return SFX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sfx_abi_version(void) { return SFX_ABI_VERSION; }
+const char* sfx_last_error(void) { return g_err.c_str(); }
+
+int sfx_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); g_err = cudaGetErrorString(e); return e == cudaErrorNoDevice ? 0 : SFX_ERR_CUDA; }
+    return n;
+}
+
+int sfx_launches_per_extract(void) { return 1; }
+
+int sfx_release(int device) {
+    if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
+    std::lock_guard<std::mutex> lk(g_mu);
+    DevCtx& c = g_ctx[device];
+    if (!c.ready && c.allocs.empty()) return SFX_OK;
+    cudaSetDevice(device);
+    free_host_path(c.hp);
+    for (void* d : c.allocs) cudaFree(d);
+    c = DevCtx{};
+    return SFX_OK;
+}
+
+int sfx_init_tables(int device, const sfx_tables_host* t) {
+    if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
+    if (!t || !t->hann || !t->tw1 || !t->tw2 || !t->melw || !t->mel_lo || !t->mel_off || !t->mel_len || !t->chroma ||
+        !t->dct || !t->edges || t->mel_rows <= 0 || t->sr <= 0)
+        return fail(SFX_ERR_ARG, "null table pointer or bad sizes");
+    if (t->pip_kmin < 1 || t->pip_kmax > sfx::kBins - 2 || t->pip_kmax < t->pip_kmin)
+        return fail(SFX_ERR_ARG, "piptrack bin range outside [1,1023]");
+    if ((t->pip_kmax - t->pip_kmin + 2) / 2 > sfx::kMaxPk) return fail(SFX_ERR_ARG, "piptrack range exceeds peak capacity");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device >= ndev) return fail(SFX_ERR_CUDA, "no such CUDA device");
+    sfx_release(device);
+    std::lock_guard<std::mutex> lk(g_mu);
+    DevCtx& c = g_ctx[device];
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(SFX_ERR_CUDA, "libsfx_b200 is built for sm_100a only");
+    c.sm_count = prop.multiProcessorCount;
+    int rc;
+    const float* f = nullptr;
+    if ((rc = upload(c, t->hann, 2048, &f))) return rc;
+    c.tb.hann = reinterpret_cast<const float2*>(f);
+    if ((rc = upload(c, t->tw1, 2048, &f))) return rc;
+    c.tb.tw1 = reinterpret_cast<const float2*>(f);
+    if ((rc = upload(c, t->tw2, 2048, &f))) return rc;
+    c.tb.tw2 = reinterpret_cast<const float2*>(f);
+    if ((rc = upload(c, t->melw, static_cast<size_t>(t->mel_rows) * 32, &c.tb.melw))) return rc;
+    if ((rc = upload(c, t->mel_lo, 128, &c.tb.mel_lo))) return rc;
+    if ((rc = upload(c, t->chroma, static_cast<size_t>(sfx::kTunings) * sfx::kChroma * sfx::kPStride, &c.tb.chroma))) return rc;
+    std::vector<double> dctT(static_cast<size_t>(sfx::kMels) * sfx::kMels);
+    for (int k = 0; k < sfx::kMels; ++k)
+        for (int m = 0; m < sfx::kMels; ++m) dctT[static_cast<size_t>(m) * sfx::kMels + k] = t->dct[static_cast<size_t>(k) * sfx::kMels + m];
+    if ((rc = upload(c, dctT.data(), dctT.size(), &c.tb.dctT))) return rc;
+    if ((rc = upload(c, t->edges, sfx::kTunings + 1, &c.tb.edges))) return rc;
+    for (int s = 0; s < 4; ++s) { c.tb.mel_off[s] = t->mel_off[s]; c.tb.mel_len[s] = t->mel_len[s]; }
+    c.tb.sr = t->sr; c.tb.kmin = t->pip_kmin; c.tb.kmax = t->pip_kmax;
+    CK(sfx::configure_kernels(&c.blocks_per_sm));
+    if (c.blocks_per_sm < 1) return fail(SFX_ERR_CUDA, "kernel does not fit on an SM");
+    c.grid_max = c.sm_count * c.blocks_per_sm;
+    c.ready = true;
+    return SFX_OK;
+}
+
+size_t sfx_workspace_bytes(int device, int64_t max_samples) {
+    if (device < 0 || device >= kMaxDev || max_samples < 1 || !g_ctx[device].ready) {
+        g_err = "sfx_workspace_bytes: bad device/max_samples or tables not initialised";
+        return 0;
+    }
+    const int Tmax = 1 + static_cast<int>(max_samples / sfx::kHop);
+    return sfx::kWsHeader + sfx::cta_scratch_bytes(Tmax) * static_cast<size_t>(g_ctx[device].grid_max);
+}
+
+int sfx_extract(int device, const float* wave, int64_t row_stride, const int32_t* lengths, int64_t n_default,
+                int64_t max_samples, int32_t B, int32_t n_mfcc, float* out, int64_t out_stride, void* workspace,
+                size_t workspace_bytes, void* stream) {
+    return do_extract(device, wave, row_stride, lengths, n_default, max_samples, B, n_mfcc, out, out_stride, workspace,
+                      workspace_bytes, stream, nullptr);
+}
+
+int sfx_extract_debug(int device, const float* wave, int64_t row_stride, const int32_t* lengths, int64_t n_default,
+                      int64_t max_samples, int32_t B, int32_t n_mfcc, float* out, int64_t out_stride, void* workspace,
+                      size_t workspace_bytes, void* stream, const sfx_debug_out* dbg) {
+    if (!dbg) return fail(SFX_ERR_ARG, "null dbg");
+    return do_extract(device, wave, row_stride, lengths, n_default, max_samples, B, n_mfcc, out, out_stride, workspace,
+                      workspace_bytes, stream, dbg);
+}
+
+int sfx_extract_host(int device, const float* host_wave, int64_t row_stride, const int32_t* host_lengths,
+                     int64_t n_default, int32_t B, int32_t n_mfcc, float* host_out, int64_t out_stride,
+                     int32_t chunk_clips) {
+    if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
+    if (B < 0 || n_mfcc < 1 || n_mfcc > sfx::kMels) return fail(SFX_ERR_ARG, "B < 0 or n_mfcc outside [1,128]");
+    if (B == 0) return SFX_OK;
+    if (!host_wave || !host_out) return fail(SFX_ERR_ARG, "null host pointer");
+    if (row_stride < 1 || out_stride < n_mfcc + 16) return fail(SFX_ERR_ARG, "bad row_stride/out_stride");
+    if (!host_lengths && (n_default < 1 || n_default > row_stride)) return fail(SFX_ERR_ARG, "n_default outside [1,row_stride]");
+    DevCtx& c = g_ctx[device];
+    if (!c.ready) return fail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this device");
+    CK(cudaSetDevice(device));
+    int64_t max_samples = n_default;
+    if (host_lengths) {
+        max_samples = 1;
+        for (int i = 0; i < B; ++i) {
+            if (host_lengths[i] <= 0 || host_lengths[i] > row_stride) return fail(SFX_ERR_BAD_CLIP, "clip length outside [1,row_stride]");
+            max_samples = std::max<int64_t>(max_samples, host_lengths[i]);
+        }
+    }
+    // rows are copied up to max_samples only (rounded to even for 8-byte alignment of every device row)
+    const int64_t dev_stride = (max_samples + 1) & ~int64_t(1);
+    int chunk = chunk_clips > 0 ? chunk_clips : static_cast<int>(std::max<int64_t>(64, (256ll << 20) / (dev_stride * 4)));
+    chunk = std::min(chunk, B);
+    const int out_w = n_mfcc + 16;
+    const size_t need_wave = static_cast<size_t>(chunk) * dev_stride;
+    const size_t need_ws = sfx_workspace_bytes(device, max_samples);
+    const size_t need_out = static_cast<size_t>(chunk) * out_w;
+    std::lock_guard<std::mutex> lk(g_mu);
+    HostPath& hp = c.hp;
+    const bool in_pinned = is_pinned(host_wave), out_pinned = is_pinned(host_out);
+    if (hp.wave_elems < need_wave || hp.ws_bytes < need_ws || hp.out_elems < need_out || hp.chunk < chunk ||
+        (!in_pinned && !hp.h_stage[0]) || (!out_pinned && !hp.h_out[0])) {
+        free_host_path(hp);
+        for (int s = 0; s < kHostStreams; ++s) {
+            CK(cudaStreamCreateWithFlags(&hp.stream[s], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&hp.ev_done[s], cudaEventDisableTiming));
+            CK(cudaMalloc(&hp.d_wave[s], need_wave * 4));
+            CK(cudaMalloc(&hp.d_len[s], static_cast<size_t>(chunk) * 4));
+            CK(cudaMalloc(&hp.d_out[s], need_out * 4));
+            CK(cudaMalloc(&hp.d_ws[s], need_ws));
+            if (!in_pinned) CK(cudaMallocHost(&hp.h_stage[s], need_wave * 4));
+            if (!out_pinned) CK(cudaMallocHost(&hp.h_out[s], need_out * 4));
+        }
+        hp.wave_elems = need_wave; hp.ws_bytes = need_ws; hp.out_elems = need_out; hp.chunk = chunk;
+    }
+    int nchunks = (B + chunk - 1) / chunk;
+    std::vector<int> pend_c0(kHostStreams, -1), pend_nb(kHostStreams, 0);
+    auto drain = [&](int s) -> int {      // copy a finished chunk's rows out of pinned staging
+        if (pend_c0[s] < 0) return SFX_OK;
+        CK(cudaEventSynchronize(hp.ev_done[s]));
+        if (!out_pinned) {
+            for (int i = 0; i < pend_nb[s]; ++i)
+                std::memcpy(host_out + static_cast<int64_t>(pend_c0[s] + i) * out_stride, hp.h_out[s] + static_cast<size_t>(i) * out_w,
+                            sizeof(float) * out_w);
+        }
+        pend_c0[s] = -1;
+        return SFX_OK;
+    };
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int s = ci % kHostStreams;
+        const int c0 = ci * chunk, nb = std::min(chunk, B - c0);
+        int rc = drain(s);
+        if (rc) return rc;
+        cudaStream_t st = hp.stream[s];
+        const float* src = host_wave + static_cast<int64_t>(c0) * row_stride;
+        const size_t row_bytes = static_cast<size_t>(max_samples) * 4;
+        if (in_pinned) {
+            CK(cudaMemcpy2DAsync(hp.d_wave[s], dev_stride * 4, src, row_stride * 4, row_bytes, nb, cudaMemcpyHostToDevice, st));
+        } else {
+            for (int i = 0; i < nb; ++i)
+                std::memcpy(hp.h_stage[s] + static_cast<size_t>(i) * dev_stride, src + static_cast<int64_t>(i) * row_stride, row_bytes);
+            CK(cudaMemcpyAsync(hp.d_wave[s], hp.h_stage[s], static_cast<size_t>(nb) * dev_stride * 4, cudaMemcpyHostToDevice, st));
+        }
+        const int32_t* dlen = nullptr;
+        if (host_lengths) {
+            CK(cudaMemcpyAsync(hp.d_len[s], host_lengths + c0, static_cast<size_t>(nb) * 4, cudaMemcpyHostToDevice, st));
+            dlen = hp.d_len[s];
+        }
+        rc = do_extract(device, hp.d_wave[s], dev_stride, dlen, n_default, max_samples, nb, n_mfcc, hp.d_out[s], out_w,
+                        hp.d_ws[s], hp.ws_bytes, st, nullptr);
+        if (rc) return rc;
+        if (out_pinned) {
+            CK(cudaMemcpy2DAsync(host_out + static_cast<int64_t>(c0) * out_stride, out_stride * 4, hp.d_out[s], out_w * 4,
+                                 static_cast<size_t>(out_w) * 4, nb, cudaMemcpyDeviceToHost, st));
+        } else {
+            CK(cudaMemcpyAsync(hp.h_out[s], hp.d_out[s], static_cast<size_t>(nb) * out_w * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaEventRecord(hp.ev_done[s], st));
+        pend_c0[s] = c0; pend_nb[s] = nb;
+    }
+    for (int s = 0; s < kHostStreams; ++s) {
+        int rc = drain(s);
+        if (rc) return rc;
+    }
+    return SFX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// sfx_internal.h -- shared between sfx_kernels.cu (device) and sfx_abi.cu (host C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/sfx.h"
+
+namespace sfx {
+
+constexpr int kNfft = SFX_N_FFT;
+constexpr int kHop = SFX_HOP;
+constexpr int kBins = SFX_N_BINS;
+constexpr int kMels = SFX_N_MELS;
+constexpr int kChroma = SFX_N_CHROMA;
+constexpr int kPStride = SFX_P_STRIDE;
+constexpr int kTunings = SFX_N_TUNINGS;
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kExFloats = 32 * 33 * 2;   // per-warp float2[32][33] exchange tile, reused as the padded |X|^2 tile
+constexpr int kMaxPk = 180;              // piptrack peaks per frame: local maxima among <= 358 bins
+constexpr size_t kWsHeader = 256;        // clip-queue counter lives in the first bytes of the workspace
+
+struct DevTables {
+    const float2* hann;     // [1024]
+    const float2* tw1;      // [32][32]
+    const float2* tw2;      // [32][32]
+    const float* melw;      // [mel_rows][32]
+    const int* mel_lo;      // [128]
+    int mel_off[4];
+    int mel_len[4];
+    const float* chroma;    // [100][12][1056]
+    const double* dctT;     // [128 mel][128 k]  (transposed: coalesced over k)
+    const double* edges;    // [101]
+    int sr, kmin, kmax;
+};
+
+struct Params {
+    const float* wave;
+    long long row_stride;
+    const int* lengths;
+    long long n_default;
+    int B;
+    int n_mfcc;
+    float* out;
+    long long out_stride;
+    unsigned char* ws;
+    long long cta_scratch_bytes;
+    int Tmax;
+    int aligned8;
+    DevTables tb;
+    sfx_debug_out dbg;
+};
+
+// bytes of scratch one CTA needs for clips of up to Tmax frames (multiple of 256)
+inline size_t cta_scratch_bytes(int Tmax) {
+    size_t b = static_cast<size_t>(Tmax) * (kPStride * 4 + kMels * 4 + kMaxPk * 8);
+    return (b + 255) & ~static_cast<size_t>(255);
+}
+
+size_t smem_bytes();
+cudaError_t configure_kernels(int* blocks_per_sm);
+cudaError_t launch_extract(const Params& p, int grid, bool debug, cudaStream_t stream);
+
+}  // namespace sfx

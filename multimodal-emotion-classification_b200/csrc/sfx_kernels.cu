@@ -1,0 +1,706 @@
+// sfx_kernels.cu -- sm_100a kernels of the batched speech feature extractor.
+//
+// One persistent CTA per clip (dynamic clip queue), 8 warps, 2 CTAs per SM.  Replaces, for a whole batch,
+// the per-clip librosa calls of the reference's preprocessing/audio_preprocessing.py:22-37:
+//   phase 1 (warp per STFT frame): framing + Hann + 2048-pt real FFT (1024-pt complex FFT as two
+//           register-resident radix-32 passes with one shared-memory transpose) -> |X|^2;
+//           rms / zero crossings from the raw samples; |X| centroid + 0.85 roll-off (warp scan);
+//           piptrack peaks (librosa.piptrack on the POWER spectrum) appended to the clip's peak list;
+//           sparse Slaney mel projection + 10*log10.  |X|^2 and log-mel rows go to the CTA's scratch slice.
+//   phase 2 (CTA): estimate_tuning = median of peak magnitudes (radix select) -> 100-bin histogram
+//           arg-max; global log-mel max for power_to_db(top_db=80).
+//   phase 3 (CTA): clamp + frame-mean of log-mel, DCT-II (float64) -> MFCC; chroma projection with the
+//           tuning's filter bank, per-frame inf-norm, frame mean; pooled spectral descriptors.
+// Output row: [mfcc_0..n_mfcc-1 | chroma C..B | zcr, centroid, rolloff, rms]  (reference :45-46).
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <cstdint>
+#include <type_traits>
+#include <utility>
+
+#include "sfx_internal.h"
+
+namespace sfx {
+
+// ------------------------------------------------------------------------------------------------
+// compile-time helpers
+template <int... I, class F>
+__device__ __forceinline__ void sfor_impl(std::integer_sequence<int, I...>, F&& f) {
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void sfor(F&& f) {
+    sfor_impl(std::make_integer_sequence<int, N>{}, static_cast<F&&>(f));
+}
+
+__host__ __device__ constexpr int brev5(int k) {
+    return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
+}
+
+__host__ __device__ constexpr float cos32(int q) {
+    constexpr float t[16] = {1.0f,
+                             0.98078528040323044913f,
+                             0.92387953251128675613f,
+                             0.83146961230254523708f,
+                             0.70710678118654752440f,
+                             0.55557023301960222474f,
+                             0.38268343236508977173f,
+                             0.19509032201612826785f,
+                             0.0f,
+                             -0.19509032201612826785f,
+                             -0.38268343236508977173f,
+                             -0.55557023301960222474f,
+                             -0.70710678118654752440f,
+                             -0.83146961230254523708f,
+                             -0.92387953251128675613f,
+                             -0.98078528040323044913f};
+    return t[q];
+}
+// sin(2*pi*q/32) = cos(2*pi*(8-q)/32) for q <= 8, cos(2*pi*(q-8)/32) for q in (8,16)
+__host__ __device__ constexpr float sin32x(int q) { return q <= 8 ? cos32(8 - q) : cos32(q - 8); }
+
+// (r + i*im) *= exp(-2*pi*i*Q/32)
+template <int Q>
+__device__ __forceinline__ void mul_w32(float& r, float& i) {
+    constexpr float kS = 0.70710678118654752440f;
+    if constexpr (Q == 0) {
+    } else if constexpr (Q == 8) {          // * (-i)
+        const float t = r; r = i; i = -t;
+    } else if constexpr (Q == 4) {          // * (1 - i)/sqrt2
+        const float t = (r + i) * kS; i = (i - r) * kS; r = t;
+    } else if constexpr (Q == 12) {         // * (-1 - i)/sqrt2
+        const float t = (i - r) * kS; i = -(r + i) * kS; r = t;
+    } else {
+        constexpr float c = cos32(Q), s = sin32x(Q);   // W = c - i*s
+        const float t = fmaf(r, c, i * s);
+        i = fmaf(i, c, -(r * s));
+        r = t;
+    }
+}
+
+// radix-2 DIF stage of half-size H over 32 register-resident points
+template <int H>
+__device__ __forceinline__ void dif_stage(float (&re)[32], float (&im)[32]) {
+    sfor<16 / H>([&](auto B) {
+        sfor<H>([&](auto J) {
+            constexpr int i0 = decltype(B)::value * 2 * H + decltype(J)::value;
+            constexpr int i1 = i0 + H;
+            constexpr int Q = decltype(J)::value * (16 / H);
+            const float ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
+            re[i0] = ar + br;
+            im[i0] = ai + bi;
+            float dr = ar - br, di = ai - bi;
+            mul_w32<Q>(dr, di);
+            re[i1] = dr;
+            im[i1] = di;
+        });
+    });
+}
+
+// 32-point complex FFT in registers; X[k] ends up in slot brev5(k)
+__device__ __forceinline__ void fft32(float (&re)[32], float (&im)[32]) {
+    dif_stage<16>(re, im);
+    dif_stage<8>(re, im);
+    dif_stage<4>(re, im);
+    dif_stage<2>(re, im);
+    dif_stage<1>(re, im);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ unsigned fkey(float f) {      // order-preserving float -> uint
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ int pidx(int k) { return k + (k >> 5); }   // padded index of bin k in the P tile
+
+// ------------------------------------------------------------------------------------------------
+// CTA-wide radix select over the clip's peak magnitudes: key of the element of ascending rank r.
+// count_le = number of elements <= that key.  All threads must call; uses s_hist[256], s_sel[4].
+__device__ unsigned radix_select(const float* mags, int np, int r, int* s_hist, int* s_sel, int& count_le) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned prefix = 0, mask = 0;
+    int less = 0, equal = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = tid; i < 256; i += kThreads) s_hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < np; i += kThreads) {
+            const unsigned key = fkey(mags[i]);
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255], 1);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int loc[8];
+            int sum = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { loc[q] = s_hist[lane * 8 + q]; sum += loc[q]; }
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            const int exc = inc - sum;
+            const unsigned bal = __ballot_sync(0xffffffffu, inc > r);
+            const int L = __ffs(bal) - 1;
+            if (lane == L) {
+                int rr = r - exc, cum = 0, q = 0, sel = 0, eq = 0;
+                bool done = false;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (!done) {
+                        if (cum + loc[u] > rr) { done = true; sel = u; eq = loc[u]; }
+                        else cum += loc[u];
+                    }
+                }
+                (void)q;
+                s_sel[0] = lane * 8 + sel;
+                s_sel[1] = rr - cum;
+                s_sel[2] = exc + cum;
+                s_sel[3] = eq;
+            }
+        }
+        __syncthreads();
+        const int bucket = s_sel[0];
+        r = s_sel[1];
+        less += s_sel[2];
+        equal = s_sel[3];
+        prefix |= static_cast<unsigned>(bucket) << shift;
+        mask |= 0xFFu << shift;
+        __syncthreads();
+    }
+    count_le = less + equal;
+    return prefix;
+}
+
+// reduce-scatter of 32 per-lane values: afterwards lane l holds sum over lanes of v[l] in v[0]
+__device__ __forceinline__ float reduce_scatter32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float send = up ? v[i] : v[i + h];
+            const float keep = up ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    return v[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool kDebug>
+__global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_hann = reinterpret_cast<float2*>(smem_raw);
+    float2* s_tw1 = s_hann + 1024;
+    float2* s_tw2 = s_tw1 + 1024;
+    float* s_ex = reinterpret_cast<float*>(s_tw2 + 1024);
+    double* s_pool = reinterpret_cast<double*>(s_ex + kWarps * kExFloats);   // [256]
+    double* s_wacc = s_pool + 256;                                           // [kWarps][16]
+    int* s_hist = reinterpret_cast<int*>(s_wacc + kWarps * 16);              // [256]
+    int* s_i = s_hist + 256;                                                 // [32]
+    float* s_f = reinterpret_cast<float*>(s_i + 32);                         // [32]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DevTables& tb = p.tb;
+
+    for (int i = tid; i < 1024; i += kThreads) {
+        s_hann[i] = tb.hann[i];
+        s_tw1[i] = tb.tw1[i];
+        s_tw2[i] = tb.tw2[i];
+    }
+    int mlo[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) mlo[s] = tb.mel_lo[32 * s + lane];
+
+    // scratch slice of this CTA
+    unsigned char* slice = p.ws + kWsHeader + static_cast<size_t>(blockIdx.x) * p.cta_scratch_bytes;
+    float* gP = reinterpret_cast<float*>(slice);
+    float* gL = gP + static_cast<size_t>(p.Tmax) * kPStride;
+    float* gMag = gL + static_cast<size_t>(p.Tmax) * kMels;
+    int* gBin = reinterpret_cast<int*>(gMag + static_cast<size_t>(p.Tmax) * kMaxPk);
+    int* counter = reinterpret_cast<int*>(p.ws);
+
+    float* Pb = s_ex + warp * kExFloats;               // this warp's exchange / P tile
+    float2* ex = reinterpret_cast<float2*>(Pb);
+    const float bin_hz = static_cast<float>(static_cast<double>(tb.sr) / kNfft);
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { s_i[0] = atomicAdd(counter, 1); s_i[1] = 0; }
+        __syncthreads();
+        const int clip = s_i[0];
+        if (clip >= p.B) break;
+        const long long n = p.lengths ? static_cast<long long>(p.lengths[clip]) : p.n_default;
+        float* out = p.out + static_cast<long long>(clip) * p.out_stride;
+        if (n <= 0) {
+            for (int i = tid; i < p.n_mfcc + 16; i += kThreads) out[i] = __int_as_float(0x7fc00000);
+            continue;
+        }
+        const int T = 1 + static_cast<int>(n / kHop);
+        const float* x = p.wave + static_cast<long long>(clip) * p.row_stride;
+
+        // ===================================== phase 1: frames =====================================
+        double acc_cent = 0.0, acc_roll = 0.0, acc_rms = 0.0;
+        int acc_zc = 0;
+        float gmax = -FLT_MAX;
+
+        for (int t = warp; t < T; t += kWarps) {
+            float re[32], im[32];
+            const long long s0 = static_cast<long long>(kHop) * t - kNfft / 2;
+            if (s0 >= 0 && s0 + kNfft <= n && p.aligned8) {
+                const float2* src = reinterpret_cast<const float2*>(x + s0) + lane;
+#pragma unroll
+                for (int m1 = 0; m1 < 32; ++m1) {
+                    const float2 v = __ldg(src + 32 * m1);
+                    re[m1] = v.x;
+                    im[m1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int m1 = 0; m1 < 32; ++m1) {
+                    const long long g = s0 + 2 * (32 * m1 + lane);
+                    re[m1] = (g >= 0 && g < n) ? __ldg(x + g) : 0.0f;
+                    im[m1] = (g + 1 >= 0 && g + 1 < n) ? __ldg(x + g + 1) : 0.0f;
+                }
+            }
+            // ---- rms (librosa.feature.rms: zero pad, no window)
+            float ss = 0.0f;
+#pragma unroll
+            for (int m1 = 0; m1 < 32; ++m1) { ss = fmaf(re[m1], re[m1], ss); ss = fmaf(im[m1], im[m1], ss); }
+            ss = warp_sum(ss);
+            const float rms_t = sqrtf(ss * (1.0f / kNfft));
+
+            // ---- zero crossings of hop t (samples [512t, 512t+512)), weighted by how many frames see them
+            int zc_hop = 0;
+            {
+                int zc = 0, zc_first = 0;
+                const long long ib = static_cast<long long>(kHop) * t;
+                sfor<8>([&](auto R) {
+                    constexpr int r = decltype(R)::value;
+                    constexpr int m1 = 16 + r;
+                    const float e0 = re[m1], e1 = im[m1];
+                    const float up = __shfl_up_sync(0xffffffffu, e1, 1);
+                    const float wrap = __shfl_sync(0xffffffffu, im[m1 - 1], 31);
+                    const float prev = lane == 0 ? wrap : up;
+                    const long long i0 = ib + 2 * (32 * r + lane);
+                    const bool sp = static_cast<double>(prev) < -1e-10;
+                    const bool sa = static_cast<double>(e0) < -1e-10;
+                    const bool sb = static_cast<double>(e1) < -1e-10;
+                    const int c0 = (i0 >= 1 && i0 <= n - 1 && sa != sp) ? 1 : 0;
+                    const int c1 = (i0 + 1 <= n - 1 && sb != sa) ? 1 : 0;
+                    zc += c0 + c1;
+                    if (r == 0 && lane == 0) zc_first = c0;
+                });
+                const int tlo = max(0, t - 1);
+                const int multA = min(T - 1, t + 2) - tlo + 1;
+                const int mult0 = min(T - 1, t + 1) - tlo + 1;
+                zc_hop = zc;
+                acc_zc += multA * zc - (multA - mult0) * zc_first;
+            }
+
+            // ---- Hann window (periodic, scipy.signal.get_window('hann', 2048))
+#pragma unroll
+            for (int m1 = 0; m1 < 32; ++m1) {
+                const float2 w = s_hann[32 * m1 + lane];
+                re[m1] *= w.x;
+                im[m1] *= w.y;
+            }
+            // ---- 1024-pt complex FFT: radix-32 over m1, twiddle, transpose, radix-32 over m2
+            fft32(re, im);
+            sfor<32>([&](auto K) {
+                constexpr int k1 = decltype(K)::value;
+                constexpr int a = brev5(k1);
+                const float2 w = s_tw1[k1 * 32 + lane];
+                const float r = fmaf(re[a], w.x, -(im[a] * w.y));
+                const float i = fmaf(re[a], w.y, im[a] * w.x);
+                ex[k1 * 33 + lane] = make_float2(r, i);
+            });
+            __syncwarp();
+#pragma unroll
+            for (int m2 = 0; m2 < 32; ++m2) {
+                const float2 v = ex[lane * 33 + m2];
+                re[m2] = v.x;
+                im[m2] = v.y;
+            }
+            __syncwarp();
+            fft32(re, im);
+
+            // ---- real-FFT unpack: bin k = lane + 32*k2; partner bin 1024-k lives in lane (32-lane)&31
+            float pmax = 0.0f;
+            float* Pg = gP + static_cast<size_t>(t) * kPStride;
+            const int plane = (32 - lane) & 31;
+            sfor<32>([&](auto K) {
+                constexpr int k2 = decltype(K)::value;
+                constexpr int a = brev5(k2), b = brev5(31 - k2), c = brev5((32 - k2) & 31);
+                const float zr = re[a], zi = im[a];
+                float pr = __shfl_sync(0xffffffffu, re[b], plane);
+                float pi = __shfl_sync(0xffffffffu, im[b], plane);
+                if (lane == 0) { pr = re[c]; pi = im[c]; }
+                const float2 w = s_tw2[k2 * 32 + lane];
+                const float er = zr + pr, ei = zi - pi, orr = zr - pr, oi = zi + pi;
+                const float xr = fmaf(0.5f, er, fmaf(w.x, oi, -(w.y * orr)));
+                const float xi = fmaf(0.5f, ei, -fmaf(w.x, orr, w.y * oi));
+                const float P = fmaf(xr, xr, xi * xi);
+                pmax = fmaxf(pmax, P);
+                Pb[lane + 33 * k2] = P;
+                Pg[lane + 32 * k2] = P;
+            });
+            {
+                const float ny = re[0] - im[0];      // X[1024] = Re Z[0] - Im Z[0] (lane 0)
+                const float Pn = ny * ny;
+                if (lane == 0) { Pb[1024 + 32] = Pn; Pg[1024] = Pn; pmax = fmaxf(pmax, Pn); }
+            }
+            pmax = warp_max(pmax);
+            __syncwarp();
+            if (kDebug) {
+                if (p.dbg.P && t < p.dbg.T_dbg) {
+                    float* dP = p.dbg.P + (static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kPStride;
+                    for (int k = lane; k < kBins; k += 32) dP[k] = Pb[pidx(k)];
+                }
+            }
+
+            // ---- |X| statistics on contiguous bins: lane owns bins [32*lane, 32*lane+32) (+1024 for lane 31)
+            float cent_t, roll_t;
+            {
+                float s[33];
+                float run = 0.0f, ks = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float sv = sqrt_approx(Pb[33 * lane + j]);
+                    run += sv;
+                    s[j] = run;
+                    ks = fmaf(static_cast<float>(j), sv, ks);
+                }
+                s[32] = run;
+                if (lane == 31) {
+                    const float sv = sqrt_approx(Pb[1024 + 32]);
+                    run += sv;
+                    s[32] = run;
+                    ks = fmaf(32.0f, sv, ks);
+                }
+                float inc = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+                if (lane == 0) exc = 0.0f;
+                const float total = __shfl_sync(0xffffffffu, inc, 31);
+                const float thr = __fmul_rn(0.85f, total);
+                int first = 1024;
+                if (lane == 31 && exc + s[32] >= thr) first = 1024;
+#pragma unroll
+                for (int j = 31; j >= 0; --j)
+                    if (exc + s[j] >= thr) first = 32 * lane + j;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+                const float num = warp_sum(fmaf(32.0f * lane, run, ks));
+                cent_t = (total < FLT_MIN) ? 0.0f : (num / total) * bin_hz;
+                roll_t = static_cast<float>(first) * bin_hz;
+            }
+            acc_cent += static_cast<double>(cent_t);
+            acc_roll += static_cast<double>(roll_t);
+            acc_rms += static_cast<double>(rms_t);
+
+            // ---- piptrack peaks on the power spectrum (bins kmin..kmax)
+            {
+                const float ref = __fmul_rn(0.1f, pmax);
+                for (int k0 = tb.kmin; k0 <= tb.kmax; k0 += 32) {
+                    const int k = min(k0 + lane, tb.kmax);
+                    const bool valid = (k0 + lane) <= tb.kmax;
+                    const float pm = Pb[pidx(k - 1)], pc = Pb[pidx(k)], pp = Pb[pidx(k + 1)];
+                    const bool pk = valid && pc > ref && pc > pm && pc >= pp;
+                    const unsigned m = __ballot_sync(0xffffffffu, pk);
+                    if (m) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&s_i[1], __popc(m));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (pk) {
+                            const int pos = base + __popc(m & ((1u << lane) - 1u));
+                            const float sum = __fadd_rn(pp, pm);
+                            const float dif = __fsub_rn(pp, pm);
+                            const double a = static_cast<double>(sum) - 2.0 * static_cast<double>(pc);
+                            const double b = static_cast<double>(dif) * 0.5;
+                            const float shift = (fabs(b) >= fabs(a)) ? 0.0f : static_cast<float>(-b / a);
+                            const float avg = dif * 0.5f;
+                            const float dskew = __fmul_rn(__fmul_rn(0.5f, avg), shift);
+                            const float mag = __fadd_rn(pc, dskew);
+                            const double pitch_d = (static_cast<double>(k) + static_cast<double>(shift)) *
+                                                   static_cast<double>(tb.sr) / static_cast<double>(kNfft);
+                            const float pitch = static_cast<float>(pitch_d);
+                            // pitch_tuning: mod(12*log2(f/27.5), 1) in float32, wrapped to [-0.5, 0.5)
+                            const float o = log2f(__fdiv_rn(pitch, 27.5f));
+                            const float v = __fmul_rn(12.0f, o);
+                            float res = v - floorf(v);
+                            if (res >= 0.5f) res = res - 1.0f;
+                            const double rd = static_cast<double>(res);
+                            int bi = static_cast<int>(floor((rd + 0.5) * 100.0));
+                            bi = max(0, min(kTunings - 1, bi));
+                            while (bi > 0 && rd < tb.edges[bi]) --bi;
+                            while (bi < kTunings - 1 && rd >= tb.edges[bi + 1]) ++bi;
+                            gMag[pos] = mag;
+                            gBin[pos] = bi;
+                        }
+                    }
+                }
+            }
+
+            // ---- sparse Slaney mel projection + 10*log10 (power_to_db before the clamp)
+            {
+                float* Lg = gL + static_cast<size_t>(t) * kMels;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int len = tb.mel_len[s], off = tb.mel_off[s];
+                    const float* w = tb.melw + off * 32 + lane;
+                    float acc = 0.0f;
+                    for (int i = 0; i < len; ++i) {
+                        const int k = min(mlo[s] + i, 1024);
+                        acc = fmaf(__ldg(w + i * 32), Pb[pidx(k)], acc);
+                    }
+                    const float lm = 10.0f * log10f(fmaxf(1e-10f, acc));
+                    Lg[32 * s + lane] = lm;
+                    gmax = fmaxf(gmax, lm);
+                    if (kDebug) {
+                        if (p.dbg.logmel && t < p.dbg.T_dbg)
+                            p.dbg.logmel[(static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kMels + 32 * s + lane] = lm;
+                    }
+                }
+            }
+            if (kDebug) {
+                const int zch = warp_sum_i(zc_hop);
+                if (p.dbg.frame_feat && t < p.dbg.T_dbg && lane == 0) {
+                    float* ff = p.dbg.frame_feat + (static_cast<size_t>(clip) * p.dbg.T_dbg + t) * 4;
+                    ff[0] = cent_t; ff[1] = roll_t; ff[2] = rms_t; ff[3] = static_cast<float>(zch);
+                }
+            }
+            (void)zc_hop;
+            __syncwarp();
+        }
+
+        // per-warp partials
+        {
+            const int zc = warp_sum_i(acc_zc);
+            gmax = warp_max(gmax);
+            if (lane == 0) {
+                s_wacc[warp * 16 + 0] = acc_cent;
+                s_wacc[warp * 16 + 1] = acc_roll;
+                s_wacc[warp * 16 + 2] = acc_rms;
+                s_i[8 + warp] = zc;
+                s_f[warp] = gmax;
+            }
+        }
+        __syncthreads();
+
+        // ===================================== phase 2: tuning =====================================
+        const int np = s_i[1];
+        float gmx = s_f[0];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) gmx = fmaxf(gmx, s_f[w]);
+
+        int tuning_idx = kTunings / 2;       // edges[50] == 0.0: librosa returns 0.0 for an empty pitch set
+        float thr = 0.0f;
+        int nsel = 0;
+        if (np > 0) {
+            int cle = 0;
+            const int r0 = (np - 1) >> 1;
+            const unsigned ka = radix_select(gMag, np, r0, s_hist, s_i + 4, cle);
+            unsigned kb = ka;
+            if ((np & 1) == 0 && cle <= (np >> 1)) {
+                // upper median = smallest key above ka
+                if (tid == 0) s_i[4] = static_cast<int>(0xffffffffu);
+                __syncthreads();
+                unsigned best = 0xffffffffu;
+                for (int i = tid; i < np; i += kThreads) {
+                    const unsigned key = fkey(gMag[i]);
+                    if (key > ka && key < best) best = key;
+                }
+                atomicMin(reinterpret_cast<unsigned*>(&s_i[4]), best);
+                __syncthreads();
+                kb = static_cast<unsigned>(s_i[4]);
+                __syncthreads();
+            }
+            const float fa = fkey_inv(ka), fb = fkey_inv(kb);
+            thr = ((np & 1) == 0) ? __fmul_rn(__fadd_rn(fa, fb), 0.5f) : fa;
+            // histogram of the residual bins of peaks with mag >= median
+            for (int i = tid; i < 128; i += kThreads) s_hist[i] = 0;
+            __syncthreads();
+            for (int i = tid; i < np; i += kThreads)
+                if (gMag[i] >= thr) atomicAdd(&s_hist[gBin[i]], 1);
+            __syncthreads();
+            if (warp == 0) {
+                int bc = -1, bi = 1 << 20, tot = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int b = lane * 4 + q;
+                    if (b < kTunings) {
+                        const int c = s_hist[b];
+                        tot += c;
+                        if (c > bc) { bc = c; bi = b; }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (oc > bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+                }
+                tot = warp_sum_i(tot);
+                if (lane == 0) { s_i[2] = bi; s_i[3] = tot; }
+            }
+            __syncthreads();
+            tuning_idx = s_i[2];
+            nsel = s_i[3];
+        }
+        if (kDebug) {
+            if (p.dbg.clip_info && tid == 0) {
+                float* ci = p.dbg.clip_info + static_cast<size_t>(clip) * 8;
+                ci[0] = static_cast<float>(tb.edges[tuning_idx]);
+                ci[1] = gmx; ci[2] = static_cast<float>(np); ci[3] = thr;
+                ci[4] = static_cast<float>(nsel); ci[5] = static_cast<float>(T); ci[6] = 0.f; ci[7] = 0.f;
+            }
+        }
+
+        // ===================================== phase 3a: MFCC ======================================
+        {
+            const float clampv = __fsub_rn(gmx, 80.0f);
+            const int m = tid & 127, h = tid >> 7;
+            double a = 0.0;
+            for (int t = h; t < T; t += 2) a += static_cast<double>(fmaxf(gL[static_cast<size_t>(t) * kMels + m], clampv));
+            s_pool[h * 128 + m] = a;
+            __syncthreads();
+            if (tid < 128) s_pool[tid] = (s_pool[tid] + s_pool[128 + tid]) / static_cast<double>(T);
+            __syncthreads();
+            if (tid < p.n_mfcc) {
+                double d = 0.0;
+                for (int q = 0; q < kMels; ++q) d = fma(tb.dctT[q * kMels + tid], s_pool[q], d);
+                out[tid] = static_cast<float>(d);
+            }
+        }
+
+        // ===================================== phase 3b: chroma ====================================
+        {
+            const float* W = tb.chroma + static_cast<size_t>(tuning_idx) * kChroma * kPStride;
+            double cacc[kChroma];
+#pragma unroll
+            for (int c = 0; c < kChroma; ++c) cacc[c] = 0.0;
+            const int ntiles = (T + 7) >> 3;
+            for (int tile = warp; tile < ntiles; tile += kWarps) {
+                const int t0 = tile * 8;
+                const int nf = min(8, T - t0);
+                const float* Pt = gP + static_cast<size_t>(t0) * kPStride;
+                float acc[96];
+#pragma unroll
+                for (int i = 0; i < 96; ++i) acc[i] = 0.0f;
+                for (int j = 0; j < 33; ++j) {
+                    const int k = lane + 32 * j;
+                    const bool ok = (j < 32) || (lane == 0);
+                    float w[kChroma], pv[8];
+#pragma unroll
+                    for (int c = 0; c < kChroma; ++c) w[c] = ok ? __ldg(W + c * kPStride + k) : 0.0f;
+#pragma unroll
+                    for (int f = 0; f < 8; ++f) pv[f] = (ok && f < nf) ? Pt[f * kPStride + k] : 0.0f;
+#pragma unroll
+                    for (int f = 0; f < 8; ++f)
+#pragma unroll
+                        for (int c = 0; c < kChroma; ++c) acc[f * kChroma + c] = fmaf(w[c], pv[f], acc[f * kChroma + c]);
+                }
+                // lane l ends up with the warp totals of acc[l], acc[32+l], acc[64+l]
+                float* red = Pb;       // 96 floats of this warp's tile
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = acc[32 * g + i];
+                    red[32 * g + lane] = reduce_scatter32(v, lane);
+                }
+                __syncwarp();
+                if (lane < nf) {
+                    float raw[kChroma];
+                    float mx = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < kChroma; ++c) { raw[c] = red[lane * kChroma + c]; mx = fmaxf(mx, fabsf(raw[c])); }
+                    if (mx < FLT_MIN) mx = 1.0f;
+#pragma unroll
+                    for (int c = 0; c < kChroma; ++c) cacc[c] += static_cast<double>(__fdiv_rn(raw[c], mx));
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int c = 0; c < kChroma; ++c) {
+                double v = (lane < 8) ? cacc[c] : 0.0;
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                if (lane == 0) s_wacc[warp * 16 + 3 + c] = v;
+            }
+        }
+        __syncthreads();
+
+        // ===================================== epilogue: pooled row ================================
+        if (tid < 16) {
+            const double invT = 1.0 / static_cast<double>(T);
+            if (tid < kChroma) {
+                double v = 0.0;
+                for (int w = 0; w < kWarps; ++w) v += s_wacc[w * 16 + 3 + tid];
+                out[p.n_mfcc + tid] = static_cast<float>(v * invT);
+            } else if (tid == 12) {
+                long long z = 0;
+                for (int w = 0; w < kWarps; ++w) z += s_i[8 + w];
+                out[p.n_mfcc + 12] = static_cast<float>(static_cast<double>(z) / (static_cast<double>(kNfft) * T));
+            } else {
+                double v = 0.0;
+                for (int w = 0; w < kWarps; ++w) v += s_wacc[w * 16 + (tid - 13)];
+                out[p.n_mfcc + tid] = static_cast<float>(v * invT);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t smem_bytes() {
+    return sizeof(float2) * 3072 + sizeof(float) * kWarps * kExFloats + sizeof(double) * (256 + kWarps * 16) +
+           sizeof(int) * (256 + 32) + sizeof(float) * 32;
+}
+
+cudaError_t configure_kernels(int* blocks_per_sm) {
+    const int smem = static_cast<int>(smem_bytes());
+    cudaError_t e = cudaFuncSetAttribute(sfx_extract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sfx_extract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, sfx_extract_kernel<false>, kThreads, smem);
+}
+
+cudaError_t launch_extract(const Params& p, int grid, bool debug, cudaStream_t stream) {
+    const size_t smem = smem_bytes();
+    if (debug) sfx_extract_kernel<true><<<grid, kThreads, smem, stream>>>(p);
+    else       sfx_extract_kernel<false><<<grid, kThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace sfx

@@ -1,0 +1,92 @@
+"""ctypes binding of libsfx_b200.so -- one Python function per entry point of include/sfx.h."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+
+class SfxError(RuntimeError):
+    """A libsfx_b200 call returned a negative status."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libsfx_b200 error {code}: {msg}")
+        self.code = code
+
+
+class TablesHost(C.Structure):
+    _fields_ = [("sr", C.c_int32), ("pip_kmin", C.c_int32), ("pip_kmax", C.c_int32), ("mel_rows", C.c_int32),
+                ("hann", C.c_void_p), ("tw1", C.c_void_p), ("tw2", C.c_void_p), ("melw", C.c_void_p),
+                ("mel_lo", C.c_void_p), ("mel_off", C.c_void_p), ("mel_len", C.c_void_p),
+                ("chroma", C.c_void_p), ("dct", C.c_void_p), ("edges", C.c_void_p)]
+
+
+class DebugOut(C.Structure):
+    _fields_ = [("P", C.c_void_p), ("logmel", C.c_void_p), ("frame_feat", C.c_void_p),
+                ("clip_info", C.c_void_p), ("T_dbg", C.c_int32)]
+
+
+EXPORTS = ["sfx_abi_version", "sfx_last_error", "sfx_device_count", "sfx_init_tables", "sfx_workspace_bytes",
+           "sfx_launches_per_extract", "sfx_extract", "sfx_extract_debug", "sfx_extract_host", "sfx_release"]
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the .so is missing and nvcc exists).  Raises if it cannot: no fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_build.LIB_PATH):
+        _build.build()
+    lib = C.CDLL(_build.LIB_PATH)
+    lib.sfx_abi_version.restype = C.c_int
+    lib.sfx_last_error.restype = C.c_char_p
+    lib.sfx_device_count.restype = C.c_int
+    lib.sfx_launches_per_extract.restype = C.c_int
+    lib.sfx_init_tables.restype = C.c_int
+    lib.sfx_init_tables.argtypes = [C.c_int, C.POINTER(TablesHost)]
+    lib.sfx_workspace_bytes.restype = C.c_size_t
+    lib.sfx_workspace_bytes.argtypes = [C.c_int, C.c_int64]
+    common = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+              C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.sfx_extract.restype = C.c_int
+    lib.sfx_extract.argtypes = common
+    lib.sfx_extract_debug.restype = C.c_int
+    lib.sfx_extract_debug.argtypes = common + [C.POINTER(DebugOut)]
+    lib.sfx_extract_host.restype = C.c_int
+    lib.sfx_extract_host.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_int64, C.c_int32]
+    lib.sfx_release.restype = C.c_int
+    lib.sfx_release.argtypes = [C.c_int]
+    if lib.sfx_abi_version() != 1:
+        raise RuntimeError("libsfx_b200.so ABI version mismatch; rebuild with sfx_b200.build.build(force=True)")
+    _LIB = lib
+    return lib
+
+
+def check(rc: int):
+    if rc < 0:
+        raise SfxError(rc, load().sfx_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def make_tables_struct(tb: dict):
+    """TablesHost pointing into the numpy arrays of tables.build_tables (keeps them alive via .keep)."""
+    keep = {k: np.ascontiguousarray(tb[k]) for k in
+            ("hann", "tw1", "tw2", "melw", "mel_lo", "mel_off", "mel_len", "chroma", "dct", "edges")}
+    assert keep["hann"].dtype == np.float32 and keep["chroma"].dtype == np.float32
+    assert keep["dct"].dtype == np.float64 and keep["edges"].dtype == np.float64
+    assert keep["mel_lo"].dtype == np.int32 and keep["mel_off"].dtype == np.int32 and keep["mel_len"].dtype == np.int32
+    t = TablesHost(sr=int(tb["sr"]), pip_kmin=int(tb["pip_kmin"]), pip_kmax=int(tb["pip_kmax"]),
+                   mel_rows=int(keep["melw"].shape[0]),
+                   **{k: v.ctypes.data for k, v in keep.items()})
+    t.keep = keep
+    return t

@@ -1,0 +1,163 @@
+"""Batched, device-resident speech feature extraction (host side of libsfx_b200).
+
+``SpeechFeatureExtractor`` hands PyTorch CUDA tensors (device pointers + the current stream) to the C ABI
+of include/sfx.h.  PyTorch is used for device memory, streams and torch.distributed only; all arithmetic
+runs in csrc/sfx_kernels.cu.  There is no CPU path: constructing an extractor without a CUDA device raises.
+
+Output layout per clip (reference preprocessing/audio_preprocessing.py:45-46):
+    [mfcc_0..n_mfcc-1 | chroma C, C#, ..., B | zcr, spectral_centroid_Hz, spectral_rolloff_Hz, rms]
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib, tables
+
+N_CHROMA = 12
+N_SPECTRAL = 4
+
+_EXTRACTORS: dict = {}
+_LOCK = threading.Lock()
+
+
+class NoCudaDeviceError(RuntimeError):
+    """Raised instead of falling back to a CPU implementation."""
+
+
+class SpeechFeatureExtractor:
+    """One instance per (device, sample rate): owns the uploaded tables and a growable workspace."""
+
+    def __init__(self, device=None, sr: int = 22050):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available() or self.lib.sfx_device_count() <= 0:
+            raise NoCudaDeviceError("sfx_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise NoCudaDeviceError(f"sfx_b200 runs on CUDA devices only, got {self.device}")
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.sr = int(sr)
+        self._tables = _lib.make_tables_struct(tables.build_tables(self.sr))
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.sfx_init_tables(self.index, C.byref(self._tables)))
+        self._ws = None
+        self._ws_samples = 0
+        self.launches = 0
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, max_samples: int) -> torch.Tensor:
+        if self._ws is None or max_samples > self._ws_samples:
+            nbytes = self.lib.sfx_workspace_bytes(self.index, int(max_samples))
+            if nbytes == 0:
+                raise _lib.SfxError(-1, self.lib.sfx_last_error().decode())
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws_samples = int(max_samples)
+        return self._ws
+
+    # ------------------------------------------------------------------ device path
+    def extract(self, waves: torch.Tensor, lengths: torch.Tensor | None = None, n_samples: int | None = None,
+                n_mfcc: int = 40, out: torch.Tensor | None = None, debug: dict | None = None) -> torch.Tensor:
+        """waves: cuda float32 [B, L] (row-contiguous); lengths: cuda int32 [B] or None; n_samples: common clip
+        length when lengths is None (default L; smaller = the pad/trim of load_audio).  Returns cuda float32
+        [B, n_mfcc+16].  Stream-ordered on torch's current stream; no host sync."""
+        if waves.device != self.device or waves.dtype != torch.float32 or waves.dim() != 2:
+            raise ValueError("waves must be a 2-D float32 tensor on the extractor's device")
+        if waves.stride(1) != 1:
+            raise ValueError("waves rows must be contiguous")
+        B, L = waves.shape
+        n_default = L if n_samples is None else int(n_samples)
+        if lengths is not None:
+            if lengths.device != self.device or lengths.dtype != torch.int32 or lengths.shape != (B,):
+                raise ValueError("lengths must be int32 [B] on the extractor's device")
+            lengths = lengths.contiguous()
+            max_samples = L
+        else:
+            if not 1 <= n_default <= L:
+                raise ValueError("n_samples must be in [1, L]")
+            max_samples = n_default
+        width = n_mfcc + N_CHROMA + N_SPECTRAL
+        if out is None:
+            out = torch.empty((B, width), dtype=torch.float32, device=self.device)
+        elif out.shape != (B, width) or out.dtype != torch.float32 or out.device != self.device or out.stride(1) != 1:
+            raise ValueError("out must be float32 [B, n_mfcc+16] on the extractor's device")
+        if B == 0:
+            return out
+        ws = self._workspace(max_samples)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        args = (self.index, waves.data_ptr(), waves.stride(0), lengths.data_ptr() if lengths is not None else None,
+                n_default, max_samples, B, n_mfcc, out.data_ptr(), out.stride(0), ws.data_ptr(), ws.numel(),
+                C.c_void_p(stream))
+        with torch.cuda.device(self.index):
+            if debug is None:
+                _lib.check(self.lib.sfx_extract(*args))
+            else:
+                T = 1 + max_samples // tables.HOP
+                debug["P"] = torch.zeros((B, T, tables.P_STRIDE), dtype=torch.float32, device=self.device)
+                debug["logmel"] = torch.zeros((B, T, tables.N_MELS), dtype=torch.float32, device=self.device)
+                debug["frame_feat"] = torch.zeros((B, T, 4), dtype=torch.float32, device=self.device)
+                debug["clip_info"] = torch.zeros((B, 8), dtype=torch.float32, device=self.device)
+                d = _lib.DebugOut(P=debug["P"].data_ptr(), logmel=debug["logmel"].data_ptr(),
+                                  frame_feat=debug["frame_feat"].data_ptr(), clip_info=debug["clip_info"].data_ptr(),
+                                  T_dbg=T)
+                _lib.check(self.lib.sfx_extract_debug(*args, C.byref(d)))
+        self.launches += self.lib.sfx_launches_per_extract()
+        return out
+
+    # ------------------------------------------------------------------ host path (the reference-facing one)
+    def extract_host(self, waves: np.ndarray, lengths: np.ndarray | None = None, n_samples: int | None = None,
+                     n_mfcc: int = 40, out: np.ndarray | None = None, chunk_clips: int = 0) -> np.ndarray:
+        """waves: host float32 [B, L] (numpy, or anything exposing a C-contiguous-row buffer; pinned memory is
+        copied without staging); returns host float32 [B, n_mfcc+16].  H2D, kernel and D2H are chunk-pipelined
+        inside the C library; the call returns when the rows are in ``out``."""
+        waves = np.asarray(waves)
+        if waves.dtype != np.float32 or waves.ndim != 2 or waves.strides[1] != 4:
+            raise ValueError("waves must be a 2-D float32 array with contiguous rows")
+        B, L = waves.shape
+        n_default = L if n_samples is None else int(n_samples)
+        width = n_mfcc + N_CHROMA + N_SPECTRAL
+        if out is None:
+            out = np.empty((B, width), dtype=np.float32)
+        if out.shape != (B, width) or out.dtype != np.float32 or out.strides[1] != 4:
+            raise ValueError("out must be float32 [B, n_mfcc+16]")
+        lp = None
+        if lengths is not None:
+            lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+            if lengths.shape != (B,):
+                raise ValueError("lengths must have shape [B]")
+            lp = lengths.ctypes.data
+        if B == 0:
+            return out
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.sfx_extract_host(self.index, waves.ctypes.data, waves.strides[0] // 4, lp, n_default,
+                                                 B, n_mfcc, out.ctypes.data, out.strides[0] // 4, int(chunk_clips)))
+        nchunk = 1 if chunk_clips <= 0 else -(-B // chunk_clips)
+        self.launches += nchunk * self.lib.sfx_launches_per_extract()
+        return out
+
+
+def get_extractor(device=None, sr: int = 22050) -> SpeechFeatureExtractor:
+    """Process-wide cache: one extractor per (device index, sr)."""
+    if not torch.cuda.is_available():
+        raise NoCudaDeviceError("sfx_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    key = (idx, int(sr))
+    with _LOCK:
+        ex = _EXTRACTORS.get(key)
+        if ex is None:
+            ex = _EXTRACTORS[key] = SpeechFeatureExtractor(torch.device("cuda", idx), sr)
+    return ex
+
+
+def extract_features_batch(waveforms, lengths=None, sr: int = 22050, n_mfcc: int = 40, n_samples=None):
+    """Batched entry point: cuda float32 [B, L] (+ int32 lengths) -> cuda float32 [B, n_mfcc+16];
+    host numpy float32 [B, L] -> host numpy [B, n_mfcc+16] through the chunk-pipelined host path."""
+    if isinstance(waveforms, torch.Tensor) and waveforms.is_cuda:
+        ex = get_extractor(waveforms.device, sr)
+        return ex.extract(waveforms, lengths, n_samples=n_samples, n_mfcc=n_mfcc)
+    if isinstance(waveforms, torch.Tensor):
+        waveforms = waveforms.numpy()
+    ex = get_extractor(None, sr)
+    return ex.extract_host(np.asarray(waveforms, dtype=np.float32), lengths, n_samples=n_samples, n_mfcc=n_mfcc)

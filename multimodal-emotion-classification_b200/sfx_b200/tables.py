@@ -1,0 +1,145 @@
+"""Host-side constant tables for the sm_100a speech feature extractor.
+
+Everything is generated in float64 with numpy and rounded once to the dtype the kernels read, so the
+filterbanks are the same numbers librosa 0.10.0 builds for the reference's calls
+(audio_preprocessing.py:23 ``feature.mfcc``, :28 ``feature.chroma_stft``): ``filters.mel`` (Slaney,
+128 bands, norm='slaney'), ``filters.chroma`` for each of the 100 tunings ``estimate_tuning`` can return,
+the ortho DCT-II matrix of ``scipy.fftpack.dct``, the periodic Hann window of ``scipy.signal.get_window``,
+and the histogram edges of ``pitch_tuning``.  FFT twiddles are cos/sin evaluated in float64.
+
+Layouts are chosen for the kernels (see DESIGN.md "HBM / SMEM layout"), not for readability:
+  hann   float32[2048]        (w[2m], w[2m+1]) pairs, read as float2[1024]
+  tw1    float32[32][32][2]   tw1[k1][lane] = exp(-2*pi*i*lane*k1/1024)      (inter-stage twiddle)
+  tw2    float32[32][32][2]   tw2[k2][lane] = 0.5*(cos, sin)(2*pi*(lane+32*k2)/2048)  (real-FFT unpack)
+  melw   float32[mel_rows][32] transposed/padded sparse mel weights: slot s (=filter//32), position i,
+                              lane (=filter%32); mel_lo[128] first bin; mel_off[4], mel_len[4]
+  chroma float32[100][12][1056] one bank per tuning edge, bin axis zero-padded to 1056
+  dct    float64[128][128]    rows k of the ortho DCT-II
+  edges  float64[101]         np.linspace(-0.5, 0.5, 101)
+"""
+from __future__ import annotations
+
+import functools
+import numpy as np
+
+N_FFT = 2048
+HOP = 512
+N_BINS = 1025
+N_MELS = 128
+N_CHROMA = 12
+N_TUNINGS = 100
+P_STRIDE = 1056          # padded bin row (33 * 32)
+
+
+def _hz_to_mel(f):
+    f = np.asarray(f, dtype=np.float64)
+    f_sp = 200.0 / 3
+    logstep = np.log(6.4) / 27.0
+    lin = f / f_sp
+    with np.errstate(divide="ignore"):
+        log = 1000.0 / f_sp + np.log(np.maximum(f, 1e-300) / 1000.0) / logstep
+    return np.where(f >= 1000.0, log, lin)
+
+
+def _mel_to_hz(m):
+    m = np.asarray(m, dtype=np.float64)
+    f_sp = 200.0 / 3
+    logstep = np.log(6.4) / 27.0
+    min_log_mel = 1000.0 / f_sp
+    return np.where(m >= min_log_mel, 1000.0 * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def mel_bank(sr: int) -> np.ndarray:
+    """Dense [128, 1025] float32 Slaney mel bank (librosa.filters.mel defaults used by feature.mfcc)."""
+    fftfreqs = np.fft.rfftfreq(N_FFT, 1.0 / sr)
+    edges_hz = _mel_to_hz(np.linspace(_hz_to_mel(0.0), _hz_to_mel(sr / 2.0), N_MELS + 2))
+    width = np.diff(edges_hz)
+    ramps = edges_hz[:, None] - fftfreqs[None, :]
+    tri = np.maximum(0.0, np.minimum(-ramps[:-2] / width[:-1, None], ramps[2:] / width[1:, None]))
+    tri = tri.astype(np.float32)                      # librosa stores the triangle in float32 first
+    enorm = 2.0 / (edges_hz[2:] - edges_hz[:-2])
+    return (tri.astype(np.float64) * enorm[:, None]).astype(np.float32)
+
+
+def chroma_bank(sr: int, tuning: float) -> np.ndarray:
+    """Dense [12, 1025] float32 chroma bank (librosa.filters.chroma: ctroct=5, octwidth=2, norm=2, base_c)."""
+    freqs = np.linspace(0, sr, N_FFT, endpoint=False)[1:]
+    a440 = 440.0 * 2.0 ** (tuning / N_CHROMA)
+    frq = N_CHROMA * np.log2(freqs / (float(a440) / 16))
+    frq = np.concatenate(([frq[0] - 1.5 * N_CHROMA], frq))
+    bw = np.concatenate((np.maximum(frq[1:] - frq[:-1], 1.0), [1]))
+    D = np.subtract.outer(frq, np.arange(0, N_CHROMA, dtype="d")).T
+    half = np.round(float(N_CHROMA) / 2)
+    D = np.remainder(D + half + 10 * N_CHROMA, N_CHROMA) - half
+    w = np.exp(-0.5 * (2 * D / np.tile(bw, (N_CHROMA, 1))) ** 2)
+    length = np.sum(np.abs(w) ** 2, axis=0, keepdims=True) ** 0.5
+    length[length < np.finfo(np.float64).tiny] = 1.0
+    w = w / length
+    w *= np.tile(np.exp(-0.5 * (((frq / N_CHROMA - 5.0) / 2) ** 2)), (N_CHROMA, 1))
+    w = np.roll(w, -3 * (N_CHROMA // 12), axis=0)
+    return np.ascontiguousarray(w[:, :N_BINS], dtype=np.float32)
+
+
+def tuning_edges() -> np.ndarray:
+    return np.linspace(-0.5, 0.5, N_TUNINGS + 1)
+
+
+def dct_matrix() -> np.ndarray:
+    """[128,128] float64: row k of scipy.fftpack.dct(type=2, norm='ortho') over 128 mel bands."""
+    m = np.arange(N_MELS, dtype=np.float64)
+    k = np.arange(N_MELS, dtype=np.float64)[:, None]
+    d = np.cos(np.pi * k * (2.0 * m + 1.0) / (2.0 * N_MELS)) * np.sqrt(2.0 / N_MELS)
+    d[0] = 1.0 / np.sqrt(N_MELS)
+    return np.ascontiguousarray(d)
+
+
+def piptrack_bin_range(sr: int, fmin: float = 150.0, fmax: float = 4000.0):
+    """First/last rFFT bin with fmin <= f < min(fmax, sr/2) (librosa.piptrack freq_mask)."""
+    f = np.fft.rfftfreq(N_FFT, 1.0 / sr)
+    idx = np.nonzero((max(fmin, 0) <= f) & (f < min(fmax, sr / 2.0)))[0]
+    return int(idx[0]), int(idx[-1])
+
+
+def mel_sparse_layout(bank: np.ndarray):
+    """Transposed, slot-padded sparse layout of the mel bank for lane-parallel gathers.
+
+    Filter m is owned by lane m % 32 in slot m // 32; slot s is padded to the longest support in the
+    slot so that weight reads are lane-consecutive: melw[(off[s] + i) * 32 + lane].
+    """
+    lo = np.zeros(N_MELS, dtype=np.int32)
+    cnt = np.zeros(N_MELS, dtype=np.int32)
+    for m in range(N_MELS):
+        nz = np.nonzero(bank[m])[0]
+        if nz.size:
+            lo[m], cnt[m] = nz[0], nz[-1] - nz[0] + 1
+    slot_len = np.array([cnt[32 * s:32 * s + 32].max() for s in range(4)], dtype=np.int32)
+    slot_off = np.concatenate(([0], np.cumsum(slot_len)[:-1])).astype(np.int32)
+    rows = int(slot_len.sum())
+    w = np.zeros((rows, 32), dtype=np.float32)
+    for m in range(N_MELS):
+        s, lane = divmod(m, 32)
+        for i in range(cnt[m]):
+            w[slot_off[s] + i, lane] = bank[m, lo[m] + i]
+    return w, lo, slot_off, slot_len
+
+
+@functools.lru_cache(maxsize=4)
+def build_tables(sr: int = 22050) -> dict:
+    n = np.arange(N_FFT, dtype=np.float64)
+    hann = (0.5 - 0.5 * np.cos(2.0 * np.pi * n / N_FFT)).astype(np.float32)
+    lane = np.arange(32, dtype=np.float64)[None, :]
+    k = np.arange(32, dtype=np.float64)[:, None]
+    a1 = 2.0 * np.pi * lane * k / 1024.0
+    tw1 = np.stack([np.cos(a1), -np.sin(a1)], axis=-1).astype(np.float32)
+    a2 = 2.0 * np.pi * (lane + 32.0 * k) / 2048.0
+    tw2 = np.stack([0.5 * np.cos(a2), 0.5 * np.sin(a2)], axis=-1).astype(np.float32)
+    mb = mel_bank(sr)
+    melw, mel_lo, mel_off, mel_len = mel_sparse_layout(mb)
+    edges = tuning_edges()
+    chroma = np.zeros((N_TUNINGS, N_CHROMA, P_STRIDE), dtype=np.float32)
+    for i in range(N_TUNINGS):
+        chroma[i, :, :N_BINS] = chroma_bank(sr, float(edges[i]))
+    kmin, kmax = piptrack_bin_range(sr)
+    return dict(sr=sr, hann=hann, tw1=np.ascontiguousarray(tw1), tw2=np.ascontiguousarray(tw2),
+                mel_dense=mb, melw=melw, mel_lo=mel_lo, mel_off=mel_off, mel_len=mel_len,
+                chroma=chroma, dct=dct_matrix(), edges=edges, pip_kmin=kmin, pip_kmax=kmax)
