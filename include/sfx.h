@@ -52,14 +52,14 @@ typedef struct {
     int32_t       sr;            /* sample rate the banks were built for (reference config.py:57) */
     int32_t       pip_kmin;      /* first/last rFFT bin with 150 Hz <= f < 4000 Hz (librosa.piptrack) */
     int32_t       pip_kmax;
-    int32_t       mel_rows;      /* rows of melw */
+    int32_t       mel_ps;        /* row stride of the per-lane mel partial-sum slots (odd, <= 31) */
+    int32_t       mel_flush32;   /* 1 if the Slaney interval index advances at the Nyquist bin */
     const float  *hann;          /* [2048] */
     const float  *tw1;           /* [32][32][2] */
     const float  *tw2;           /* [32][32][2] */
-    const float  *melw;          /* [mel_rows][32] */
-    const int32_t*mel_lo;        /* [128] */
-    const int32_t*mel_off;       /* [4] */
-    const int32_t*mel_len;       /* [4] */
+    const float  *mel_ab;        /* [33][32][2] (falling, rising) weights of bin 32*lane + j at [j][lane] */
+    const uint32_t*mel_mask;     /* [32] bit j: interval index advances at bin 32*lane + j */
+    const int32_t*mel_src;       /* [128][3] partial-sum slots of each filter (32*mel_ps = zero slot) */
     const float  *chroma;        /* [100][12][1056] */
     const double *dct;           /* [128][128] */
     const double *edges;         /* [101] */

@@ -141,9 +141,11 @@ int sfx_release(int device) {
 
 int sfx_init_tables(int device, const sfx_tables_host* t) {
     if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
-    if (!t || !t->hann || !t->tw1 || !t->tw2 || !t->melw || !t->mel_lo || !t->mel_off || !t->mel_len || !t->chroma ||
-        !t->dct || !t->edges || t->mel_rows <= 0 || t->sr <= 0)
+    if (!t || !t->hann || !t->tw1 || !t->tw2 || !t->mel_ab || !t->mel_mask || !t->mel_src || !t->chroma || !t->dct ||
+        !t->edges || t->sr <= 0)
         return fail(SFX_ERR_ARG, "null table pointer or bad sizes");
+    if (t->mel_ps < 3 || (t->mel_ps & 1) == 0 || sfx::kPartOff + 32 * t->mel_ps + 1 > sfx::kExFloats)
+        return fail(SFX_ERR_ARG, "mel_ps must be odd and fit the warp tile");
     if (t->pip_kmin < 1 || t->pip_kmax > sfx::kBins - 2 || t->pip_kmax < t->pip_kmin)
         return fail(SFX_ERR_ARG, "piptrack bin range outside [1,1023]");
     if ((t->pip_kmax - t->pip_kmin + 2) / 2 > sfx::kMaxPk) return fail(SFX_ERR_ARG, "piptrack range exceeds peak capacity");
@@ -166,15 +168,17 @@ int sfx_init_tables(int device, const sfx_tables_host* t) {
     c.tb.tw1 = reinterpret_cast<const float2*>(f);
     if ((rc = upload(c, t->tw2, 2048, &f))) return rc;
     c.tb.tw2 = reinterpret_cast<const float2*>(f);
-    if ((rc = upload(c, t->melw, static_cast<size_t>(t->mel_rows) * 32, &c.tb.melw))) return rc;
-    if ((rc = upload(c, t->mel_lo, 128, &c.tb.mel_lo))) return rc;
+    if ((rc = upload(c, t->mel_ab, 33 * 32 * 2, &f))) return rc;
+    c.tb.mel_ab = reinterpret_cast<const float2*>(f);
+    if ((rc = upload(c, t->mel_mask, 32, &c.tb.mel_mask))) return rc;
+    if ((rc = upload(c, t->mel_src, 128 * 3, &c.tb.mel_src))) return rc;
     if ((rc = upload(c, t->chroma, static_cast<size_t>(sfx::kTunings) * sfx::kChroma * sfx::kPStride, &c.tb.chroma))) return rc;
     std::vector<double> dctT(static_cast<size_t>(sfx::kMels) * sfx::kMels);
     for (int k = 0; k < sfx::kMels; ++k)
         for (int m = 0; m < sfx::kMels; ++m) dctT[static_cast<size_t>(m) * sfx::kMels + k] = t->dct[static_cast<size_t>(k) * sfx::kMels + m];
     if ((rc = upload(c, dctT.data(), dctT.size(), &c.tb.dctT))) return rc;
     if ((rc = upload(c, t->edges, sfx::kTunings + 1, &c.tb.edges))) return rc;
-    for (int s = 0; s < 4; ++s) { c.tb.mel_off[s] = t->mel_off[s]; c.tb.mel_len[s] = t->mel_len[s]; }
+    c.tb.mel_ps = t->mel_ps; c.tb.mel_flush32 = t->mel_flush32;
     c.tb.sr = t->sr; c.tb.kmin = t->pip_kmin; c.tb.kmax = t->pip_kmax;
     CK(sfx::configure_kernels(&c.blocks_per_sm));
     if (c.blocks_per_sm < 1) return fail(SFX_ERR_CUDA, "kernel does not fit on an SM");

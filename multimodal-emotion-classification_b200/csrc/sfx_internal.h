@@ -19,16 +19,18 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kExFloats = 32 * 33 * 2;   // per-warp float2[32][33] exchange tile, reused as the padded |X|^2 tile
 constexpr int kMaxPk = 180;              // piptrack peaks per frame: local maxima among <= 358 bins
+constexpr int kPartOff = 1088;           // offset of the mel partial-sum slots inside a warp's tile
+constexpr int kKeyCap = 16384;           // peak keys kept in shared memory during the median select
 constexpr size_t kWsHeader = 256;        // clip-queue counter lives in the first bytes of the workspace
 
 struct DevTables {
     const float2* hann;     // [1024]
     const float2* tw1;      // [32][32]
     const float2* tw2;      // [32][32]
-    const float* melw;      // [mel_rows][32]
-    const int* mel_lo;      // [128]
-    int mel_off[4];
-    int mel_len[4];
+    const float2* mel_ab;   // [33][32]
+    const unsigned* mel_mask;   // [32]
+    const int* mel_src;     // [128][3]
+    int mel_ps, mel_flush32;
     const float* chroma;    // [100][12][1056]
     const double* dctT;     // [128 mel][128 k]  (transposed: coalesced over k)
     const double* edges;    // [101]
@@ -54,7 +56,8 @@ struct Params {
 
 // bytes of scratch one CTA needs for clips of up to Tmax frames (multiple of 256)
 inline size_t cta_scratch_bytes(int Tmax) {
-    size_t b = static_cast<size_t>(Tmax) * (kPStride * 4 + kMels * 4 + kMaxPk * 8);
+    // |X|^2 rows, log-mel rows, peak records (float4), peak keys (u32, overflow path), peak bins (u8)
+    size_t b = static_cast<size_t>(Tmax) * (kPStride * 4 + kMels * 4 + kMaxPk * (16 + 4 + 1));
     return (b + 255) & ~static_cast<size_t>(255);
 }
 

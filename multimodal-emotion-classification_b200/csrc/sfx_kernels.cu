@@ -138,7 +138,7 @@ __device__ __forceinline__ int pidx(int k) { return k + (k >> 5); }   // padded 
 // ------------------------------------------------------------------------------------------------
 // CTA-wide radix select over the clip's peak magnitudes: key of the element of ascending rank r.
 // count_le = number of elements <= that key.  All threads must call; uses s_hist[256], s_sel[4].
-__device__ unsigned radix_select(const float* mags, int np, int r, int* s_hist, int* s_sel, int& count_le) {
+__device__ unsigned radix_select(const unsigned* keys, int np, int r, int* s_hist, int* s_sel, int& count_le) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned prefix = 0, mask = 0;
     int less = 0, equal = 0;
@@ -147,7 +147,7 @@ __device__ unsigned radix_select(const float* mags, int np, int r, int* s_hist, 
         for (int i = tid; i < 256; i += kThreads) s_hist[i] = 0;
         __syncthreads();
         for (int i = tid; i < np; i += kThreads) {
-            const unsigned key = fkey(mags[i]);
+            const unsigned key = keys[i];
             if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255], 1);
         }
         __syncthreads();
@@ -166,7 +166,7 @@ __device__ unsigned radix_select(const float* mags, int np, int r, int* s_hist, 
             const unsigned bal = __ballot_sync(0xffffffffu, inc > r);
             const int L = __ffs(bal) - 1;
             if (lane == L) {
-                int rr = r - exc, cum = 0, q = 0, sel = 0, eq = 0;
+                int rr = r - exc, cum = 0, sel = 0, eq = 0;
                 bool done = false;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -175,7 +175,6 @@ __device__ unsigned radix_select(const float* mags, int np, int r, int* s_hist, 
                         else cum += loc[u];
                     }
                 }
-                (void)q;
                 s_sel[0] = lane * 8 + sel;
                 s_sel[1] = rr - cum;
                 s_sel[2] = exc + cum;
@@ -209,6 +208,44 @@ __device__ __forceinline__ float reduce_scatter32(float (&v)[32], int lane) {
     }
     return v[0];
 }
+// 16 per-lane values: lanes l and l^16 both end with the warp total of v[l & 15]
+__device__ __forceinline__ float reduce_scatter16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float send = up ? v[i] : v[i + h];
+            const float keep = up ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    return v[0];
+}
+
+// raw samples of STFT frame t (zero padded) -> re[m1] = x[2m], im[m1] = x[2m+1], m = 32*m1 + lane
+__device__ __forceinline__ void load_frame(const float* __restrict__ x, long long n, int t, int lane, bool aligned8,
+                                           float (&re)[32], float (&im)[32]) {
+    const long long s0 = static_cast<long long>(kHop) * t - kNfft / 2;
+    if (s0 >= 0 && s0 + kNfft <= n && aligned8) {
+        const float2* src = reinterpret_cast<const float2*>(x + s0) + lane;
+#pragma unroll
+        for (int m1 = 0; m1 < 32; ++m1) {
+            const float2 v = __ldg(src + 32 * m1);
+            re[m1] = v.x;
+            im[m1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int m1 = 0; m1 < 32; ++m1) {
+            const long long g = s0 + 2 * (32 * m1 + lane);
+            re[m1] = (g >= 0 && g < n) ? __ldg(x + g) : 0.0f;
+            im[m1] = (g + 1 >= 0 && g + 1 < n) ? __ldg(x + g + 1) : 0.0f;
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 template <bool kDebug>
@@ -217,10 +254,12 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     float2* s_hann = reinterpret_cast<float2*>(smem_raw);
     float2* s_tw1 = s_hann + 1024;
     float2* s_tw2 = s_tw1 + 1024;
-    float* s_ex = reinterpret_cast<float*>(s_tw2 + 1024);
+    float2* s_melab = s_tw2 + 1024;                                          // [33*32]
+    float* s_ex = reinterpret_cast<float*>(s_melab + 33 * 32);               // [kWarps][kExFloats]
     double* s_pool = reinterpret_cast<double*>(s_ex + kWarps * kExFloats);   // [256]
     double* s_wacc = s_pool + 256;                                           // [kWarps][16]
-    int* s_hist = reinterpret_cast<int*>(s_wacc + kWarps * 16);              // [256]
+    double* s_edges = s_wacc + kWarps * 16;                                  // [104]
+    int* s_hist = reinterpret_cast<int*>(s_edges + 104);                     // [256]
     int* s_i = s_hist + 256;                                                 // [32]
     float* s_f = reinterpret_cast<float*>(s_i + 32);                         // [32]
 
@@ -232,21 +271,31 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         s_tw1[i] = tb.tw1[i];
         s_tw2[i] = tb.tw2[i];
     }
-    int mlo[4];
+    for (int i = tid; i < 33 * 32; i += kThreads) s_melab[i] = tb.mel_ab[i];
+    for (int i = tid; i <= kTunings; i += kThreads) s_edges[i] = tb.edges[i];
+    const unsigned mel_mask = tb.mel_mask[lane];
+    const int mel_ps = tb.mel_ps;
+    int msrc[4];                                   // 3 x 10-bit partial-sum slots per filter 32*s + lane
 #pragma unroll
-    for (int s = 0; s < 4; ++s) mlo[s] = tb.mel_lo[32 * s + lane];
+    for (int s = 0; s < 4; ++s) {
+        const int* q = tb.mel_src + (32 * s + lane) * 3;
+        msrc[s] = q[0] | (q[1] << 10) | (q[2] << 20);
+    }
 
     // scratch slice of this CTA
     unsigned char* slice = p.ws + kWsHeader + static_cast<size_t>(blockIdx.x) * p.cta_scratch_bytes;
     float* gP = reinterpret_cast<float*>(slice);
     float* gL = gP + static_cast<size_t>(p.Tmax) * kPStride;
-    float* gMag = gL + static_cast<size_t>(p.Tmax) * kMels;
-    int* gBin = reinterpret_cast<int*>(gMag + static_cast<size_t>(p.Tmax) * kMaxPk);
+    float4* gRec = reinterpret_cast<float4*>(gL + static_cast<size_t>(p.Tmax) * kMels);
+    unsigned* gKey = reinterpret_cast<unsigned*>(gRec + static_cast<size_t>(p.Tmax) * kMaxPk);
+    unsigned char* gBin = reinterpret_cast<unsigned char*>(gKey + static_cast<size_t>(p.Tmax) * kMaxPk);
     int* counter = reinterpret_cast<int*>(p.ws);
 
-    float* Pb = s_ex + warp * kExFloats;               // this warp's exchange / P tile
+    float* Pb = s_ex + warp * kExFloats;               // this warp's exchange / |X|^2 tile
     float2* ex = reinterpret_cast<float2*>(Pb);
+    float* part = Pb + kPartOff;                       // mel partial sums [32][mel_ps] + zero slot
     const float bin_hz = static_cast<float>(static_cast<double>(tb.sr) / kNfft);
+    const bool aligned8 = p.aligned8 != 0;
 
     for (;;) {
         __syncthreads();
@@ -264,29 +313,12 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         const float* x = p.wave + static_cast<long long>(clip) * p.row_stride;
 
         // ===================================== phase 1: frames =====================================
-        double acc_cent = 0.0, acc_roll = 0.0, acc_rms = 0.0;
+        double acc_cent = 0.0, acc_roll = 0.0, acc_rms = 0.0;   // per-warp sums over its frames
         int acc_zc = 0;
         float gmax = -FLT_MAX;
-
+        float re[32], im[32];
+        if (warp < T) load_frame(x, n, warp, lane, aligned8, re, im);
         for (int t = warp; t < T; t += kWarps) {
-            float re[32], im[32];
-            const long long s0 = static_cast<long long>(kHop) * t - kNfft / 2;
-            if (s0 >= 0 && s0 + kNfft <= n && p.aligned8) {
-                const float2* src = reinterpret_cast<const float2*>(x + s0) + lane;
-#pragma unroll
-                for (int m1 = 0; m1 < 32; ++m1) {
-                    const float2 v = __ldg(src + 32 * m1);
-                    re[m1] = v.x;
-                    im[m1] = v.y;
-                }
-            } else {
-#pragma unroll
-                for (int m1 = 0; m1 < 32; ++m1) {
-                    const long long g = s0 + 2 * (32 * m1 + lane);
-                    re[m1] = (g >= 0 && g < n) ? __ldg(x + g) : 0.0f;
-                    im[m1] = (g + 1 >= 0 && g + 1 < n) ? __ldg(x + g + 1) : 0.0f;
-                }
-            }
             // ---- rms (librosa.feature.rms: zero pad, no window)
             float ss = 0.0f;
 #pragma unroll
@@ -351,7 +383,8 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
 
             // ---- real-FFT unpack: bin k = lane + 32*k2; partner bin 1024-k lives in lane (32-lane)&31
             float pmax = 0.0f;
-            float* Pg = gP + static_cast<size_t>(t) * kPStride;
+            float* Pg = gP + static_cast<size_t>(t) * kPStride + lane;
+            float* Pbl = Pb + lane;
             const int plane = (32 - lane) & 31;
             sfor<32>([&](auto K) {
                 constexpr int k2 = decltype(K)::value;
@@ -366,8 +399,8 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 const float xi = fmaf(0.5f, ei, -fmaf(w.x, orr, w.y * oi));
                 const float P = fmaf(xr, xr, xi * xi);
                 pmax = fmaxf(pmax, P);
-                Pb[lane + 33 * k2] = P;
-                Pg[lane + 32 * k2] = P;
+                Pbl[33 * k2] = P;
+                Pg[32 * k2] = P;
             });
             {
                 const float ny = re[0] - im[0];      // X[1024] = Re Z[0] - Im Z[0] (lane 0)
@@ -376,6 +409,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
             }
             pmax = warp_max(pmax);
             __syncwarp();
+
             if (kDebug) {
                 if (p.dbg.P && t < p.dbg.T_dbg) {
                     float* dP = p.dbg.P + (static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kPStride;
@@ -383,25 +417,42 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 }
             }
 
-            // ---- |X| statistics on contiguous bins: lane owns bins [32*lane, 32*lane+32) (+1024 for lane 31)
+            // ---- contiguous pass: lane owns bins [32*lane, 32*lane+32) (+1024 for lane 31):
+            //      |X| prefix sums (centroid, 0.85 roll-off) and the Slaney mel projection as running
+            //      falling/rising partial sums flushed whenever the filter interval advances
             float cent_t, roll_t;
             {
                 float s[33];
-                float run = 0.0f, ks = 0.0f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float sv = sqrt_approx(Pb[33 * lane + j]);
+                float run = 0.0f, ks = 0.0f, accA = 0.0f, accB = 0.0f;
+                float* pq = part + lane * mel_ps;
+                const float* Prow = Pb + 33 * lane;
+                sfor<32>([&](auto J) {
+                    constexpr int j = decltype(J)::value;
+                    const float P = Prow[j];
+                    if (j > 0 && ((mel_mask >> j) & 1u)) { *pq++ = accA; accA = accB; accB = 0.0f; }
+                    const float2 ab = s_melab[j * 32 + lane];
+                    accA = fmaf(ab.x, P, accA);
+                    accB = fmaf(ab.y, P, accB);
+                    const float sv = sqrt_approx(P);
                     run += sv;
                     s[j] = run;
                     ks = fmaf(static_cast<float>(j), sv, ks);
-                }
+                });
                 s[32] = run;
                 if (lane == 31) {
-                    const float sv = sqrt_approx(Pb[1024 + 32]);
+                    const float P = Pb[1024 + 32];
+                    if (tb.mel_flush32) { *pq++ = accA; accA = accB; accB = 0.0f; }
+                    const float2 ab = s_melab[32 * 32 + 31];
+                    accA = fmaf(ab.x, P, accA);
+                    accB = fmaf(ab.y, P, accB);
+                    const float sv = sqrt_approx(P);
                     run += sv;
                     s[32] = run;
                     ks = fmaf(32.0f, sv, ks);
                 }
+                pq[0] = accA;
+                pq[1] = accB;
+                if (lane == 0) part[32 * mel_ps] = 0.0f;   // zero slot read by filters with < 3 contributing lanes
                 float inc = run;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -413,7 +464,6 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 const float total = __shfl_sync(0xffffffffu, inc, 31);
                 const float thr = __fmul_rn(0.85f, total);
                 int first = 1024;
-                if (lane == 31 && exc + s[32] >= thr) first = 1024;
 #pragma unroll
                 for (int j = 31; j >= 0; --j)
                     if (exc + s[j] >= thr) first = 32 * lane + j;
@@ -426,8 +476,31 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
             acc_cent += static_cast<double>(cent_t);
             acc_roll += static_cast<double>(roll_t);
             acc_rms += static_cast<double>(rms_t);
+            __syncwarp();
 
-            // ---- piptrack peaks on the power spectrum (bins kmin..kmax)
+            // ---- prefetch the raw samples of this warp's next frame; they land while the rest of the tile
+            //      (log-mel gather, peak detection) is processed
+            if (t + kWarps < T) load_frame(x, n, t + kWarps, lane, aligned8, re, im);
+
+            // ---- log-mel rows: filter m = 32*s + lane adds its (<= 3) partial sums in a fixed order
+            {
+                float* Lg = gL + static_cast<size_t>(t) * kMels;
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const int ms = msrc[s4];
+                    const float mel = (part[ms & 1023] + part[(ms >> 10) & 1023]) + part[ms >> 20];
+                    const float lm = 10.0f * log10f(fmaxf(1e-10f, mel));
+                    Lg[32 * s4 + lane] = lm;
+                    gmax = fmaxf(gmax, lm);
+                    if (kDebug) {
+                        if (p.dbg.logmel && t < p.dbg.T_dbg)
+                            p.dbg.logmel[(static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kMels + 32 * s4 + lane] = lm;
+                    }
+                }
+            }
+
+            // ---- piptrack peak detection on the power spectrum (bins kmin..kmax); the per-peak arithmetic
+            //      (parabolic shift, pitch, tuning residual) is done in phase 2 on the compacted records
             {
                 const float ref = __fmul_rn(0.1f, pmax);
                 for (int k0 = tb.kmin; k0 <= tb.kmax; k0 += 32) {
@@ -440,54 +513,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                         int base = 0;
                         if (lane == 0) base = atomicAdd(&s_i[1], __popc(m));
                         base = __shfl_sync(0xffffffffu, base, 0);
-                        if (pk) {
-                            const int pos = base + __popc(m & ((1u << lane) - 1u));
-                            const float sum = __fadd_rn(pp, pm);
-                            const float dif = __fsub_rn(pp, pm);
-                            const double a = static_cast<double>(sum) - 2.0 * static_cast<double>(pc);
-                            const double b = static_cast<double>(dif) * 0.5;
-                            const float shift = (fabs(b) >= fabs(a)) ? 0.0f : static_cast<float>(-b / a);
-                            const float avg = dif * 0.5f;
-                            const float dskew = __fmul_rn(__fmul_rn(0.5f, avg), shift);
-                            const float mag = __fadd_rn(pc, dskew);
-                            const double pitch_d = (static_cast<double>(k) + static_cast<double>(shift)) *
-                                                   static_cast<double>(tb.sr) / static_cast<double>(kNfft);
-                            const float pitch = static_cast<float>(pitch_d);
-                            // pitch_tuning: mod(12*log2(f/27.5), 1) in float32, wrapped to [-0.5, 0.5)
-                            const float o = log2f(__fdiv_rn(pitch, 27.5f));
-                            const float v = __fmul_rn(12.0f, o);
-                            float res = v - floorf(v);
-                            if (res >= 0.5f) res = res - 1.0f;
-                            const double rd = static_cast<double>(res);
-                            int bi = static_cast<int>(floor((rd + 0.5) * 100.0));
-                            bi = max(0, min(kTunings - 1, bi));
-                            while (bi > 0 && rd < tb.edges[bi]) --bi;
-                            while (bi < kTunings - 1 && rd >= tb.edges[bi + 1]) ++bi;
-                            gMag[pos] = mag;
-                            gBin[pos] = bi;
-                        }
-                    }
-                }
-            }
-
-            // ---- sparse Slaney mel projection + 10*log10 (power_to_db before the clamp)
-            {
-                float* Lg = gL + static_cast<size_t>(t) * kMels;
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const int len = tb.mel_len[s], off = tb.mel_off[s];
-                    const float* w = tb.melw + off * 32 + lane;
-                    float acc = 0.0f;
-                    for (int i = 0; i < len; ++i) {
-                        const int k = min(mlo[s] + i, 1024);
-                        acc = fmaf(__ldg(w + i * 32), Pb[pidx(k)], acc);
-                    }
-                    const float lm = 10.0f * log10f(fmaxf(1e-10f, acc));
-                    Lg[32 * s + lane] = lm;
-                    gmax = fmaxf(gmax, lm);
-                    if (kDebug) {
-                        if (p.dbg.logmel && t < p.dbg.T_dbg)
-                            p.dbg.logmel[(static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kMels + 32 * s + lane] = lm;
+                        if (pk) gRec[base + __popc(m & ((1u << lane) - 1u))] = make_float4(pm, pc, pp, __int_as_float(k));
                     }
                 }
             }
@@ -526,9 +552,40 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         float thr = 0.0f;
         int nsel = 0;
         if (np > 0) {
+            // ---- per-peak arithmetic of librosa.piptrack / pitch_tuning at full lane occupancy
+            unsigned* keys = (np <= kKeyCap) ? reinterpret_cast<unsigned*>(s_ex) : gKey;
+            for (int i = tid; i < np; i += kThreads) {
+                const float4 rec = gRec[i];
+                const float pm = rec.x, pc = rec.y, pp = rec.z;
+                const int k = __float_as_int(rec.w);
+                const float sum = __fadd_rn(pp, pm);
+                const float dif = __fsub_rn(pp, pm);
+                const double a = static_cast<double>(sum) - 2.0 * static_cast<double>(pc);
+                const double b = static_cast<double>(dif) * 0.5;
+                const float shift = (fabs(b) >= fabs(a)) ? 0.0f : static_cast<float>(-b / a);
+                const float avg = dif * 0.5f;
+                const float dskew = __fmul_rn(__fmul_rn(0.5f, avg), shift);
+                const float mag = __fadd_rn(pc, dskew);
+                const double pitch_d = (static_cast<double>(k) + static_cast<double>(shift)) *
+                                       static_cast<double>(tb.sr) / static_cast<double>(kNfft);
+                const float pitch = static_cast<float>(pitch_d);
+                // pitch_tuning: mod(12*log2(f/27.5), 1) in float32, wrapped to [-0.5, 0.5)
+                const float o = log2f(__fdiv_rn(pitch, 27.5f));
+                const float v = __fmul_rn(12.0f, o);
+                float res = v - floorf(v);
+                if (res >= 0.5f) res = res - 1.0f;
+                const double rd = static_cast<double>(res);
+                int bi = static_cast<int>(floor((rd + 0.5) * 100.0));
+                bi = max(0, min(kTunings - 1, bi));
+                while (bi > 0 && rd < s_edges[bi]) --bi;
+                while (bi < kTunings - 1 && rd >= s_edges[bi + 1]) ++bi;
+                keys[i] = fkey(mag);
+                gBin[i] = static_cast<unsigned char>(bi);
+            }
+            __syncthreads();
             int cle = 0;
             const int r0 = (np - 1) >> 1;
-            const unsigned ka = radix_select(gMag, np, r0, s_hist, s_i + 4, cle);
+            const unsigned ka = radix_select(keys, np, r0, s_hist, s_i + 4, cle);
             unsigned kb = ka;
             if ((np & 1) == 0 && cle <= (np >> 1)) {
                 // upper median = smallest key above ka
@@ -536,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 __syncthreads();
                 unsigned best = 0xffffffffu;
                 for (int i = tid; i < np; i += kThreads) {
-                    const unsigned key = fkey(gMag[i]);
+                    const unsigned key = keys[i];
                     if (key > ka && key < best) best = key;
                 }
                 atomicMin(reinterpret_cast<unsigned*>(&s_i[4]), best);
@@ -546,11 +603,12 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
             }
             const float fa = fkey_inv(ka), fb = fkey_inv(kb);
             thr = ((np & 1) == 0) ? __fmul_rn(__fadd_rn(fa, fb), 0.5f) : fa;
+            const unsigned kthr = fkey(thr);
             // histogram of the residual bins of peaks with mag >= median
             for (int i = tid; i < 128; i += kThreads) s_hist[i] = 0;
             __syncthreads();
             for (int i = tid; i < np; i += kThreads)
-                if (gMag[i] >= thr) atomicAdd(&s_hist[gBin[i]], 1);
+                if (keys[i] >= kthr) atomicAdd(&s_hist[gBin[i]], 1);
             __syncthreads();
             if (warp == 0) {
                 int bc = -1, bi = 1 << 20, tot = 0;
@@ -579,14 +637,19 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         if (kDebug) {
             if (p.dbg.clip_info && tid == 0) {
                 float* ci = p.dbg.clip_info + static_cast<size_t>(clip) * 8;
-                ci[0] = static_cast<float>(tb.edges[tuning_idx]);
+                ci[0] = static_cast<float>(s_edges[tuning_idx]);
                 ci[1] = gmx; ci[2] = static_cast<float>(np); ci[3] = thr;
                 ci[4] = static_cast<float>(nsel); ci[5] = static_cast<float>(T); ci[6] = 0.f; ci[7] = 0.f;
             }
         }
 
         // ===================================== phase 3a: MFCC ======================================
+        // (also stages the tuning's chroma bank into shared memory: the warp tiles are free now)
+        float* sW = s_ex;                                   // [12][1056]
         {
+            const float4* Wg = reinterpret_cast<const float4*>(tb.chroma + static_cast<size_t>(tuning_idx) * kChroma * kPStride);
+            float4* Ws = reinterpret_cast<float4*>(sW);
+            for (int i = tid; i < kChroma * kPStride / 4; i += kThreads) Ws[i] = __ldg(Wg + i);
             const float clampv = __fsub_rn(gmx, 80.0f);
             const int m = tid & 127, h = tid >> 7;
             double a = 0.0;
@@ -603,47 +666,63 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         }
 
         // ===================================== phase 3b: chroma ====================================
+        // warp tile = 4 frames x 12 chroma; lane owns bins 4*lane + 128*j (float4), bin 1024 is added at the end
         {
-            const float* W = tb.chroma + static_cast<size_t>(tuning_idx) * kChroma * kPStride;
             double cacc[kChroma];
 #pragma unroll
             for (int c = 0; c < kChroma; ++c) cacc[c] = 0.0;
-            const int ntiles = (T + 7) >> 3;
+            float* red = s_ex + kChroma * kPStride + warp * 64;
+            const int ntiles = (T + 3) >> 2;
             for (int tile = warp; tile < ntiles; tile += kWarps) {
-                const int t0 = tile * 8;
-                const int nf = min(8, T - t0);
+                const int t0 = tile * 4;
+                const int nf = min(4, T - t0);
                 const float* Pt = gP + static_cast<size_t>(t0) * kPStride;
-                float acc[96];
+                float acc[48];
 #pragma unroll
-                for (int i = 0; i < 96; ++i) acc[i] = 0.0f;
-                for (int j = 0; j < 33; ++j) {
-                    const int k = lane + 32 * j;
-                    const bool ok = (j < 32) || (lane == 0);
-                    float w[kChroma], pv[8];
+                for (int i = 0; i < 48; ++i) acc[i] = 0.0f;
+#pragma unroll 2
+                for (int j = 0; j < 8; ++j) {
+                    const int k = 4 * lane + 128 * j;
+                    float4 pv[4];
 #pragma unroll
-                    for (int c = 0; c < kChroma; ++c) w[c] = ok ? __ldg(W + c * kPStride + k) : 0.0f;
+                    for (int f = 0; f < 4; ++f)
+                        pv[f] = (f < nf) ? *reinterpret_cast<const float4*>(Pt + f * kPStride + k) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int f = 0; f < 8; ++f) pv[f] = (ok && f < nf) ? Pt[f * kPStride + k] : 0.0f;
+                    for (int c = 0; c < kChroma; ++c) {
+                        const float4 w = *reinterpret_cast<const float4*>(sW + c * kPStride + k);
 #pragma unroll
-                    for (int f = 0; f < 8; ++f)
-#pragma unroll
-                        for (int c = 0; c < kChroma; ++c) acc[f * kChroma + c] = fmaf(w[c], pv[f], acc[f * kChroma + c]);
+                        for (int f = 0; f < 4; ++f) {
+                            float a = acc[f * kChroma + c];
+                            a = fmaf(w.x, pv[f].x, a);
+                            a = fmaf(w.y, pv[f].y, a);
+                            a = fmaf(w.z, pv[f].z, a);
+                            a = fmaf(w.w, pv[f].w, a);
+                            acc[f * kChroma + c] = a;
+                        }
+                    }
                 }
-                // lane l ends up with the warp totals of acc[l], acc[32+l], acc[64+l]
-                float* red = Pb;       // 96 floats of this warp's tile
-#pragma unroll
-                for (int g = 0; g < 3; ++g) {
+                // lane l ends up with the warp totals of acc[l] (and lanes l, l^16 with acc[32 + (l & 15)])
+                {
                     float v[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = acc[32 * g + i];
-                    red[32 * g + lane] = reduce_scatter32(v, lane);
+                    for (int i = 0; i < 32; ++i) v[i] = acc[i];
+                    red[lane] = reduce_scatter32(v, lane);
+                    float u[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) u[i] = acc[32 + i];
+                    const float r16 = reduce_scatter16(u, lane);
+                    if (lane < 16) red[32 + lane] = r16;
                 }
                 __syncwarp();
                 if (lane < nf) {
+                    const float pn = Pt[lane * kPStride + 1024];            // Nyquist bin of frame t0 + lane
                     float raw[kChroma];
                     float mx = 0.0f;
 #pragma unroll
-                    for (int c = 0; c < kChroma; ++c) { raw[c] = red[lane * kChroma + c]; mx = fmaxf(mx, fabsf(raw[c])); }
+                    for (int c = 0; c < kChroma; ++c) {
+                        raw[c] = fmaf(sW[c * kPStride + 1024], pn, red[lane * kChroma + c]);
+                        mx = fmaxf(mx, fabsf(raw[c]));
+                    }
                     if (mx < FLT_MIN) mx = 1.0f;
 #pragma unroll
                     for (int c = 0; c < kChroma; ++c) cacc[c] += static_cast<double>(__fdiv_rn(raw[c], mx));
@@ -652,10 +731,9 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
             }
 #pragma unroll
             for (int c = 0; c < kChroma; ++c) {
-                double v = (lane < 8) ? cacc[c] : 0.0;
+                double v = (lane < 4) ? cacc[c] : 0.0;
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
                 if (lane == 0) s_wacc[warp * 16 + 3 + c] = v;
             }
         }
@@ -683,8 +761,8 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
 
 // ------------------------------------------------------------------------------------------------
 size_t smem_bytes() {
-    return sizeof(float2) * 3072 + sizeof(float) * kWarps * kExFloats + sizeof(double) * (256 + kWarps * 16) +
-           sizeof(int) * (256 + 32) + sizeof(float) * 32;
+    return sizeof(float2) * (3072 + 33 * 32) + sizeof(float) * kWarps * kExFloats +
+           sizeof(double) * (256 + kWarps * 16 + 104) + sizeof(int) * (256 + 32) + sizeof(float) * 32;
 }
 
 cudaError_t configure_kernels(int* blocks_per_sm) {

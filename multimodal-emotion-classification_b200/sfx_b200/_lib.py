@@ -20,9 +20,10 @@ class SfxError(RuntimeError):
 
 
 class TablesHost(C.Structure):
-    _fields_ = [("sr", C.c_int32), ("pip_kmin", C.c_int32), ("pip_kmax", C.c_int32), ("mel_rows", C.c_int32),
-                ("hann", C.c_void_p), ("tw1", C.c_void_p), ("tw2", C.c_void_p), ("melw", C.c_void_p),
-                ("mel_lo", C.c_void_p), ("mel_off", C.c_void_p), ("mel_len", C.c_void_p),
+    _fields_ = [("sr", C.c_int32), ("pip_kmin", C.c_int32), ("pip_kmax", C.c_int32), ("mel_ps", C.c_int32),
+                ("mel_flush32", C.c_int32),
+                ("hann", C.c_void_p), ("tw1", C.c_void_p), ("tw2", C.c_void_p), ("mel_ab", C.c_void_p),
+                ("mel_mask", C.c_void_p), ("mel_src", C.c_void_p),
                 ("chroma", C.c_void_p), ("dct", C.c_void_p), ("edges", C.c_void_p)]
 
 
@@ -81,12 +82,12 @@ def check(rc: int):
 def make_tables_struct(tb: dict):
     """TablesHost pointing into the numpy arrays of tables.build_tables (keeps them alive via .keep)."""
     keep = {k: np.ascontiguousarray(tb[k]) for k in
-            ("hann", "tw1", "tw2", "melw", "mel_lo", "mel_off", "mel_len", "chroma", "dct", "edges")}
+            ("hann", "tw1", "tw2", "mel_ab", "mel_mask", "mel_src", "chroma", "dct", "edges")}
     assert keep["hann"].dtype == np.float32 and keep["chroma"].dtype == np.float32
     assert keep["dct"].dtype == np.float64 and keep["edges"].dtype == np.float64
-    assert keep["mel_lo"].dtype == np.int32 and keep["mel_off"].dtype == np.int32 and keep["mel_len"].dtype == np.int32
+    assert keep["mel_ab"].dtype == np.float32 and keep["mel_mask"].dtype == np.uint32 and keep["mel_src"].dtype == np.int32
     t = TablesHost(sr=int(tb["sr"]), pip_kmin=int(tb["pip_kmin"]), pip_kmax=int(tb["pip_kmax"]),
-                   mel_rows=int(keep["melw"].shape[0]),
+                   mel_ps=int(tb["mel_ps"]), mel_flush32=int(tb["mel_flush32"]),
                    **{k: v.ctypes.data for k, v in keep.items()})
     t.keep = keep
     return t

@@ -11,8 +11,9 @@ Layouts are chosen for the kernels (see DESIGN.md "HBM / SMEM layout"), not for 
   hann   float32[2048]        (w[2m], w[2m+1]) pairs, read as float2[1024]
   tw1    float32[32][32][2]   tw1[k1][lane] = exp(-2*pi*i*lane*k1/1024)      (inter-stage twiddle)
   tw2    float32[32][32][2]   tw2[k2][lane] = 0.5*(cos, sin)(2*pi*(lane+32*k2)/2048)  (real-FFT unpack)
-  melw   float32[mel_rows][32] transposed/padded sparse mel weights: slot s (=filter//32), position i,
-                              lane (=filter%32); mel_lo[128] first bin; mel_off[4], mel_len[4]
+  mel_ab float32[33][32][2]   (falling, rising) Slaney weights of bin 32*lane + j at [j][lane]; mel_mask uint32[32]
+                              flush bits, mel_src int32[128][3] partial-sum slots (see mel_chunk_layout)
+  melw   float32[mel_rows][32] transposed/padded sparse mel weights (dense-bank audit layout, host tests only)
   chroma float32[100][12][1056] one bank per tuning edge, bin axis zero-padded to 1056
   dct    float64[128][128]    rows k of the ortho DCT-II
   edges  float64[101]         np.linspace(-0.5, 0.5, 101)
@@ -123,6 +124,71 @@ def mel_sparse_layout(bank: np.ndarray):
     return w, lo, slot_off, slot_len
 
 
+def mel_chunk_layout(sr: int, bank: np.ndarray):
+    """Layout for the kernel's contiguous-chunk mel projection (lane l owns bins [32l, 32l+32), lane 31 also 1024).
+
+    Every rFFT bin lies in one interval [edge_i, edge_{i+1}) of the 130 Slaney edges, i.e. on the falling slope
+    of filter i-1 (weight wa) and the rising slope of filter i (weight wb).  A lane walks its bins with two running
+    sums and flushes one partial sum whenever the interval index advances (bit j of mel_mask[lane]); the partial of
+    filter m written by lane L sits at slot L*mel_ps + (m - i0[L] + 1).  mel_src[m] lists the (<= 3) slots to add up.
+    Requires the interval index to advance by at most 1 per bin (true for sr <= ~60 kHz); raises otherwise.
+    """
+    fftfreqs = np.fft.rfftfreq(N_FFT, 1.0 / sr)
+    edges_hz = _mel_to_hz(np.linspace(_hz_to_mel(0.0), _hz_to_mel(sr / 2.0), N_MELS + 2))
+    iv = np.clip(np.searchsorted(edges_hz, fftfreqs, side="right") - 1, 0, N_MELS)
+    if not bank[:, N_BINS - 1].any():
+        iv[N_BINS - 1] = iv[N_BINS - 2]          # common case: no weight on the Nyquist bin, no flush needed
+    if np.diff(iv).max() > 1:
+        raise ValueError(f"sample rate {sr}: mel intervals narrower than an FFT bin are not supported")
+    wa = np.zeros(N_BINS, dtype=np.float32)
+    wb = np.zeros(N_BINS, dtype=np.float32)
+    for k in range(N_BINS):
+        i = iv[k]
+        if 1 <= i <= N_MELS:
+            wa[k] = bank[i - 1, k]
+        if i <= N_MELS - 1:
+            wb[k] = bank[i, k]
+    recon = np.zeros_like(bank)
+    for k in range(N_BINS):
+        i = iv[k]
+        if 1 <= i <= N_MELS:
+            recon[i - 1, k] += wa[k]
+        if i <= N_MELS - 1:
+            recon[i, k] += wb[k]
+    if not np.array_equal(recon, bank):
+        raise ValueError("mel bank is not expressible as adjacent falling/rising slopes")
+    ab = np.zeros((33, 32, 2), dtype=np.float32)
+    mask = np.zeros(32, dtype=np.uint32)
+    i0 = np.zeros(32, dtype=np.int32)
+    flush32 = int(iv[N_BINS - 1] != iv[N_BINS - 2])
+    touched = []
+    for lane in range(32):
+        i0[lane] = iv[32 * lane]
+        tl = set()
+        for j in range(33 if lane == 31 else 32):
+            k = 32 * lane + j
+            ab[j, lane] = (wa[k], wb[k])
+            if 0 < j < 32 and iv[k] != iv[k - 1]:
+                mask[lane] |= np.uint32(1) << np.uint32(j)
+            tl.update((iv[k] - 1, iv[k]))
+        touched.append(tl)
+    nflush = [bin(int(mask[l])).count("1") + 2 + (flush32 if l == 31 else 0) for l in range(32)]
+    ps = max(nflush) | 1                       # odd row stride of the partial-sum slots
+    if 1088 + 32 * ps + 1 > 2112:
+        raise ValueError(f"sample rate {sr}: too many mel filters per 32-bin chunk for the kernel's tile")
+    zero_slot = 32 * ps
+    src = np.full((N_MELS, 3), zero_slot, dtype=np.int32)
+    nsrc = np.zeros(N_MELS, dtype=np.int32)
+    for lane in range(32):
+        for m in sorted(touched[lane]):
+            if 0 <= m < N_MELS:
+                q = m - (i0[lane] - 1)
+                assert 0 <= q < nflush[lane] and nsrc[m] < 3
+                src[m, nsrc[m]] = lane * ps + q
+                nsrc[m] += 1
+    return dict(mel_ab=ab, mel_mask=mask, mel_i0=i0, mel_src=src, mel_flush32=flush32, mel_ps=int(ps))
+
+
 @functools.lru_cache(maxsize=4)
 def build_tables(sr: int = 22050) -> dict:
     n = np.arange(N_FFT, dtype=np.float64)
@@ -140,6 +206,7 @@ def build_tables(sr: int = 22050) -> dict:
     for i in range(N_TUNINGS):
         chroma[i, :, :N_BINS] = chroma_bank(sr, float(edges[i]))
     kmin, kmax = piptrack_bin_range(sr)
-    return dict(sr=sr, hann=hann, tw1=np.ascontiguousarray(tw1), tw2=np.ascontiguousarray(tw2),
+    chunk = mel_chunk_layout(sr, mb)
+    return dict(**chunk, sr=sr, hann=hann, tw1=np.ascontiguousarray(tw1), tw2=np.ascontiguousarray(tw2),
                 mel_dense=mb, melw=melw, mel_lo=mel_lo, mel_off=mel_off, mel_len=mel_len,
                 chroma=chroma, dct=dct_matrix(), edges=edges, pip_kmin=kmin, pip_kmax=kmax)

@@ -1,0 +1,241 @@
+"""GPU parity tests (pytest -m gpu): the sm_100a path, called through the C ABI (ctypes -> libsfx_b200.so),
+against the CPU oracle on the same seeded inputs, the committed golden fixtures, and size-independent
+properties at full batch sizes.  Tolerance: |err| <= 1e-3*|ref| + atol(group), see tests/synth.py."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import librosa_port as lp
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+N3S = 66150
+
+
+@pytest.fixture(scope="module")
+def ex():
+    from sfx_b200 import get_extractor
+    return get_extractor(torch.device("cuda", 0))
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def assert_parity(got, ref, n_mfcc=40):
+    ok, report = synth.compare(got, ref, n_mfcc=n_mfcc)
+    assert ok, "\n" + report
+
+
+def test_native_library_is_loaded(ex):
+    maps = open("/proc/self/maps").read()
+    assert "libsfx_b200.so" in maps
+    assert ex.lib.sfx_device_count() >= 1 and ex.lib.sfx_launches_per_extract() == 1
+
+
+def test_config1_golden_64_clips(ex):
+    """BASELINE configs[0]: 64 synthetic 3 s clips, seed 0, against the committed oracle fixture."""
+    g = np.load(os.path.join(GOLD, "config1_seed0.npz"))
+    w = synth.make_batch(64, N3S, seed=0)
+    assert np.uint32(zlib.crc32(w.tobytes())) == g["crc"]
+    dbg = {}
+    got = ex.extract(dev(w), debug=dbg).cpu().numpy()
+    assert_parity(got, g["features"])
+    tuning = dbg["clip_info"].cpu().numpy()[:, 0]
+    flips = int((np.abs(tuning - g["tuning"]) > 1e-6).sum())
+    assert flips == 0, f"{flips} tuning arg-max flips vs the oracle"
+    got2 = ex.extract(dev(w)).cpu().numpy()                   # non-debug kernel instantiation, bitwise equal
+    assert np.array_equal(got, got2)
+
+
+def test_edge_cases_golden(ex):
+    e = np.load(os.path.join(GOLD, "edge_cases.npz"))
+    rng = np.random.default_rng(5)
+    clips = np.stack([synth.make_clip(k, N3S, rng) for k in ("zero", "dc", "square")])
+    got = ex.extract(dev(clips)).cpu().numpy()
+    assert_parity(got, e["features"])
+    assert got[0, 0] == pytest.approx(-100.0 * np.sqrt(128.0), rel=1e-6)       # silence: every band -100 dB
+    assert np.abs(got[0, 1:40]).max() < 1e-3 and not got[0, 40:].any()
+
+
+def test_ragged_golden_and_poisoned_padding(ex):
+    g = np.load(os.path.join(GOLD, "ragged_seed3.npz"))
+    wr, lens = synth.make_ragged(10, 11025, 200000, seed=3)
+    got = ex.extract(dev(wr), dev(lens)).cpu().numpy()
+    assert_parity(got, g["features"])
+
+
+def test_config2_ravdess_shaped(ex):
+    """BASELINE configs[1] shape: ~3.7 s clips; preprocess_audio semantics (truncate to 3 s, T=130) and raw (T=160)."""
+    rng = np.random.default_rng(11)
+    n_raw = 81586
+    w = synth.make_batch(1440, n_raw, seed=11)
+    d = dev(w)
+    trunc = ex.extract(d, n_samples=N3S).cpu().numpy()
+    raw = ex.extract(d).cpu().numpy()
+    assert np.isfinite(trunc).all() and np.isfinite(raw).all()
+    idx = rng.choice(1440, size=24, replace=False)
+    assert_parity(trunc[idx], lp.features_batch(w[idx, :N3S]))
+    assert_parity(raw[idx[:8]], lp.features_batch(w[idx[:8]]))
+    # truncation == extracting the first 66150 samples laid out contiguously, bit for bit
+    again = ex.extract(dev(w[:64, :N3S])).cpu().numpy()
+    assert np.array_equal(again, trunc[:64])
+
+
+def test_config3_tess_shaped_zero_tail(ex):
+    """BASELINE configs[2] shape: ~2 s of signal zero-padded to 3 s by load_audio -> top_db clamp is active."""
+    rng = np.random.default_rng(12)
+    w = np.zeros((256, N3S), dtype=np.float32)
+    for i in range(256):
+        n = int(44100 * rng.uniform(0.85, 1.15))
+        w[i, :n] = synth.make_clip(synth.KINDS[i % 2], n, rng)
+    got = ex.extract(dev(w)).cpu().numpy()
+    idx = rng.choice(256, size=16, replace=False)
+    assert_parity(got[idx], lp.features_batch(w[idx]))
+
+
+def test_config5_variable_length_extremes(ex):
+    """BASELINE configs[4] shape: 0.5 s .. 60 s, padded rows + lengths (T = 22 .. 2584)."""
+    lens = np.array([11025, 11026, 511, 512, 513, 2047, 2048, 2049, 66150, 123457, 1323000], dtype=np.int32)
+    rng = np.random.default_rng(13)
+    w = np.full((len(lens), 1323000), 3.0, dtype=np.float32)
+    for i, n in enumerate(lens):
+        w[i, :n] = synth.make_clip(synth.KINDS[i % 4], int(n), rng)
+    got = ex.extract(dev(w), dev(lens)).cpu().numpy()
+    ref = lp.features_batch(w, lens)
+    assert_parity(got, ref)
+
+
+def test_single_sample_and_bad_lengths(ex):
+    w = np.full((3, 4096), 0.5, dtype=np.float32)
+    lens = np.array([1, 0, -5], dtype=np.int32)
+    got = ex.extract(dev(w), dev(lens)).cpu().numpy()
+    assert np.isfinite(got[0]).all()                                # T = 1 frame
+    assert_parity(got[:1], lp.features_batch(w[:1], lens[:1]))
+    assert np.isnan(got[1:]).all()                                  # length <= 0 -> NaN row (host wrapper raises)
+
+
+def test_unaligned_rows_and_strided_batch(ex):
+    base = synth.make_batch(6, N3S + 1, seed=21)
+    d = dev(base)
+    odd = ex.extract(d, n_samples=N3S).cpu().numpy()                # odd row stride: scalar-load path
+    assert_parity(odd, lp.features_batch(base[:, :N3S]))
+    shifted = d[:, 1:]                                              # rows start 4 bytes off 8-byte alignment
+    got = ex.extract(shifted).cpu().numpy()
+    assert_parity(got, lp.features_batch(base[:, 1:]))
+
+
+@pytest.mark.parametrize("n_mfcc", [13, 20, 128])
+def test_other_n_mfcc(ex, n_mfcc):
+    w = synth.make_batch(4, N3S, seed=31)
+    got = ex.extract(dev(w), n_mfcc=n_mfcc).cpu().numpy()
+    assert got.shape == (4, n_mfcc + 16)
+    ref = np.stack([np.concatenate([lp.extract_mfcc(x, 22050, n_mfcc), lp.extract_chroma(x, 22050),
+                                    lp.extract_spectral_features(x, 22050)]) for x in w])
+    assert_parity(got, ref, n_mfcc=n_mfcc)
+
+
+def test_other_sample_rate(ex):
+    from sfx_b200 import get_extractor
+    ex16 = get_extractor(torch.device("cuda", 0), sr=16000)
+    w = synth.make_batch(4, 48000, seed=41)
+    got = ex16.extract(dev(w)).cpu().numpy()
+    ref = np.stack([lp.features_from_audio(x, sr=16000) for x in w])
+    assert_parity(got, ref)
+
+
+def test_host_path_matches_device_path_and_chunks(ex):
+    w = synth.make_batch(37, N3S, seed=51)
+    d = ex.extract(dev(w)).cpu().numpy()
+    assert np.array_equal(ex.extract_host(w), d)
+    assert np.array_equal(ex.extract_host(w, chunk_clips=8), d)     # 5 chunks over two streams
+    pinned = torch.from_numpy(w).pin_memory()
+    out = torch.empty((37, 56), dtype=torch.float32).pin_memory()
+    ex.extract_host(pinned.numpy(), out=out.numpy(), chunk_clips=16)
+    assert np.array_equal(out.numpy(), d)
+    wr, lens = synth.make_ragged(9, 11025, 150000, seed=52)
+    dr = ex.extract(dev(wr), dev(lens)).cpu().numpy()
+    assert np.array_equal(ex.extract_host(wr, lens, chunk_clips=4), dr)
+
+
+def test_dropin_module_functions(ex):
+    """The reference's tests/test_preprocessing.py:30-67 against the drop-in module, plus values vs the oracle."""
+    from config import Config
+    from preprocessing.audio_preprocessing import (extract_chroma, extract_mfcc, extract_spectral_features,
+                                                   extract_features_batch)
+    audio = np.random.default_rng(0).standard_normal(Config.SAMPLE_RATE * Config.AUDIO_DURATION)   # float64
+    mfcc = extract_mfcc(audio, Config.SAMPLE_RATE)
+    assert mfcc.shape == (Config.N_MFCC,) and np.all(np.isfinite(mfcc))
+    chroma = extract_chroma(audio, Config.SAMPLE_RATE)
+    assert chroma.shape == (12,) and np.all(np.isfinite(chroma))
+    spectral = extract_spectral_features(audio, Config.SAMPLE_RATE)
+    assert spectral.shape == (4,) and spectral.dtype == np.float32 and np.all(np.isfinite(spectral))
+    a32 = audio.astype(np.float32)
+    got = np.concatenate([extract_mfcc(a32, 22050), extract_chroma(a32, 22050), extract_spectral_features(a32, 22050)])
+    assert_parity(got[None], lp.features_from_audio(a32)[None])
+    batch = extract_features_batch(np.stack([a32, a32 * 0.5]))
+    assert np.array_equal(batch[0], got.astype(np.float32))
+    with pytest.raises(ValueError):
+        extract_features_batch(np.stack([a32, np.full_like(a32, np.nan)]))
+
+
+def test_preprocess_audio_file_roundtrip(ex, tmp_path):
+    import wave
+    from preprocessing.audio_preprocessing import load_audio, preprocess_audio, preprocess_audio_batch
+    y = synth.make_clip("harmonic", 50000, np.random.default_rng(3))
+    p = os.path.join(tmp_path, "a.wav")
+    with wave.open(p, "wb") as wf:
+        wf.setnchannels(1); wf.setsampwidth(2); wf.setframerate(22050)
+        wf.writeframes((y * 32767).astype("<i2").tobytes())
+    feats = preprocess_audio(p)
+    assert feats.shape == (56,) and feats.dtype == np.float32
+    audio, _ = load_audio(p)
+    assert_parity(feats[None], lp.features_from_audio(audio)[None])
+    fb, kept = preprocess_audio_batch([p, os.path.join(tmp_path, "missing.wav"), p], on_error="skip")
+    assert kept == [0, 2] and np.array_equal(fb[0], feats) and np.array_equal(fb[1], feats)
+
+
+def test_properties_at_full_batch(ex):
+    """Size-independent checks on a batch too large for the oracle: determinism, permutation equivariance,
+    duplicate rows, amplitude scaling laws (rms ~ a, zcr/chroma/centroid/rolloff invariant, mfcc0 + 20log10(a)*sqrt(128))."""
+    B = 4096
+    g = torch.Generator(device="cuda").manual_seed(7)
+    w = torch.randn((B, N3S), device="cuda", generator=g) * 0.1
+    w[1::2] = w[0:1]                                                 # half the batch duplicates clip 0
+    a = ex.extract(w)
+    b = ex.extract(w)
+    assert torch.equal(a, b)                                         # bitwise deterministic
+    assert torch.equal(a[1::2], a[0:1].expand(B // 2, -1))           # identical clips -> identical rows
+    perm = torch.randperm(B, device="cuda", generator=g)
+    assert torch.equal(ex.extract(w[perm].contiguous()), a[perm])    # clips are independent units
+    s = ex.extract(w[:512] * 0.25)
+    r = a[:512]
+    assert torch.allclose(s[:, 55], 0.25 * r[:, 55], rtol=1e-5)
+    assert torch.equal(s[:, 52], r[:, 52])
+    assert torch.allclose(s[:, 53:55], r[:, 53:55], rtol=1e-4)
+    assert torch.allclose(s[:, 40:52], r[:, 40:52], atol=2e-5)       # 0.25 is a power of two: tuning identical
+    shift = 20 * np.log10(0.25) * np.sqrt(128.0)
+    assert torch.allclose(s[:, 0], r[:, 0] + shift, rtol=1e-5)
+    assert torch.allclose(s[:, 1:40], r[:, 1:40], atol=2e-3)
+    ref = lp.features_batch(w[:4].cpu().numpy())                     # spot-check against the oracle
+    assert_parity(a[:4].cpu().numpy(), ref)
+
+
+def test_stream_ordering_and_reentrancy(ex):
+    """Two extractions on different torch streams with their own workspaces must not interfere."""
+    from sfx_b200.extractor import SpeechFeatureExtractor
+    ex2 = SpeechFeatureExtractor(torch.device("cuda", 0))
+    w1, w2 = dev(synth.make_batch(300, N3S, seed=61)), dev(synth.make_batch(300, N3S, seed=62))
+    ref1, ref2 = ex.extract(w1).clone(), ex.extract(w2).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    with torch.cuda.stream(s1):
+        o1 = ex.extract(w1)
+    with torch.cuda.stream(s2):
+        o2 = ex2.extract(w2)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, ref1) and torch.equal(o2, ref2)

@@ -1,0 +1,114 @@
+"""Host-side logic that needs no GPU: the drop-in module's surface and load_audio, clip sharding, and the
+world_size-2 all-gather of the feature cache over gloo."""
+import inspect
+import os
+import wave
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sfx_b200 import shard
+
+
+def test_dropin_surface_matches_reference():
+    import preprocessing.audio_preprocessing as ap
+    from config import Config
+    assert (Config.SAMPLE_RATE, Config.AUDIO_DURATION, Config.N_MFCC) == (22050, 3, 40)
+    sig = {n: str(inspect.signature(getattr(ap, n))) for n in
+           ("load_audio", "extract_mfcc", "extract_chroma", "extract_spectral_features", "preprocess_audio")}
+    assert sig["load_audio"] == "(file_path, sr=22050, duration=3)"
+    assert sig["extract_mfcc"] == "(audio, sr, n_mfcc=40)"
+    assert sig["extract_chroma"] == "(audio, sr)"
+    assert sig["extract_spectral_features"] == "(audio, sr)"
+    assert sig["preprocess_audio"] == "(file_path)"
+
+
+def test_invalid_audio_raises_before_any_device_work():
+    import preprocessing.audio_preprocessing as ap
+    with pytest.raises(ValueError):
+        ap.extract_mfcc(np.array([0.0, np.inf], dtype=np.float32), 22050)
+    with pytest.raises(ValueError):
+        ap.extract_chroma(np.zeros(100, dtype=np.int16), 22050)
+    with pytest.raises(ValueError):
+        ap.extract_spectral_features(np.zeros(0, dtype=np.float32), 22050)
+
+
+def _write_wav(path, data, rate, width=2):
+    with wave.open(path, "wb") as w:
+        w.setnchannels(data.shape[1])
+        w.setsampwidth(width)
+        w.setframerate(rate)
+        w.writeframes((data * 32767).astype("<i2").tobytes())
+
+
+def test_load_audio_pad_trim_and_mono(tmp_path):
+    import preprocessing.audio_preprocessing as ap
+    rng = np.random.default_rng(0)
+    short = rng.uniform(-0.5, 0.5, size=(22050, 2))
+    p = os.path.join(tmp_path, "short.wav")
+    _write_wav(p, short, 22050)
+    audio, sr = ap.load_audio(p)
+    assert sr == 22050 and audio.shape == (66150,) and audio.dtype == np.float32
+    q = (short * 32767).astype("<i2").astype(np.float32) / 32768.0
+    np.testing.assert_allclose(audio[:22050], q.mean(axis=1), atol=1e-7)
+    assert not audio[22050:].any()                                    # zero right-pad (reference :15-16)
+    long = rng.uniform(-0.5, 0.5, size=(4 * 22050, 1))
+    p2 = os.path.join(tmp_path, "long.wav")
+    _write_wav(p2, long, 22050)
+    audio2, _ = ap.load_audio(p2)
+    assert audio2.shape == (66150,)                                   # trimmed (reference :17-18)
+    p3 = os.path.join(tmp_path, "rate.wav")
+    _write_wav(p3, rng.uniform(-0.5, 0.5, size=(48000, 1)), 48000)
+    audio3, sr3 = ap.load_audio(p3)
+    assert sr3 == 22050 and audio3.shape == (66150,) and not audio3[22050 + 64:].any()
+    with pytest.raises(ValueError):
+        open(os.path.join(tmp_path, "bad.wav"), "wb").write(b"not a wav")
+        ap.load_audio(os.path.join(tmp_path, "bad.wav"))
+
+
+def test_shard_ranges_cover_exactly():
+    for n, w in ((1_000_000, 8), (1440, 4), (7, 8), (0, 2), (64, 1)):
+        ranges = [shard.shard_range(n, w, r) for r in range(w)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        assert max(hi - lo for lo, hi in ranges) == shard.shard_size(n, w)
+
+
+def test_partition_by_samples_balances():
+    rng = np.random.default_rng(0)
+    lengths = np.exp(rng.uniform(np.log(11025), np.log(1323000), size=4096)).astype(np.int64)
+    parts = shard.partition_by_samples(lengths, 8)
+    assert parts[0][0] == 0 and parts[-1][1] == 4096
+    loads = np.array([lengths[lo:hi].sum() for lo, hi in parts])
+    assert loads.max() / loads.mean() < 1.05
+
+
+def _worker(rank, world, port, n_total, ragged):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        table = torch.arange(n_total * 5, dtype=torch.float32).reshape(n_total, 5)
+
+        def fake_extract(w, lengths):                                  # stands in for the CUDA extractor
+            return torch.cat([w * 2.0, w.sum(dim=1, keepdim=True)], dim=1)[:, :6]
+
+        expect = fake_extract(table, None)
+        if ragged:
+            lens = np.arange(1, n_total + 1)
+            ranges = shard.partition_by_samples(lens, world)
+            lo, hi = ranges[rank]
+            full = shard.gather_ragged_feature_cache(fake_extract(table[lo:hi], None), ranges)
+        else:
+            full = shard.extract_sharded(fake_extract, table)
+        assert full.shape == expect.shape and torch.equal(full, expect)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total,ragged", [(10, False), (7, False), (9, True)])
+def test_feature_cache_allgather_gloo_world2(n_total, ragged):
+    port = 29500 + (os.getpid() + n_total) % 2000
+    mp.spawn(_worker, args=(2, port, n_total, ragged), nprocs=2, join=True)
