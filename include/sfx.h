@@ -80,7 +80,8 @@ const char *sfx_last_error(void);
 /* Number of CUDA devices visible (<0 on error; 0 = none: compute calls will fail). */
 int         sfx_device_count(void);
 
-/* Upload the constant tables to `device` (idempotent per (device, sr); replaces earlier tables). */
+/* Upload the constant tables of sample rate tables->sr to `device`.  Idempotent per (device, sr); table sets
+ * of several sample rates coexist and are selected by the `sr` argument of the extract calls. */
 int         sfx_init_tables(int device, const sfx_tables_host *tables);
 
 /* Bytes of device workspace sfx_extract needs for clips of at most max_samples samples.
@@ -91,6 +92,7 @@ size_t      sfx_workspace_bytes(int device, int64_t max_samples);
 int         sfx_launches_per_extract(void);
 
 /* Batched extraction, device buffers.
+ *   sr          sample rate of a table set uploaded with sfx_init_tables
  *   wave        [B] rows of float32 samples, row i at wave + i*row_stride (device)
  *   lengths     [B] int32 sample counts (device) or NULL = every clip has n_default samples
  *   out         [B] rows of (n_mfcc + 12 + 4) float32 at out + i*out_stride (device):
@@ -99,13 +101,13 @@ int         sfx_launches_per_extract(void);
  *   stream      cudaStream_t (NULL = legacy default stream)
  * A clip with length <= 0 yields a row of NaN (the host wrapper raises, as librosa would).
  */
-int         sfx_extract(int device, const float *wave, int64_t row_stride, const int32_t *lengths,
+int         sfx_extract(int device, int32_t sr, const float *wave, int64_t row_stride, const int32_t *lengths,
                         int64_t n_default, int64_t max_samples, int32_t B, int32_t n_mfcc,
                         float *out, int64_t out_stride, void *workspace, size_t workspace_bytes,
                         void *stream);
 
 /* Same, additionally filling `dbg`. */
-int         sfx_extract_debug(int device, const float *wave, int64_t row_stride, const int32_t *lengths,
+int         sfx_extract_debug(int device, int32_t sr, const float *wave, int64_t row_stride, const int32_t *lengths,
                               int64_t n_default, int64_t max_samples, int32_t B, int32_t n_mfcc,
                               float *out, int64_t out_stride, void *workspace, size_t workspace_bytes,
                               void *stream, const sfx_debug_out *dbg);
@@ -114,7 +116,7 @@ int         sfx_extract_debug(int device, const float *wave, int64_t row_stride,
  * H2D copy overlapped with the kernel on two streams, D2H of the feature rows, then a stream sync.
  * host_wave rows must hold finite float32 samples; host_lengths may be NULL.  Allocates and caches
  * its own device buffers per device.  chunk_clips <= 0 selects the default chunk. */
-int         sfx_extract_host(int device, const float *host_wave, int64_t row_stride,
+int         sfx_extract_host(int device, int32_t sr, const float *host_wave, int64_t row_stride,
                              const int32_t *host_lengths, int64_t n_default, int32_t B, int32_t n_mfcc,
                              float *host_out, int64_t out_stride, int32_t chunk_clips);
 

@@ -28,13 +28,25 @@ struct HostPath {               // cached buffers of sfx_extract_host
     int chunk = 0;
 };
 
+struct TableSet {               // one per sample rate
+    int sr = 0;
+    sfx::DevTables tb{};
+};
+
 struct DevCtx {
     bool ready = false;
     int sm_count = 0, blocks_per_sm = 0, grid_max = 0;
-    sfx::DevTables tb{};
+    int max_pk = 0;             // max over table sets of local maxima that fit the piptrack bin range (multiple of 4)
+    std::vector<TableSet> sets;
     std::vector<void*> allocs;
     HostPath hp;
 };
+
+const TableSet* find_set(const DevCtx& c, int sr) {
+    for (const TableSet& t : c.sets)
+        if (t.sr == sr) return &t;
+    return nullptr;
+}
 
 DevCtx g_ctx[kMaxDev];
 std::mutex g_mu;
@@ -80,7 +92,7 @@ bool is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
-int do_extract(int device, const float* wave, int64_t row_stride, const int32_t* lengths, int64_t n_default,
+int do_extract(int device, int sr, const float* wave, int64_t row_stride, const int32_t* lengths, int64_t n_default,
                int64_t max_samples, int32_t B, int32_t n_mfcc, float* out, int64_t out_stride, void* ws,
                size_t ws_bytes, void* stream, const sfx_debug_out* dbg) {
     if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
@@ -91,10 +103,11 @@ int do_extract(int device, const float* wave, int64_t row_stride, const int32_t*
     if (max_samples < 1) return fail(SFX_ERR_ARG, "max_samples < 1");
     if (!lengths && (n_default < 1 || n_default > max_samples)) return fail(SFX_ERR_ARG, "n_default outside [1,max_samples]");
     DevCtx& c = g_ctx[device];
-    if (!c.ready) return fail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this device");
+    const TableSet* ts = c.ready ? find_set(c, sr) : nullptr;
+    if (!ts) return fail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this (device, sample rate)");
     CK(cudaSetDevice(device));
     const int Tmax = 1 + static_cast<int>(max_samples / sfx::kHop);
-    const size_t slice = sfx::cta_scratch_bytes(Tmax);
+    const size_t slice = sfx::cta_scratch_bytes(Tmax, c.max_pk);
     const int grid = std::min<int64_t>(B, c.grid_max);
     if (ws_bytes < sfx::kWsHeader + slice * static_cast<size_t>(grid))
         return fail(SFX_ERR_WORKSPACE, "workspace smaller than sfx_workspace_bytes(device, max_samples)");
@@ -103,7 +116,8 @@ int do_extract(int device, const float* wave, int64_t row_stride, const int32_t*
     p.B = B; p.n_mfcc = n_mfcc; p.out = out; p.out_stride = out_stride;
     p.ws = static_cast<unsigned char*>(ws); p.cta_scratch_bytes = static_cast<long long>(slice); p.Tmax = Tmax;
     p.aligned8 = ((reinterpret_cast<uintptr_t>(wave) & 7u) == 0 && (row_stride & 1) == 0) ? 1 : 0;
-    p.tb = c.tb;
+    p.tb = ts->tb;
+    p.max_pk = c.max_pk;
     if (dbg) p.dbg = *dbg;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaMemsetAsync(ws, 0, sfx::kWsHeader, st));
@@ -148,41 +162,44 @@ int sfx_init_tables(int device, const sfx_tables_host* t) {
         return fail(SFX_ERR_ARG, "mel_ps must be odd and fit the warp tile");
     if (t->pip_kmin < 1 || t->pip_kmax > sfx::kBins - 2 || t->pip_kmax < t->pip_kmin)
         return fail(SFX_ERR_ARG, "piptrack bin range outside [1,1023]");
-    if ((t->pip_kmax - t->pip_kmin + 2) / 2 > sfx::kMaxPk) return fail(SFX_ERR_ARG, "piptrack range exceeds peak capacity");
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (device >= ndev) return fail(SFX_ERR_CUDA, "no such CUDA device");
-    sfx_release(device);
     std::lock_guard<std::mutex> lk(g_mu);
     DevCtx& c = g_ctx[device];
+    if (c.ready && find_set(c, t->sr)) return SFX_OK;        // idempotent per (device, sr)
     CK(cudaSetDevice(device));
     cudaDeviceProp prop{};
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(SFX_ERR_CUDA, "libsfx_b200 is built for sm_100a only");
     c.sm_count = prop.multiProcessorCount;
+    TableSet set;
+    set.sr = t->sr;
     int rc;
     const float* f = nullptr;
     if ((rc = upload(c, t->hann, 2048, &f))) return rc;
-    c.tb.hann = reinterpret_cast<const float2*>(f);
+    set.tb.hann = reinterpret_cast<const float2*>(f);
     if ((rc = upload(c, t->tw1, 2048, &f))) return rc;
-    c.tb.tw1 = reinterpret_cast<const float2*>(f);
+    set.tb.tw1 = reinterpret_cast<const float2*>(f);
     if ((rc = upload(c, t->tw2, 2048, &f))) return rc;
-    c.tb.tw2 = reinterpret_cast<const float2*>(f);
+    set.tb.tw2 = reinterpret_cast<const float2*>(f);
     if ((rc = upload(c, t->mel_ab, 33 * 32 * 2, &f))) return rc;
-    c.tb.mel_ab = reinterpret_cast<const float2*>(f);
-    if ((rc = upload(c, t->mel_mask, 32, &c.tb.mel_mask))) return rc;
-    if ((rc = upload(c, t->mel_src, 128 * 3, &c.tb.mel_src))) return rc;
-    if ((rc = upload(c, t->chroma, static_cast<size_t>(sfx::kTunings) * sfx::kChroma * sfx::kPStride, &c.tb.chroma))) return rc;
+    set.tb.mel_ab = reinterpret_cast<const float2*>(f);
+    if ((rc = upload(c, t->mel_mask, 32, &set.tb.mel_mask))) return rc;
+    if ((rc = upload(c, t->mel_src, 128 * 3, &set.tb.mel_src))) return rc;
+    if ((rc = upload(c, t->chroma, static_cast<size_t>(sfx::kTunings) * sfx::kChroma * sfx::kPStride, &set.tb.chroma))) return rc;
     std::vector<double> dctT(static_cast<size_t>(sfx::kMels) * sfx::kMels);
     for (int k = 0; k < sfx::kMels; ++k)
         for (int m = 0; m < sfx::kMels; ++m) dctT[static_cast<size_t>(m) * sfx::kMels + k] = t->dct[static_cast<size_t>(k) * sfx::kMels + m];
-    if ((rc = upload(c, dctT.data(), dctT.size(), &c.tb.dctT))) return rc;
-    if ((rc = upload(c, t->edges, sfx::kTunings + 1, &c.tb.edges))) return rc;
-    c.tb.mel_ps = t->mel_ps; c.tb.mel_flush32 = t->mel_flush32;
-    c.tb.sr = t->sr; c.tb.kmin = t->pip_kmin; c.tb.kmax = t->pip_kmax;
+    if ((rc = upload(c, dctT.data(), dctT.size(), &set.tb.dctT))) return rc;
+    if ((rc = upload(c, t->edges, sfx::kTunings + 1, &set.tb.edges))) return rc;
+    set.tb.mel_ps = t->mel_ps; set.tb.mel_flush32 = t->mel_flush32;
+    set.tb.sr = t->sr; set.tb.kmin = t->pip_kmin; set.tb.kmax = t->pip_kmax;
     CK(sfx::configure_kernels(&c.blocks_per_sm));
     if (c.blocks_per_sm < 1) return fail(SFX_ERR_CUDA, "kernel does not fit on an SM");
     c.grid_max = c.sm_count * c.blocks_per_sm;
+    c.max_pk = std::max(c.max_pk, (((t->pip_kmax - t->pip_kmin + 2) / 2) + 3) & ~3);
+    c.sets.push_back(set);
     c.ready = true;
     return SFX_OK;
 }
@@ -193,25 +210,25 @@ size_t sfx_workspace_bytes(int device, int64_t max_samples) {
         return 0;
     }
     const int Tmax = 1 + static_cast<int>(max_samples / sfx::kHop);
-    return sfx::kWsHeader + sfx::cta_scratch_bytes(Tmax) * static_cast<size_t>(g_ctx[device].grid_max);
+    return sfx::kWsHeader + sfx::cta_scratch_bytes(Tmax, g_ctx[device].max_pk) * static_cast<size_t>(g_ctx[device].grid_max);
 }
 
-int sfx_extract(int device, const float* wave, int64_t row_stride, const int32_t* lengths, int64_t n_default,
+int sfx_extract(int device, int32_t sr, const float* wave, int64_t row_stride, const int32_t* lengths, int64_t n_default,
                 int64_t max_samples, int32_t B, int32_t n_mfcc, float* out, int64_t out_stride, void* workspace,
                 size_t workspace_bytes, void* stream) {
-    return do_extract(device, wave, row_stride, lengths, n_default, max_samples, B, n_mfcc, out, out_stride, workspace,
+    return do_extract(device, sr, wave, row_stride, lengths, n_default, max_samples, B, n_mfcc, out, out_stride, workspace,
                       workspace_bytes, stream, nullptr);
 }
 
-int sfx_extract_debug(int device, const float* wave, int64_t row_stride, const int32_t* lengths, int64_t n_default,
+int sfx_extract_debug(int device, int32_t sr, const float* wave, int64_t row_stride, const int32_t* lengths, int64_t n_default,
                       int64_t max_samples, int32_t B, int32_t n_mfcc, float* out, int64_t out_stride, void* workspace,
                       size_t workspace_bytes, void* stream, const sfx_debug_out* dbg) {
     if (!dbg) return fail(SFX_ERR_ARG, "null dbg");
-    return do_extract(device, wave, row_stride, lengths, n_default, max_samples, B, n_mfcc, out, out_stride, workspace,
+    return do_extract(device, sr, wave, row_stride, lengths, n_default, max_samples, B, n_mfcc, out, out_stride, workspace,
                       workspace_bytes, stream, dbg);
 }
 
-int sfx_extract_host(int device, const float* host_wave, int64_t row_stride, const int32_t* host_lengths,
+int sfx_extract_host(int device, int32_t sr, const float* host_wave, int64_t row_stride, const int32_t* host_lengths,
                      int64_t n_default, int32_t B, int32_t n_mfcc, float* host_out, int64_t out_stride,
                      int32_t chunk_clips) {
     if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
@@ -221,7 +238,7 @@ int sfx_extract_host(int device, const float* host_wave, int64_t row_stride, con
     if (row_stride < 1 || out_stride < n_mfcc + 16) return fail(SFX_ERR_ARG, "bad row_stride/out_stride");
     if (!host_lengths && (n_default < 1 || n_default > row_stride)) return fail(SFX_ERR_ARG, "n_default outside [1,row_stride]");
     DevCtx& c = g_ctx[device];
-    if (!c.ready) return fail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this device");
+    if (!c.ready || !find_set(c, sr)) return fail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this (device, sample rate)");
     CK(cudaSetDevice(device));
     int64_t max_samples = n_default;
     if (host_lengths) {
@@ -290,7 +307,7 @@ int sfx_extract_host(int device, const float* host_wave, int64_t row_stride, con
             CK(cudaMemcpyAsync(hp.d_len[s], host_lengths + c0, static_cast<size_t>(nb) * 4, cudaMemcpyHostToDevice, st));
             dlen = hp.d_len[s];
         }
-        rc = do_extract(device, hp.d_wave[s], dev_stride, dlen, n_default, max_samples, nb, n_mfcc, hp.d_out[s], out_w,
+        rc = do_extract(device, sr, hp.d_wave[s], dev_stride, dlen, n_default, max_samples, nb, n_mfcc, hp.d_out[s], out_w,
                         hp.d_ws[s], hp.ws_bytes, st, nullptr);
         if (rc) return rc;
         if (out_pinned) {

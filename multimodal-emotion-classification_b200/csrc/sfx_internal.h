@@ -18,7 +18,6 @@ constexpr int kTunings = SFX_N_TUNINGS;
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kExFloats = 32 * 33 * 2;   // per-warp float2[32][33] exchange tile, reused as the padded |X|^2 tile
-constexpr int kMaxPk = 180;              // piptrack peaks per frame: local maxima among <= 358 bins
 constexpr int kPartOff = 1088;           // offset of the mel partial-sum slots inside a warp's tile
 constexpr int kKeyCap = 16384;           // peak keys kept in shared memory during the median select
 constexpr size_t kWsHeader = 256;        // clip-queue counter lives in the first bytes of the workspace
@@ -50,14 +49,15 @@ struct Params {
     long long cta_scratch_bytes;
     int Tmax;
     int aligned8;
+    int max_pk;             // peak records per frame the scratch slice is sized for
     DevTables tb;
     sfx_debug_out dbg;
 };
 
 // bytes of scratch one CTA needs for clips of up to Tmax frames (multiple of 256)
-inline size_t cta_scratch_bytes(int Tmax) {
+inline size_t cta_scratch_bytes(int Tmax, int max_pk) {
     // |X|^2 rows, log-mel rows, peak records (float4), peak keys (u32, overflow path), peak bins (u8)
-    size_t b = static_cast<size_t>(Tmax) * (kPStride * 4 + kMels * 4 + kMaxPk * (16 + 4 + 1));
+    size_t b = static_cast<size_t>(Tmax) * (kPStride * 4 + kMels * 4 + static_cast<size_t>(max_pk) * (16 + 4 + 1));
     return (b + 255) & ~static_cast<size_t>(255);
 }
 

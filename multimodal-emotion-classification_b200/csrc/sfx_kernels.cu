@@ -123,7 +123,7 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 }
 __device__ __forceinline__ float sqrt_approx(float x) {
     float y;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 __device__ __forceinline__ unsigned fkey(float f) {      // order-preserving float -> uint
@@ -287,8 +287,8 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     float* gP = reinterpret_cast<float*>(slice);
     float* gL = gP + static_cast<size_t>(p.Tmax) * kPStride;
     float4* gRec = reinterpret_cast<float4*>(gL + static_cast<size_t>(p.Tmax) * kMels);
-    unsigned* gKey = reinterpret_cast<unsigned*>(gRec + static_cast<size_t>(p.Tmax) * kMaxPk);
-    unsigned char* gBin = reinterpret_cast<unsigned char*>(gKey + static_cast<size_t>(p.Tmax) * kMaxPk);
+    unsigned* gKey = reinterpret_cast<unsigned*>(gRec + static_cast<size_t>(p.Tmax) * p.max_pk);
+    unsigned char* gBin = reinterpret_cast<unsigned char*>(gKey + static_cast<size_t>(p.Tmax) * p.max_pk);
     int* counter = reinterpret_cast<int*>(p.ws);
 
     float* Pb = s_ex + warp * kExFloats;               // this warp's exchange / |X|^2 tile
@@ -313,12 +313,15 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         const float* x = p.wave + static_cast<long long>(clip) * p.row_stride;
 
         // ===================================== phase 1: frames =====================================
-        double acc_cent = 0.0, acc_roll = 0.0, acc_rms = 0.0;   // per-warp sums over its frames
+        // per-warp running sums live in shared memory (s_wacc[warp][0..2] = centroid, rolloff, rms; s_f = log-mel max)
+        if (lane < 3) s_wacc[warp * 16 + lane] = 0.0;
+        if (lane == 0) s_f[warp] = -FLT_MAX;
         int acc_zc = 0;
-        float gmax = -FLT_MAX;
-        float re[32], im[32];
-        if (warp < T) load_frame(x, n, warp, lane, aligned8, re, im);
+        __syncwarp();
+
         for (int t = warp; t < T; t += kWarps) {
+            float re[32], im[32];
+            load_frame(x, n, t, lane, aligned8, re, im);
             // ---- rms (librosa.feature.rms: zero pad, no window)
             float ss = 0.0f;
 #pragma unroll
@@ -473,18 +476,17 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 cent_t = (total < FLT_MIN) ? 0.0f : (num / total) * bin_hz;
                 roll_t = static_cast<float>(first) * bin_hz;
             }
-            acc_cent += static_cast<double>(cent_t);
-            acc_roll += static_cast<double>(roll_t);
-            acc_rms += static_cast<double>(rms_t);
+            if (lane == 0) {
+                s_wacc[warp * 16 + 0] += static_cast<double>(cent_t);
+                s_wacc[warp * 16 + 1] += static_cast<double>(roll_t);
+                s_wacc[warp * 16 + 2] += static_cast<double>(rms_t);
+            }
             __syncwarp();
-
-            // ---- prefetch the raw samples of this warp's next frame; they land while the rest of the tile
-            //      (log-mel gather, peak detection) is processed
-            if (t + kWarps < T) load_frame(x, n, t + kWarps, lane, aligned8, re, im);
 
             // ---- log-mel rows: filter m = 32*s + lane adds its (<= 3) partial sums in a fixed order
             {
                 float* Lg = gL + static_cast<size_t>(t) * kMels;
+                float gmax = -FLT_MAX;
 #pragma unroll
                 for (int s4 = 0; s4 < 4; ++s4) {
                     const int ms = msrc[s4];
@@ -497,16 +499,20 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                             p.dbg.logmel[(static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kMels + 32 * s4 + lane] = lm;
                     }
                 }
+                gmax = warp_max(gmax);
+                if (lane == 0) s_f[warp] = fmaxf(s_f[warp], gmax);
             }
 
             // ---- piptrack peak detection on the power spectrum (bins kmin..kmax); the per-peak arithmetic
             //      (parabolic shift, pitch, tuning residual) is done in phase 2 on the compacted records
             {
                 const float ref = __fmul_rn(0.1f, pmax);
-                for (int k0 = tb.kmin; k0 <= tb.kmax; k0 += 32) {
-                    const int k = min(k0 + lane, tb.kmax);
-                    const bool valid = (k0 + lane) <= tb.kmax;
-                    const float pm = Pb[pidx(k - 1)], pc = Pb[pidx(k)], pp = Pb[pidx(k + 1)];
+                const int kfirst = tb.kmin + lane;
+                const float* q = Pb + pidx(kfirst - 1);
+                const int d0 = pidx(kfirst) - pidx(kfirst - 1), d1 = pidx(kfirst + 1) - pidx(kfirst - 1);
+                for (int k = kfirst; k - lane <= tb.kmax; k += 32, q += 33) {
+                    const bool valid = k <= tb.kmax;
+                    const float pm = q[0], pc = q[d0], pp = q[d1];
                     const bool pk = valid && pc > ref && pc > pm && pc >= pp;
                     const unsigned m = __ballot_sync(0xffffffffu, pk);
                     if (m) {
@@ -531,14 +537,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         // per-warp partials
         {
             const int zc = warp_sum_i(acc_zc);
-            gmax = warp_max(gmax);
-            if (lane == 0) {
-                s_wacc[warp * 16 + 0] = acc_cent;
-                s_wacc[warp * 16 + 1] = acc_roll;
-                s_wacc[warp * 16 + 2] = acc_rms;
-                s_i[8 + warp] = zc;
-                s_f[warp] = gmax;
-            }
+            if (lane == 0) s_i[8 + warp] = zc;
         }
         __syncthreads();
 
@@ -554,6 +553,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         if (np > 0) {
             // ---- per-peak arithmetic of librosa.piptrack / pitch_tuning at full lane occupancy
             unsigned* keys = (np <= kKeyCap) ? reinterpret_cast<unsigned*>(s_ex) : gKey;
+#pragma unroll 2
             for (int i = tid; i < np; i += kThreads) {
                 const float4 rec = gRec[i];
                 const float pm = rec.x, pc = rec.y, pp = rec.z;
@@ -680,13 +680,22 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 float acc[48];
 #pragma unroll
                 for (int i = 0; i < 48; ++i) acc[i] = 0.0f;
-#pragma unroll 2
+                // |X|^2 rows come from the scratch slice (L2/HBM): loads for step j+1 are issued before the FMAs of step j
+                float4 pn[4];
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+                    pn[f] = (f < nf) ? *reinterpret_cast<const float4*>(Pt + f * kPStride + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
                 for (int j = 0; j < 8; ++j) {
                     const int k = 4 * lane + 128 * j;
                     float4 pv[4];
 #pragma unroll
-                    for (int f = 0; f < 4; ++f)
-                        pv[f] = (f < nf) ? *reinterpret_cast<const float4*>(Pt + f * kPStride + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int f = 0; f < 4; ++f) pv[f] = pn[f];
+                    if (j < 7) {
+#pragma unroll
+                        for (int f = 0; f < 4; ++f)
+                            if (f < nf) pn[f] = *reinterpret_cast<const float4*>(Pt + f * kPStride + k + 128);
+                    }
 #pragma unroll
                     for (int c = 0; c < kChroma; ++c) {
                         const float4 w = *reinterpret_cast<const float4*>(sW + c * kPStride + k);

@@ -56,14 +56,14 @@ def load():
     lib.sfx_init_tables.argtypes = [C.c_int, C.POINTER(TablesHost)]
     lib.sfx_workspace_bytes.restype = C.c_size_t
     lib.sfx_workspace_bytes.argtypes = [C.c_int, C.c_int64]
-    common = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+    common = [C.c_int, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
               C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.sfx_extract.restype = C.c_int
     lib.sfx_extract.argtypes = common
     lib.sfx_extract_debug.restype = C.c_int
     lib.sfx_extract_debug.argtypes = common + [C.POINTER(DebugOut)]
     lib.sfx_extract_host.restype = C.c_int
-    lib.sfx_extract_host.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+    lib.sfx_extract_host.argtypes = [C.c_int, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_int64, C.c_int32]
     lib.sfx_release.restype = C.c_int
     lib.sfx_release.argtypes = [C.c_int]

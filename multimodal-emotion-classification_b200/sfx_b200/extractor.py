@@ -49,12 +49,13 @@ class SpeechFeatureExtractor:
 
     # ------------------------------------------------------------------ workspace
     def _workspace(self, max_samples: int) -> torch.Tensor:
-        if self._ws is None or max_samples > self._ws_samples:
-            nbytes = self.lib.sfx_workspace_bytes(self.index, int(max_samples))
-            if nbytes == 0:
-                raise _lib.SfxError(-1, self.lib.sfx_last_error().decode())
+        # re-queried every call: the requirement also grows when another sample rate's tables are uploaded
+        nbytes = self.lib.sfx_workspace_bytes(self.index, int(max(max_samples, self._ws_samples)))
+        if nbytes == 0:
+            raise _lib.SfxError(-1, self.lib.sfx_last_error().decode())
+        if self._ws is None or nbytes > self._ws.numel():
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self._ws_samples = int(max_samples)
+        self._ws_samples = int(max(max_samples, self._ws_samples))
         return self._ws
 
     # ------------------------------------------------------------------ device path
@@ -87,7 +88,7 @@ class SpeechFeatureExtractor:
             return out
         ws = self._workspace(max_samples)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        args = (self.index, waves.data_ptr(), waves.stride(0), lengths.data_ptr() if lengths is not None else None,
+        args = (self.index, self.sr, waves.data_ptr(), waves.stride(0), lengths.data_ptr() if lengths is not None else None,
                 n_default, max_samples, B, n_mfcc, out.data_ptr(), out.stride(0), ws.data_ptr(), ws.numel(),
                 C.c_void_p(stream))
         with torch.cuda.device(self.index):
@@ -131,7 +132,7 @@ class SpeechFeatureExtractor:
         if B == 0:
             return out
         with torch.cuda.device(self.index):
-            _lib.check(self.lib.sfx_extract_host(self.index, waves.ctypes.data, waves.strides[0] // 4, lp, n_default,
+            _lib.check(self.lib.sfx_extract_host(self.index, self.sr, waves.ctypes.data, waves.strides[0] // 4, lp, n_default,
                                                  B, n_mfcc, out.ctypes.data, out.strides[0] // 4, int(chunk_clips)))
         nchunk = 1 if chunk_clips <= 0 else -(-B // chunk_clips)
         self.launches += nchunk * self.lib.sfx_launches_per_extract()

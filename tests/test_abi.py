@@ -34,9 +34,9 @@ def test_abi_version_and_argument_validation():
     assert lib.sfx_abi_version() == 1
     assert lib.sfx_launches_per_extract() == 1
     # argument validation happens before any CUDA work
-    rc = lib.sfx_extract(99, None, 0, None, 0, 0, 1, 40, None, 56, None, 0, None)
+    rc = lib.sfx_extract(99, 22050, None, 0, None, 0, 0, 1, 40, None, 56, None, 0, None)
     assert rc == -1 and b"device" in lib.sfx_last_error()
-    rc = lib.sfx_extract(0, None, 0, None, 0, 0, 1, 400, None, 56, None, 0, None)
+    rc = lib.sfx_extract(0, 22050, None, 0, None, 0, 0, 1, 400, None, 56, None, 0, None)
     assert rc == -1
     assert lib.sfx_workspace_bytes(0, 66150) == 0 or torch.cuda.is_available()
 
@@ -50,7 +50,7 @@ def test_no_cpu_fallback():
         get_extractor()
     x = np.zeros((1, 66150), dtype=np.float32)
     out = np.zeros((1, 56), dtype=np.float32)
-    rc = lib.sfx_extract_host(0, x.ctypes.data, 66150, None, 66150, 1, 40, out.ctypes.data, 56, 0)
+    rc = lib.sfx_extract_host(0, 22050, x.ctypes.data, 66150, None, 66150, 1, 40, out.ctypes.data, 56, 0)
     assert rc == -3                                   # SFX_ERR_NOT_INIT: nothing ran, nothing was computed
     from preprocessing.audio_preprocessing import extract_mfcc
     with pytest.raises(NoCudaDeviceError):
