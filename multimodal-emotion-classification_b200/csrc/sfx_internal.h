@@ -19,7 +19,7 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kExFloats = 32 * 33 * 2;   // per-warp float2[32][33] exchange tile, reused as the padded |X|^2 tile
 constexpr int kPartOff = 1088;           // offset of the mel partial-sum slots inside a warp's tile
-constexpr int kKeyCap = 16384;           // peak keys kept in shared memory during the median select
+constexpr int kKeyCap = 13312;           // peak keys (u32) + bins (u8) kept in shared memory during the median select
 constexpr size_t kWsHeader = 256;        // clip-queue counter lives in the first bytes of the workspace
 
 struct DevTables {

@@ -225,6 +225,61 @@ __device__ __forceinline__ float reduce_scatter16(float (&v)[16], int lane) {
     return v[0];
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+// One chroma tile: NF consecutive frames x 12 chroma for the warp; lane owns bins 4*lane + 128*j.  The |X|^2 rows come
+// from the scratch slice (L2/HBM): the loads of step j+1 are issued before the FMAs of step j.  Returns through `red`
+// (shared, >= 48 floats): red[f*12 + c] = sum over bins < 1024 of W[c][k] * P[f][k].
+template <int NF>
+__device__ __forceinline__ void chroma_tile(const float* __restrict__ sW, const float* Pt, float* red, int lane) {
+    float acc[NF * kChroma];
+#pragma unroll
+    for (int i = 0; i < NF * kChroma; ++i) acc[i] = 0.0f;
+    float4 pn[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) pn[f] = *reinterpret_cast<const float4*>(Pt + f * kPStride + 4 * lane);
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+        const int k = 4 * lane + 128 * j;
+        float4 pv[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) pv[f] = pn[f];
+        if (j < 7) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) pn[f] = *reinterpret_cast<const float4*>(Pt + f * kPStride + k + 128);
+        }
+#pragma unroll
+        for (int c = 0; c < kChroma; ++c) {
+            const float4 w = *reinterpret_cast<const float4*>(sW + c * kPStride + k);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                float a = acc[f * kChroma + c];
+                a = fmaf(w.x, pv[f].x, a);
+                a = fmaf(w.y, pv[f].y, a);
+                a = fmaf(w.z, pv[f].z, a);
+                a = fmaf(w.w, pv[f].w, a);
+                acc[f * kChroma + c] = a;
+            }
+        }
+    }
+    // warp totals: value i ends up in lane i (i < 32) resp. lanes (i-32), (i-32)^16
+    constexpr int NV = NF * kChroma;
+    {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (i < NV) ? acc[i] : 0.0f;
+        const float r = reduce_scatter32(v, lane);
+        if (lane < NV) red[lane] = r;
+    }
+    if constexpr (NV > 32) {
+        float u[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) u[i] = (32 + i < NV) ? acc[32 + i] : 0.0f;
+        const float r16 = reduce_scatter16(u, lane);
+        if (lane < NV - 32) red[32 + lane] = r16;
+    }
+}
+
 // raw samples of STFT frame t (zero padded) -> re[m1] = x[2m], im[m1] = x[2m+1], m = 32*m1 + lane
 __device__ __forceinline__ void load_frame(const float* __restrict__ x, long long n, int t, int lane, bool aligned8,
                                            float (&re)[32], float (&im)[32]) {
@@ -332,8 +387,12 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
             // ---- zero crossings of hop t (samples [512t, 512t+512)), weighted by how many frames see them
             int zc_hop = 0;
             {
+                // librosa.zero_crossings(threshold=1e-10, zero_pos=True): sign(x) := (double)x < -1e-10, which for float32
+                // x is exactly x < -9.99999944e-11f (0xaedbe6fe, the smallest float32 not below -1e-10)
+                const float zthr = __uint_as_float(0xaedbe6feu);
                 int zc = 0, zc_first = 0;
-                const long long ib = static_cast<long long>(kHop) * t;
+                const int ib = kHop * t + 2 * lane;
+                const int nm1 = static_cast<int>(n) - 1;
                 sfor<8>([&](auto R) {
                     constexpr int r = decltype(R)::value;
                     constexpr int m1 = 16 + r;
@@ -341,12 +400,10 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                     const float up = __shfl_up_sync(0xffffffffu, e1, 1);
                     const float wrap = __shfl_sync(0xffffffffu, im[m1 - 1], 31);
                     const float prev = lane == 0 ? wrap : up;
-                    const long long i0 = ib + 2 * (32 * r + lane);
-                    const bool sp = static_cast<double>(prev) < -1e-10;
-                    const bool sa = static_cast<double>(e0) < -1e-10;
-                    const bool sb = static_cast<double>(e1) < -1e-10;
-                    const int c0 = (i0 >= 1 && i0 <= n - 1 && sa != sp) ? 1 : 0;
-                    const int c1 = (i0 + 1 <= n - 1 && sb != sa) ? 1 : 0;
+                    const int i0 = ib + 64 * r;
+                    const bool sp = prev < zthr, sa = e0 < zthr, sb = e1 < zthr;
+                    const int c0 = (i0 >= 1 && i0 <= nm1 && sa != sp) ? 1 : 0;
+                    const int c1 = (i0 + 1 <= nm1 && sb != sa) ? 1 : 0;
                     zc += c0 + c1;
                     if (r == 0 && lane == 0) zc_first = c0;
                 });
@@ -384,35 +441,54 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
             __syncwarp();
             fft32(re, im);
 
-            // ---- real-FFT unpack: bin k = lane + 32*k2; partner bin 1024-k lives in lane (32-lane)&31
+            // ---- real-FFT unpack, one conjugate pair per step: lane holds Z[lane + 32*k2]; for k2 < 16 it forms
+            //      X[k] and X[1024-k] (k = lane + 32*k2) from Z[k] and Z[1024-k] (lane (32-lane)&31, register 31-k2;
+            //      lane 0 pairs with its own register (32-k2)&31).  Bin 512 (self-paired) is lane 0's register 16.
             float pmax = 0.0f;
-            float* Pg = gP + static_cast<size_t>(t) * kPStride + lane;
-            float* Pbl = Pb + lane;
-            const int plane = (32 - lane) & 31;
-            sfor<32>([&](auto K) {
-                constexpr int k2 = decltype(K)::value;
-                constexpr int a = brev5(k2), b = brev5(31 - k2), c = brev5((32 - k2) & 31);
-                const float zr = re[a], zi = im[a];
-                float pr = __shfl_sync(0xffffffffu, re[b], plane);
-                float pi = __shfl_sync(0xffffffffu, im[b], plane);
-                if (lane == 0) { pr = re[c]; pi = im[c]; }
-                const float2 w = s_tw2[k2 * 32 + lane];
-                const float er = zr + pr, ei = zi - pi, orr = zr - pr, oi = zi + pi;
-                const float xr = fmaf(0.5f, er, fmaf(w.x, oi, -(w.y * orr)));
-                const float xi = fmaf(0.5f, ei, -fmaf(w.x, orr, w.y * oi));
-                const float P = fmaf(xr, xr, xi * xi);
-                pmax = fmaxf(pmax, P);
-                Pbl[33 * k2] = P;
-                Pg[32 * k2] = P;
-            });
             {
-                const float ny = re[0] - im[0];      // X[1024] = Re Z[0] - Im Z[0] (lane 0)
-                const float Pn = ny * ny;
-                if (lane == 0) { Pb[1024 + 32] = Pn; Pg[1024] = Pn; pmax = fmaxf(pmax, Pn); }
+                float* Pg = gP + static_cast<size_t>(t) * kPStride;
+                float* PgL = Pg + lane;
+                float* PgU = Pg + 1024 - lane;
+                float* PbL = Pb + lane;
+                float* PbU = Pb + (lane == 0 ? 1056 : 1055 - lane);
+                const int plane = (32 - lane) & 31;
+                sfor<16>([&](auto K) {
+                    constexpr int k2 = decltype(K)::value;
+                    constexpr int a = brev5(k2), b = brev5(31 - k2), c = brev5((32 - k2) & 31);
+                    const float zr = re[a], zi = im[a];
+                    float pr = __shfl_sync(0xffffffffu, re[b], plane);
+                    float pi = __shfl_sync(0xffffffffu, im[b], plane);
+                    if (lane == 0) { pr = re[c]; pi = im[c]; }
+                    const float2 w = s_tw2[k2 * 32 + lane];          // (0.5 cos, 0.5 sin)(2 pi k / 2048)
+                    const float er = zr + pr, ei = zi - pi, orr = zr - pr, oi = zi + pi;
+                    const float u = fmaf(w.x, orr, w.y * oi);         // Re(w O)/2
+                    const float v = fmaf(w.x, oi, -(w.y * orr));      // Im(w O)/2
+                    const float xr = fmaf(0.5f, er, v), xi = fmaf(0.5f, ei, -u);       // X[k]
+                    const float yr = fmaf(0.5f, er, -v), yi = fmaf(-0.5f, ei, -u);     // X[1024-k]
+                    const float P = fmaf(xr, xr, xi * xi);
+                    const float Q = fmaf(yr, yr, yi * yi);
+                    pmax = fmaxf(pmax, fmaxf(P, Q));
+                    PbL[33 * k2] = P;
+                    PgL[32 * k2] = P;
+                    PbU[-33 * k2] = Q;
+                    PgU[-32 * k2] = Q;
+                });
+                if (lane == 0) {
+                    constexpr int h = brev5(16);
+                    const float P512 = fmaf(re[h], re[h], im[h] * im[h]);
+                    Pb[512 + 16] = P512;
+                    Pg[512] = P512;
+                    pmax = fmaxf(pmax, P512);
+                }
             }
             pmax = warp_max(pmax);
             __syncwarp();
-
+            // ---- warm L2 with the newest hop of this warp's next frame (its other three hops are shared with
+            //      frames the neighbouring warps are reading now)
+            {
+                const long long nh = static_cast<long long>(kHop) * (t + kWarps) + kHop + lane * 32;
+                if (lane < 16 && nh < n) prefetch_l2(x + nh);
+            }
             if (kDebug) {
                 if (p.dbg.P && t < p.dbg.T_dbg) {
                     float* dP = p.dbg.P + (static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kPStride;
@@ -508,18 +584,38 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
             {
                 const float ref = __fmul_rn(0.1f, pmax);
                 const int kfirst = tb.kmin + lane;
-                const float* q = Pb + pidx(kfirst - 1);
+                const float* q0 = Pb + pidx(kfirst - 1);
                 const int d0 = pidx(kfirst) - pidx(kfirst - 1), d1 = pidx(kfirst + 1) - pidx(kfirst - 1);
-                for (int k = kfirst; k - lane <= tb.kmax; k += 32, q += 33) {
-                    const bool valid = k <= tb.kmax;
-                    const float pm = q[0], pc = q[d0], pp = q[d1];
-                    const bool pk = valid && pc > ref && pc > pm && pc >= pp;
-                    const unsigned m = __ballot_sync(0xffffffffu, pk);
-                    if (m) {
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(&s_i[1], __popc(m));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (pk) gRec[base + __popc(m & ((1u << lane) - 1u))] = make_float4(pm, pc, pp, __int_as_float(k));
+                const int nrows = (tb.kmax - tb.kmin + 32) >> 5;          // <= 16 (bins 1..1023, 32 per row)
+                const unsigned lt = (1u << lane) - 1u;
+                unsigned flags = 0;                                      // bit r: this lane's bin of row r is a peak
+                int total = 0;
+                unsigned offs[8];                                        // two 16-bit record offsets per register
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    if ((r & 1) == 0) offs[r >> 1] = 0;
+                    if (r < nrows) {
+                        const float* q = q0 + 33 * r;
+                        const bool valid = kfirst + 32 * r <= tb.kmax;
+                        const float pm = q[0], pc = q[d0], pp = q[d1];
+                        const bool pk = valid && pc > ref && pc > pm && pc >= pp;
+                        const unsigned m = __ballot_sync(0xffffffffu, pk);
+                        if (pk) flags |= 1u << r;
+                        offs[r >> 1] |= static_cast<unsigned>(total + __popc(m & lt)) << (16 * (r & 1));
+                        total += __popc(m);
+                    }
+                }
+                if (total) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_i[1], total);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        if (flags & (1u << r)) {
+                            const float* q = q0 + 33 * r;
+                            const int pos = base + static_cast<int>((offs[r >> 1] >> (16 * (r & 1))) & 0xffffu);
+                            gRec[pos] = make_float4(q[0], q[d0], q[d1], __int_as_float(kfirst + 32 * r));
+                        }
                     }
                 }
             }
@@ -552,35 +648,46 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         int nsel = 0;
         if (np > 0) {
             // ---- per-peak arithmetic of librosa.piptrack / pitch_tuning at full lane occupancy
-            unsigned* keys = (np <= kKeyCap) ? reinterpret_cast<unsigned*>(s_ex) : gKey;
-#pragma unroll 2
-            for (int i = tid; i < np; i += kThreads) {
-                const float4 rec = gRec[i];
-                const float pm = rec.x, pc = rec.y, pp = rec.z;
-                const int k = __float_as_int(rec.w);
-                const float sum = __fadd_rn(pp, pm);
-                const float dif = __fsub_rn(pp, pm);
-                const double a = static_cast<double>(sum) - 2.0 * static_cast<double>(pc);
-                const double b = static_cast<double>(dif) * 0.5;
-                const float shift = (fabs(b) >= fabs(a)) ? 0.0f : static_cast<float>(-b / a);
-                const float avg = dif * 0.5f;
-                const float dskew = __fmul_rn(__fmul_rn(0.5f, avg), shift);
-                const float mag = __fadd_rn(pc, dskew);
-                const double pitch_d = (static_cast<double>(k) + static_cast<double>(shift)) *
-                                       static_cast<double>(tb.sr) / static_cast<double>(kNfft);
-                const float pitch = static_cast<float>(pitch_d);
-                // pitch_tuning: mod(12*log2(f/27.5), 1) in float32, wrapped to [-0.5, 0.5)
-                const float o = log2f(__fdiv_rn(pitch, 27.5f));
-                const float v = __fmul_rn(12.0f, o);
-                float res = v - floorf(v);
-                if (res >= 0.5f) res = res - 1.0f;
-                const double rd = static_cast<double>(res);
-                int bi = static_cast<int>(floor((rd + 0.5) * 100.0));
-                bi = max(0, min(kTunings - 1, bi));
-                while (bi > 0 && rd < s_edges[bi]) --bi;
-                while (bi < kTunings - 1 && rd >= s_edges[bi + 1]) ++bi;
-                keys[i] = fkey(mag);
-                gBin[i] = static_cast<unsigned char>(bi);
+            const bool in_smem = np <= kKeyCap;
+            unsigned* keys = in_smem ? reinterpret_cast<unsigned*>(s_ex) : gKey;
+            unsigned char* bins = in_smem ? reinterpret_cast<unsigned char*>(s_ex + kKeyCap) : gBin;
+            for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
+                float4 recs[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * kThreads;
+                    recs[u] = (i < np) ? gRec[i] : make_float4(0.f, 1.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * kThreads;
+                    if (i >= np) break;
+                    const float pm = recs[u].x, pc = recs[u].y, pp = recs[u].z;
+                    const int k = __float_as_int(recs[u].w);
+                    const float sum = __fadd_rn(pp, pm);
+                    const float dif = __fsub_rn(pp, pm);
+                    const double a = static_cast<double>(sum) - 2.0 * static_cast<double>(pc);
+                    const double b = static_cast<double>(dif) * 0.5;
+                    const float shift = (fabs(b) >= fabs(a)) ? 0.0f : static_cast<float>(-b / a);
+                    const float avg = dif * 0.5f;
+                    const float dskew = __fmul_rn(__fmul_rn(0.5f, avg), shift);
+                    const float mag = __fadd_rn(pc, dskew);
+                    const double pitch_d = (static_cast<double>(k) + static_cast<double>(shift)) *
+                                           static_cast<double>(tb.sr) / static_cast<double>(kNfft);
+                    const float pitch = static_cast<float>(pitch_d);
+                    // pitch_tuning: mod(12*log2(f/27.5), 1) in float32, wrapped to [-0.5, 0.5)
+                    const float o = log2f(__fdiv_rn(pitch, 27.5f));
+                    const float v = __fmul_rn(12.0f, o);
+                    float res = v - floorf(v);
+                    if (res >= 0.5f) res = res - 1.0f;
+                    const double rd = static_cast<double>(res);
+                    int bi = static_cast<int>(floor((rd + 0.5) * 100.0));
+                    bi = max(0, min(kTunings - 1, bi));
+                    while (bi > 0 && rd < s_edges[bi]) --bi;
+                    while (bi < kTunings - 1 && rd >= s_edges[bi + 1]) ++bi;
+                    keys[i] = fkey(mag);
+                    bins[i] = static_cast<unsigned char>(bi);
+                }
             }
             __syncthreads();
             int cle = 0;
@@ -608,7 +715,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
             for (int i = tid; i < 128; i += kThreads) s_hist[i] = 0;
             __syncthreads();
             for (int i = tid; i < np; i += kThreads)
-                if (keys[i] >= kthr) atomicAdd(&s_hist[gBin[i]], 1);
+                if (keys[i] >= kthr) atomicAdd(&s_hist[bins[i]], 1);
             __syncthreads();
             if (warp == 0) {
                 int bc = -1, bi = 1 << 20, tot = 0;
@@ -666,62 +773,28 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         }
 
         // ===================================== phase 3b: chroma ====================================
-        // warp tile = 4 frames x 12 chroma; lane owns bins 4*lane + 128*j (float4), bin 1024 is added at the end
+        // warp w owns a contiguous, balanced range of frames and walks it in tiles of <= 4 frames x 12 chroma;
+        // lane owns bins 4*lane + 128*j (float4); bin 1024 is added when the frame is normalised
         {
             double cacc[kChroma];
 #pragma unroll
             for (int c = 0; c < kChroma; ++c) cacc[c] = 0.0;
             float* red = s_ex + kChroma * kPStride + warp * 64;
-            const int ntiles = (T + 3) >> 2;
-            for (int tile = warp; tile < ntiles; tile += kWarps) {
-                const int t0 = tile * 4;
-                const int nf = min(4, T - t0);
+            const int fbase = T / kWarps, frem = T % kWarps;
+            const int f_lo = warp * fbase + min(warp, frem);
+            const int f_hi = f_lo + fbase + (warp < frem ? 1 : 0);
+            for (int t0 = f_lo; t0 < f_hi; t0 += 4) {
+                const int nf = min(4, f_hi - t0);
                 const float* Pt = gP + static_cast<size_t>(t0) * kPStride;
-                float acc[48];
-#pragma unroll
-                for (int i = 0; i < 48; ++i) acc[i] = 0.0f;
-                // |X|^2 rows come from the scratch slice (L2/HBM): loads for step j+1 are issued before the FMAs of step j
-                float4 pn[4];
-#pragma unroll
-                for (int f = 0; f < 4; ++f)
-                    pn[f] = (f < nf) ? *reinterpret_cast<const float4*>(Pt + f * kPStride + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-                for (int j = 0; j < 8; ++j) {
-                    const int k = 4 * lane + 128 * j;
-                    float4 pv[4];
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) pv[f] = pn[f];
-                    if (j < 7) {
-#pragma unroll
-                        for (int f = 0; f < 4; ++f)
-                            if (f < nf) pn[f] = *reinterpret_cast<const float4*>(Pt + f * kPStride + k + 128);
-                    }
-#pragma unroll
-                    for (int c = 0; c < kChroma; ++c) {
-                        const float4 w = *reinterpret_cast<const float4*>(sW + c * kPStride + k);
-#pragma unroll
-                        for (int f = 0; f < 4; ++f) {
-                            float a = acc[f * kChroma + c];
-                            a = fmaf(w.x, pv[f].x, a);
-                            a = fmaf(w.y, pv[f].y, a);
-                            a = fmaf(w.z, pv[f].z, a);
-                            a = fmaf(w.w, pv[f].w, a);
-                            acc[f * kChroma + c] = a;
-                        }
-                    }
+                if (t0 + 4 < f_hi) {                      // next tile's rows -> L2 while this one is computed
+                    const char* nx = reinterpret_cast<const char*>(Pt + 4 * kPStride);
+                    const int nbytes = min(4, f_hi - t0 - 4) * kPStride * 4;
+                    for (int o = lane * 128; o < nbytes; o += 32 * 128) prefetch_l2(nx + o);
                 }
-                // lane l ends up with the warp totals of acc[l] (and lanes l, l^16 with acc[32 + (l & 15)])
-                {
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = acc[i];
-                    red[lane] = reduce_scatter32(v, lane);
-                    float u[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) u[i] = acc[32 + i];
-                    const float r16 = reduce_scatter16(u, lane);
-                    if (lane < 16) red[32 + lane] = r16;
-                }
+                if (nf == 4) chroma_tile<4>(sW, Pt, red, lane);
+                else if (nf == 3) chroma_tile<3>(sW, Pt, red, lane);
+                else if (nf == 2) chroma_tile<2>(sW, Pt, red, lane);
+                else chroma_tile<1>(sW, Pt, red, lane);
                 __syncwarp();
                 if (lane < nf) {
                     const float pn = Pt[lane * kPStride + 1024];            // Nyquist bin of frame t0 + lane
