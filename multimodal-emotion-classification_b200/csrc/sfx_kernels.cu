@@ -59,51 +59,56 @@ __host__ __device__ constexpr float cos32(int q) {
 // sin(2*pi*q/32) = cos(2*pi*(8-q)/32) for q <= 8, cos(2*pi*(q-8)/32) for q in (8,16)
 __host__ __device__ constexpr float sin32x(int q) { return q <= 8 ? cos32(8 - q) : cos32(q - 8); }
 
-// (r + i*im) *= exp(-2*pi*i*Q/32)
+// DIT butterfly on (a, b) with twiddle w = exp(-2*pi*i*Q/32) = (c, -s):  a' = a + w*b,  b' = a - w*b.
+// Non-trivial twiddles use the 6-FMA "tangent" form: w*b = c*(br + t*bi, bi - t*br) with t = s/c when |c| >= |s|,
+// and w*b = s*(t*br + bi, t*bi - br) with t = c/s otherwise (|t| <= 1 in both cases).
 template <int Q>
-__device__ __forceinline__ void mul_w32(float& r, float& i) {
-    constexpr float kS = 0.70710678118654752440f;
+__device__ __forceinline__ void dit_bfly(float& ar, float& ai, float& br, float& bi) {
     if constexpr (Q == 0) {
-    } else if constexpr (Q == 8) {          // * (-i)
-        const float t = r; r = i; i = -t;
-    } else if constexpr (Q == 4) {          // * (1 - i)/sqrt2
-        const float t = (r + i) * kS; i = (i - r) * kS; r = t;
-    } else if constexpr (Q == 12) {         // * (-1 - i)/sqrt2
-        const float t = (i - r) * kS; i = -(r + i) * kS; r = t;
+        const float xr = ar - br, xi = ai - bi;
+        ar += br; ai += bi; br = xr; bi = xi;
+    } else if constexpr (Q == 8) {          // w = -i: w*b = (bi, -br)
+        const float xr = ar - bi, xi = ai + br;
+        ar += bi; ai -= br; br = xr; bi = xi;
     } else {
-        constexpr float c = cos32(Q), s = sin32x(Q);   // W = c - i*s
-        const float t = fmaf(r, c, i * s);
-        i = fmaf(i, c, -(r * s));
-        r = t;
+        constexpr float c = cos32(Q), sn = sin32x(Q);
+        constexpr bool use_c = (c >= 0 ? c : -c) >= sn;        // sn >= 0 for Q in (0, 16)
+        if constexpr (use_c) {
+            constexpr float t = sn / c;
+            const float pr = fmaf(t, bi, br);
+            const float pi = fmaf(-t, br, bi);
+            br = fmaf(-c, pr, ar); bi = fmaf(-c, pi, ai);
+            ar = fmaf(c, pr, ar);  ai = fmaf(c, pi, ai);
+        } else {
+            constexpr float t = c / sn;
+            const float pr = fmaf(t, br, bi);
+            const float pi = fmaf(t, bi, -br);
+            br = fmaf(-sn, pr, ar); bi = fmaf(-sn, pi, ai);
+            ar = fmaf(sn, pr, ar);  ai = fmaf(sn, pi, ai);
+        }
     }
 }
 
-// radix-2 DIF stage of half-size H over 32 register-resident points
+// radix-2 DIT stage of half-size H on the bit-reversed view v[p] = reg[brev5(p)]
 template <int H>
-__device__ __forceinline__ void dif_stage(float (&re)[32], float (&im)[32]) {
+__device__ __forceinline__ void dit_stage(float (&re)[32], float (&im)[32]) {
     sfor<16 / H>([&](auto B) {
         sfor<H>([&](auto J) {
-            constexpr int i0 = decltype(B)::value * 2 * H + decltype(J)::value;
-            constexpr int i1 = i0 + H;
+            constexpr int p0 = decltype(B)::value * 2 * H + decltype(J)::value;
+            constexpr int i0 = brev5(p0), i1 = brev5(p0 + H);
             constexpr int Q = decltype(J)::value * (16 / H);
-            const float ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
-            re[i0] = ar + br;
-            im[i0] = ai + bi;
-            float dr = ar - br, di = ai - bi;
-            mul_w32<Q>(dr, di);
-            re[i1] = dr;
-            im[i1] = di;
+            dit_bfly<Q>(re[i0], im[i0], re[i1], im[i1]);
         });
     });
 }
 
-// 32-point complex FFT in registers; X[k] ends up in slot brev5(k)
+// 32-point complex FFT in registers: natural-order input x[n] in slot n, output X[k] in slot brev5(k)
 __device__ __forceinline__ void fft32(float (&re)[32], float (&im)[32]) {
-    dif_stage<16>(re, im);
-    dif_stage<8>(re, im);
-    dif_stage<4>(re, im);
-    dif_stage<2>(re, im);
-    dif_stage<1>(re, im);
+    dit_stage<1>(re, im);
+    dit_stage<2>(re, im);
+    dit_stage<4>(re, im);
+    dit_stage<8>(re, im);
+    dit_stage<16>(re, im);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -542,10 +547,12 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 if (lane == 0) exc = 0.0f;
                 const float total = __shfl_sync(0xffffffffu, inc, 31);
                 const float thr = __fmul_rn(0.85f, total);
-                int first = 1024;
+                // first bin whose cumulative |X| reaches the threshold = number of (monotone) prefix sums below it
+                const float thrL = thr - exc;
+                int cnt = 0;
 #pragma unroll
-                for (int j = 31; j >= 0; --j)
-                    if (exc + s[j] >= thr) first = 32 * lane + j;
+                for (int j = 0; j < 32; ++j) cnt += (s[j] < thrL) ? 1 : 0;
+                int first = (cnt < 32) ? 32 * lane + cnt : 1024;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
                 const float num = warp_sum(fmaf(32.0f * lane, run, ks));
@@ -567,7 +574,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 for (int s4 = 0; s4 < 4; ++s4) {
                     const int ms = msrc[s4];
                     const float mel = (part[ms & 1023] + part[(ms >> 10) & 1023]) + part[ms >> 20];
-                    const float lm = 10.0f * log10f(fmaxf(1e-10f, mel));
+                    const float lm = 3.01029995663981195f * __log2f(fmaxf(1e-10f, mel));   // 10*log10(x)
                     Lg[32 * s4 + lane] = lm;
                     gmax = fmaxf(gmax, lm);
                     if (kDebug) {
