@@ -56,8 +56,8 @@ struct Params {
 
 // bytes of scratch one CTA needs for clips of up to Tmax frames (multiple of 256)
 inline size_t cta_scratch_bytes(int Tmax, int max_pk) {
-    // |X|^2 rows, log-mel rows, peak records (float4), peak keys (u32, overflow path), peak bins (u8)
-    size_t b = static_cast<size_t>(Tmax) * (kPStride * 4 + kMels * 4 + static_cast<size_t>(max_pk) * (16 + 4 + 1));
+    // |X|^2 rows, log-mel rows, peak records (float4), peak keys (u32, overflow path), hop energies, peak bins (u8)
+    size_t b = static_cast<size_t>(Tmax) * (kPStride * 4 + kMels * 4 + 4 + static_cast<size_t>(max_pk) * (16 + 4 + 1));
     return (b + 255) & ~static_cast<size_t>(255);
 }
 

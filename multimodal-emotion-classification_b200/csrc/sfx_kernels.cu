@@ -348,7 +348,8 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     float* gL = gP + static_cast<size_t>(p.Tmax) * kPStride;
     float4* gRec = reinterpret_cast<float4*>(gL + static_cast<size_t>(p.Tmax) * kMels);
     unsigned* gKey = reinterpret_cast<unsigned*>(gRec + static_cast<size_t>(p.Tmax) * p.max_pk);
-    unsigned char* gBin = reinterpret_cast<unsigned char*>(gKey + static_cast<size_t>(p.Tmax) * p.max_pk);
+    float* gE = reinterpret_cast<float*>(gKey + static_cast<size_t>(p.Tmax) * p.max_pk);        // hop energies [Tmax]
+    unsigned char* gBin = reinterpret_cast<unsigned char*>(gE + p.Tmax);
     int* counter = reinterpret_cast<int*>(p.ws);
 
     float* Pb = s_ex + warp * kExFloats;               // this warp's exchange / |X|^2 tile
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
 
         // ===================================== phase 1: frames =====================================
         // per-warp running sums live in shared memory (s_wacc[warp][0..2] = centroid, rolloff, rms; s_f = log-mel max)
-        if (lane < 3) s_wacc[warp * 16 + lane] = 0.0;
+        if (lane < 2) s_wacc[warp * 16 + lane] = 0.0;
         if (lane == 0) s_f[warp] = -FLT_MAX;
         int acc_zc = 0;
         __syncwarp();
@@ -382,12 +383,15 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         for (int t = warp; t < T; t += kWarps) {
             float re[32], im[32];
             load_frame(x, n, t, lane, aligned8, re, im);
-            // ---- rms (librosa.feature.rms: zero pad, no window)
-            float ss = 0.0f;
+            // ---- energy of hop t (samples [512t, 512t+512) = rows 16..23); librosa.feature.rms of frame t is
+            //      sqrt((E[t-2] + E[t-1] + E[t] + E[t+1]) / 2048) and is pooled in the epilogue
+            {
+                float he = 0.0f;
 #pragma unroll
-            for (int m1 = 0; m1 < 32; ++m1) { ss = fmaf(re[m1], re[m1], ss); ss = fmaf(im[m1], im[m1], ss); }
-            ss = warp_sum(ss);
-            const float rms_t = sqrtf(ss * (1.0f / kNfft));
+                for (int m1 = 16; m1 < 24; ++m1) { he = fmaf(re[m1], re[m1], he); he = fmaf(im[m1], im[m1], he); }
+                he = warp_sum(he);
+                if (lane == 0) gE[t] = he;
+            }
 
             // ---- zero crossings of hop t (samples [512t, 512t+512)), weighted by how many frames see them
             int zc_hop = 0;
@@ -562,7 +566,6 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
             if (lane == 0) {
                 s_wacc[warp * 16 + 0] += static_cast<double>(cent_t);
                 s_wacc[warp * 16 + 1] += static_cast<double>(roll_t);
-                s_wacc[warp * 16 + 2] += static_cast<double>(rms_t);
             }
             __syncwarp();
 
@@ -594,35 +597,34 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 const float* q0 = Pb + pidx(kfirst - 1);
                 const int d0 = pidx(kfirst) - pidx(kfirst - 1), d1 = pidx(kfirst + 1) - pidx(kfirst - 1);
                 const int nrows = (tb.kmax - tb.kmin + 32) >> 5;          // <= 16 (bins 1..1023, 32 per row)
-                const unsigned lt = (1u << lane) - 1u;
                 unsigned flags = 0;                                      // bit r: this lane's bin of row r is a peak
-                int total = 0;
-                unsigned offs[8];                                        // two 16-bit record offsets per register
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
-                    if ((r & 1) == 0) offs[r >> 1] = 0;
                     if (r < nrows) {
                         const float* q = q0 + 33 * r;
-                        const bool valid = kfirst + 32 * r <= tb.kmax;
                         const float pm = q[0], pc = q[d0], pp = q[d1];
-                        const bool pk = valid && pc > ref && pc > pm && pc >= pp;
-                        const unsigned m = __ballot_sync(0xffffffffu, pk);
-                        if (pk) flags |= 1u << r;
-                        offs[r >> 1] |= static_cast<unsigned>(total + __popc(m & lt)) << (16 * (r & 1));
-                        total += __popc(m);
+                        if (kfirst + 32 * r <= tb.kmax && pc > ref && pc > pm && pc >= pp) flags |= 1u << r;
                     }
                 }
+                // lane-wise compaction: exclusive prefix of the per-lane peak counts, one atomic per frame
+                const int mine = __popc(flags);
+                int inc = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                const int total = __shfl_sync(0xffffffffu, inc, 31);
                 if (total) {
                     int base = 0;
                     if (lane == 0) base = atomicAdd(&s_i[1], total);
                     base = __shfl_sync(0xffffffffu, base, 0);
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        if (flags & (1u << r)) {
-                            const float* q = q0 + 33 * r;
-                            const int pos = base + static_cast<int>((offs[r >> 1] >> (16 * (r & 1))) & 0xffffu);
-                            gRec[pos] = make_float4(q[0], q[d0], q[d1], __int_as_float(kfirst + 32 * r));
-                        }
+                    float4* dst = gRec + base + (inc - mine);
+                    while (flags) {
+                        const int r = __ffs(flags) - 1;
+                        flags &= flags - 1;
+                        const float* q = q0 + 33 * r;
+                        *dst++ = make_float4(q[0], q[d0], q[d1], __int_as_float(kfirst + 32 * r));
                     }
                 }
             }
@@ -630,7 +632,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 const int zch = warp_sum_i(zc_hop);
                 if (p.dbg.frame_feat && t < p.dbg.T_dbg && lane == 0) {
                     float* ff = p.dbg.frame_feat + (static_cast<size_t>(clip) * p.dbg.T_dbg + t) * 4;
-                    ff[0] = cent_t; ff[1] = roll_t; ff[2] = rms_t; ff[3] = static_cast<float>(zch);
+                    ff[0] = cent_t; ff[1] = roll_t; ff[3] = static_cast<float>(zch);
                 }
             }
             (void)zc_hop;
@@ -829,7 +831,26 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         __syncthreads();
 
         // ===================================== epilogue: pooled row ================================
-        if (tid < 16) {
+        if (warp == 1) {
+            // pooled rms from the hop energies (frame t spans hops t-2 .. t+1; hops outside [0, T) are zero padding)
+            double a = 0.0;
+            for (int t = lane; t < T; t += 32) {
+                float e = (t >= 2) ? gE[t - 2] : 0.0f;
+                e += (t >= 1) ? gE[t - 1] : 0.0f;
+                e += gE[t];
+                e += (t + 1 < T) ? gE[t + 1] : 0.0f;
+                const float r = sqrtf(e * (1.0f / kNfft));
+                a += static_cast<double>(r);
+                if (kDebug) {
+                    if (p.dbg.frame_feat && t < p.dbg.T_dbg)
+                        p.dbg.frame_feat[(static_cast<size_t>(clip) * p.dbg.T_dbg + t) * 4 + 2] = r;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) out[p.n_mfcc + 15] = static_cast<float>(a / static_cast<double>(T));
+        }
+        if (tid < 15) {
             const double invT = 1.0 / static_cast<double>(T);
             if (tid < kChroma) {
                 double v = 0.0;
