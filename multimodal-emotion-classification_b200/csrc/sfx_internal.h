@@ -18,6 +18,8 @@ constexpr int kTunings = SFX_N_TUNINGS;
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kExFloats = 32 * 33 * 2;   // per-warp float2[32][33] exchange tile, reused as the padded |X|^2 tile
+constexpr int kWStride = 1072;           // shared-memory row stride of the chroma bank (= 16 mod 32: conflict-free LDS.128)
+constexpr int kChromaTiles = 20;         // 8-frame tiles whose K-half partial sums fit beside the bank in the warp tiles
 constexpr int kPartOff = 1088;           // offset of the mel partial-sum slots inside a warp's tile
 constexpr int kKeyCap = 13312;           // peak keys (u32) + bins (u8) kept in shared memory during the median select
 constexpr size_t kWsHeader = 256;        // clip-queue counter lives in the first bytes of the workspace

@@ -230,6 +230,19 @@ __device__ __forceinline__ float reduce_scatter16(float (&v)[16], int lane) {
     return v[0];
 }
 
+__device__ __forceinline__ unsigned to_tf32(float x) {
+    unsigned u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return u;
+}
+// D(16x8, f32) += A(16x8, tf32, row) * B(8x8, tf32, col): warp-level tensor-core MMA, FP32 accumulate
+__device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+                                         unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
 // One chroma tile: NF consecutive frames x 12 chroma for the warp; lane owns bins 4*lane + 128*j.  The |X|^2 rows come
@@ -760,12 +773,14 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         }
 
         // ===================================== phase 3a: MFCC ======================================
-        // (also stages the tuning's chroma bank into shared memory: the warp tiles are free now)
-        float* sW = s_ex;                                   // [12][1056]
+        // (also stages the tuning's TF32 chroma bank into shared memory, row stride 1072 floats: the warp tiles are free)
+        float* sW = s_ex;                                   // [12][kWStride]
         {
             const float4* Wg = reinterpret_cast<const float4*>(tb.chroma + static_cast<size_t>(tuning_idx) * kChroma * kPStride);
-            float4* Ws = reinterpret_cast<float4*>(sW);
-            for (int i = tid; i < kChroma * kPStride / 4; i += kThreads) Ws[i] = __ldg(Wg + i);
+            for (int i = tid; i < kChroma * (kPStride / 4); i += kThreads) {
+                const int c = i / (kPStride / 4), k4 = i - c * (kPStride / 4);
+                *reinterpret_cast<float4*>(sW + c * kWStride + 4 * k4) = __ldg(Wg + i);
+            }
             const float clampv = __fsub_rn(gmx, 80.0f);
             const int m = tid & 127, h = tid >> 7;
             double a = 0.0;
@@ -782,49 +797,74 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         }
 
         // ===================================== phase 3b: chroma ====================================
-        // warp w owns a contiguous, balanced range of frames and walks it in tiles of <= 4 frames x 12 chroma;
-        // lane owns bins 4*lane + 128*j (float4); bin 1024 is added when the frame is normalised
+        // raw[c][t] = sum_k W[c][k] |X|^2[k][t] on the tensor cores (TF32 operands, FP32 accumulate): one unit = 8 frames x
+        // 512 bins = 32 steps of two m16n8k8 MMAs; lane (g = lane/4, t4 = lane%4) feeds frame g's bins k0+4*t4..+3 as the
+        // B fragments and rows g, g+8 of the bank as the A fragments.  Units are dealt round-robin to the warps, the two
+        // K-halves of a tile are added in a fixed order, then each frame is normalised by its max (librosa norm=inf).
         {
-            double cacc[kChroma];
+            float* part = s_ex + kChroma * kWStride;        // [kChromaTiles][2][96]
+            const int g = lane >> 2, t4 = lane & 3;
+            double csum[kChroma];                           // per-thread sums over its frames
 #pragma unroll
-            for (int c = 0; c < kChroma; ++c) cacc[c] = 0.0;
-            float* red = s_ex + kChroma * kPStride + warp * 64;
-            const int fbase = T / kWarps, frem = T % kWarps;
-            const int f_lo = warp * fbase + min(warp, frem);
-            const int f_hi = f_lo + fbase + (warp < frem ? 1 : 0);
-            for (int t0 = f_lo; t0 < f_hi; t0 += 4) {
-                const int nf = min(4, f_hi - t0);
-                const float* Pt = gP + static_cast<size_t>(t0) * kPStride;
-                if (t0 + 4 < f_hi) {                      // next tile's rows -> L2 while this one is computed
-                    const char* nx = reinterpret_cast<const char*>(Pt + 4 * kPStride);
-                    const int nbytes = min(4, f_hi - t0 - 4) * kPStride * 4;
-                    for (int o = lane * 128; o < nbytes; o += 32 * 128) prefetch_l2(nx + o);
-                }
-                if (nf == 4) chroma_tile<4>(sW, Pt, red, lane);
-                else if (nf == 3) chroma_tile<3>(sW, Pt, red, lane);
-                else if (nf == 2) chroma_tile<2>(sW, Pt, red, lane);
-                else chroma_tile<1>(sW, Pt, red, lane);
-                __syncwarp();
-                if (lane < nf) {
-                    const float pn = Pt[lane * kPStride + 1024];            // Nyquist bin of frame t0 + lane
-                    float raw[kChroma];
-                    float mx = 0.0f;
+            for (int c = 0; c < kChroma; ++c) csum[c] = 0.0;
+            const int ntiles = (T + 7) >> 3;
+            for (int tile0 = 0; tile0 < ntiles; tile0 += kChromaTiles) {
+                const int nt = min(kChromaTiles, ntiles - tile0);
+                for (int u = warp; u < 2 * nt; u += kWarps) {
+                    const int tl = u >> 1, kh = u & 1;
+                    const int f = (tile0 + tl) * 8 + g;
+                    const bool valid = f < T;
+                    const float* prow = gP + static_cast<size_t>(valid ? f : 0) * kPStride + kh * 512 + 4 * t4;
+                    const float* w0p = sW + g * kWStride + kh * 512 + 4 * t4;
+                    const float* w1p = sW + (g < 4 ? g + 8 : g) * kWStride + kh * 512 + 4 * t4;
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+                    for (int kb0 = 0; kb0 < 32; kb0 += 8) {
+                        float4 pv[8];
 #pragma unroll
-                    for (int c = 0; c < kChroma; ++c) {
-                        raw[c] = fmaf(sW[c * kPStride + 1024], pn, red[lane * kChroma + c]);
-                        mx = fmaxf(mx, fabsf(raw[c]));
+                        for (int i = 0; i < 8; ++i)
+                            pv[i] = valid ? *reinterpret_cast<const float4*>(prow + (kb0 + i) * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 w0 = *reinterpret_cast<const float4*>(w0p + (kb0 + i) * 16);
+                            float4 w1 = *reinterpret_cast<const float4*>(w1p + (kb0 + i) * 16);
+                            if (g >= 4) w1 = make_float4(0.f, 0.f, 0.f, 0.f);           // bank rows 12..15 do not exist
+                            mma_tf32(acc, __float_as_uint(w0.x), __float_as_uint(w1.x), __float_as_uint(w0.y), __float_as_uint(w1.y),
+                                     to_tf32(pv[i].x), to_tf32(pv[i].y));
+                            mma_tf32(acc, __float_as_uint(w0.z), __float_as_uint(w1.z), __float_as_uint(w0.w), __float_as_uint(w1.w),
+                                     to_tf32(pv[i].z), to_tf32(pv[i].w));
+                        }
                     }
-                    if (mx < FLT_MIN) mx = 1.0f;
-#pragma unroll
-                    for (int c = 0; c < kChroma; ++c) cacc[c] += static_cast<double>(__fdiv_rn(raw[c], mx));
+                    // D fragment: acc[0..1] = (chroma g, frames 2*t4, 2*t4+1), acc[2..3] = (chroma g+8, same frames)
+                    float* dst = part + (tl * 2 + kh) * 96;
+                    *reinterpret_cast<float2*>(dst + g * 8 + 2 * t4) = make_float2(acc[0], acc[1]);
+                    if (g < 4) *reinterpret_cast<float2*>(dst + (g + 8) * 8 + 2 * t4) = make_float2(acc[2], acc[3]);
                 }
-                __syncwarp();
+                __syncthreads();
+                for (int fl = tid; fl < nt * 8; fl += kThreads) {
+                    const int f = tile0 * 8 + fl;
+                    if (f < T) {
+                        const float* q = part + (fl >> 3) * 192 + (fl & 7);
+                        const float pn = gP[static_cast<size_t>(f) * kPStride + 1024];     // Nyquist bin
+                        float raw[kChroma];
+                        float mx = 0.0f;
+#pragma unroll
+                        for (int c = 0; c < kChroma; ++c) {
+                            raw[c] = fmaf(sW[c * kWStride + 1024], pn, q[c * 8] + q[96 + c * 8]);
+                            mx = fmaxf(mx, fabsf(raw[c]));
+                        }
+                        if (mx < FLT_MIN) mx = 1.0f;
+#pragma unroll
+                        for (int c = 0; c < kChroma; ++c) csum[c] += static_cast<double>(__fdiv_rn(raw[c], mx));
+                    }
+                }
+                __syncthreads();
             }
 #pragma unroll
             for (int c = 0; c < kChroma; ++c) {
-                double v = (lane < 4) ? cacc[c] : 0.0;
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                double v = csum[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 if (lane == 0) s_wacc[warp * 16 + 3 + c] = v;
             }
         }

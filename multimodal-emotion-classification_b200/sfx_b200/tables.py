@@ -14,7 +14,8 @@ Layouts are chosen for the kernels (see DESIGN.md "HBM / SMEM layout"), not for 
   mel_ab float32[33][32][2]   (falling, rising) Slaney weights of bin 32*lane + j at [j][lane]; mel_mask uint32[32]
                               flush bits, mel_src int32[128][3] partial-sum slots (see mel_chunk_layout)
   melw   float32[mel_rows][32] transposed/padded sparse mel weights (dense-bank audit layout, host tests only)
-  chroma float32[100][12][1056] one bank per tuning edge, bin axis zero-padded to 1056
+  chroma float32[100][12][1056] one bank per tuning edge, bin axis zero-padded to 1056, values rounded to TF32
+                              (operand of the tensor-core chroma projection); chroma_f32 is the unrounded bank
   dct    float64[128][128]    rows k of the ortho DCT-II
   edges  float64[101]         np.linspace(-0.5, 0.5, 101)
 """
@@ -79,6 +80,12 @@ def chroma_bank(sr: int, tuning: float) -> np.ndarray:
     w *= np.tile(np.exp(-0.5 * (((frq / N_CHROMA - 5.0) / 2) ** 2)), (N_CHROMA, 1))
     w = np.roll(w, -3 * (N_CHROMA // 12), axis=0)
     return np.ascontiguousarray(w[:, :N_BINS], dtype=np.float32)
+
+
+def round_to_tf32(x: np.ndarray) -> np.ndarray:
+    """Round float32 to the TF32 grid (10-bit mantissa), nearest / ties away: what cvt.rna.tf32.f32 does."""
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
 
 
 def tuning_edges() -> np.ndarray:
@@ -209,4 +216,4 @@ def build_tables(sr: int = 22050) -> dict:
     chunk = mel_chunk_layout(sr, mb)
     return dict(**chunk, sr=sr, hann=hann, tw1=np.ascontiguousarray(tw1), tw2=np.ascontiguousarray(tw2),
                 mel_dense=mb, melw=melw, mel_lo=mel_lo, mel_off=mel_off, mel_len=mel_len,
-                chroma=chroma, dct=dct_matrix(), edges=edges, pip_kmin=kmin, pip_kmax=kmax)
+                chroma=round_to_tf32(chroma), chroma_f32=chroma, dct=dct_matrix(), edges=edges, pip_kmin=kmin, pip_kmax=kmax)

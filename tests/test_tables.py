@@ -14,8 +14,13 @@ def test_banks_bit_identical_to_oracle():
     e = tb["edges"]
     assert np.array_equal(e, np.linspace(-0.5, 0.5, 101)) and e[50] == 0.0
     for i in (0, 17, 50, 83, 99):
-        assert np.array_equal(tb["chroma"][i, :, :1025], lp.chroma_filterbank(tuning=float(e[i])))
+        ref = lp.chroma_filterbank(tuning=float(e[i]))
+        assert np.array_equal(tb["chroma_f32"][i, :, :1025], ref)
         assert not tb["chroma"][i, :, 1025:].any()
+        # device operand: TF32-rounded (10-bit mantissa, round to nearest): <= 2^-11 relative
+        dev = tb["chroma"][i, :, :1025]
+        assert np.all(np.abs(dev - ref) <= np.abs(ref) * 2.0 ** -11)
+        assert not (dev.view(np.uint32) & 0x1FFF).any()
     assert np.array_equal(tb["hann"], lp.hann_window().astype(np.float32))
     assert (tb["pip_kmin"], tb["pip_kmax"]) == (14, 371)
 
@@ -40,7 +45,7 @@ def test_mel_sparse_layout_roundtrip():
 def test_other_sample_rate_tables():
     tb = tables.build_tables(16000)
     assert np.array_equal(tb["mel_dense"], lp.mel_filterbank(sr=16000))
-    assert np.array_equal(tb["chroma"][50, :, :1025], lp.chroma_filterbank(sr=16000, tuning=0.0))
+    assert np.array_equal(tb["chroma_f32"][50, :, :1025], lp.chroma_filterbank(sr=16000, tuning=0.0))
 
 
 def test_warp_fft_model_matches_rfft():
