@@ -74,7 +74,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = host_cores()
-    per_step = max(cores * 2, 16)
+    per_step = max(cores * 16, 16)
     for _ in range(min(args.warmup, 1)):
         cpu_reference_rate(cores, cores)
     rates, tot, t0 = [], 0, time.perf_counter()
@@ -223,7 +223,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        total = min(512, max(64, 4 * cores))
+        total = min(4096, max(64, 48 * cores))          # ~15-25 s of CPU work spread over the cores
         rate, nclips, secs = cpu_reference_rate(total, cores)
         rate1, n1, secs1 = cpu_reference_rate(8, 1)
         cpu_baseline = {"value": rate, "unit": "clips/s", "cores": cores, "kind": "port",

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     float2* s_hann = reinterpret_cast<float2*>(smem_raw);
     float2* s_tw1 = s_hann + 1024;
     float2* s_tw2 = s_tw1 + 1024;
-    float2* s_melab = s_tw2 + 1024;                                          // [33*32]
+    float2* s_melab = s_tw2 + 512;                                           // [33*32]  (tw2: rows k2 < 16 only)
     float* s_ex = reinterpret_cast<float*>(s_melab + 33 * 32);               // [kWarps][kExFloats]
     double* s_pool = reinterpret_cast<double*>(s_ex + kWarps * kExFloats);   // [256]
     double* s_wacc = s_pool + 256;                                           // [kWarps][16]
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     for (int i = tid; i < 1024; i += kThreads) {
         s_hann[i] = tb.hann[i];
         s_tw1[i] = tb.tw1[i];
-        s_tw2[i] = tb.tw2[i];
+        if (i < 512) s_tw2[i] = tb.tw2[i];
     }
     for (int i = tid; i < 33 * 32; i += kThreads) s_melab[i] = tb.mel_ab[i];
     for (int i = tid; i <= kTunings; i += kThreads) s_edges[i] = tb.edges[i];
@@ -782,10 +782,12 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 *reinterpret_cast<float4*>(sW + c * kWStride + 4 * k4) = __ldg(Wg + i);
             }
             const float clampv = __fsub_rn(gmx, 80.0f);
-            const int m = tid & 127, h = tid >> 7;
-            double a = 0.0;
-            for (int t = h; t < T; t += 2) a += static_cast<double>(fmaxf(gL[static_cast<size_t>(t) * kMels + m], clampv));
-            s_pool[h * 128 + m] = a;
+            if (tid < 256) {
+                const int m = tid & 127, h = tid >> 7;
+                double a = 0.0;
+                for (int t = h; t < T; t += 2) a += static_cast<double>(fmaxf(gL[static_cast<size_t>(t) * kMels + m], clampv));
+                s_pool[h * 128 + m] = a;
+            }
             __syncthreads();
             if (tid < 128) s_pool[tid] = (s_pool[tid] + s_pool[128 + tid]) / static_cast<double>(T);
             __syncthreads();
@@ -911,7 +913,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
 
 // ------------------------------------------------------------------------------------------------
 size_t smem_bytes() {
-    return sizeof(float2) * (3072 + 33 * 32) + sizeof(float) * kWarps * kExFloats +
+    return sizeof(float2) * (2560 + 33 * 32) + sizeof(float) * kWarps * kExFloats +
            sizeof(double) * (256 + kWarps * 16 + 104) + sizeof(int) * (256 + 32) + sizeof(float) * 32;
 }
 
