@@ -60,7 +60,8 @@ typedef struct {
     const float  *mel_ab;        /* [33][32][2] (falling, rising) weights of bin 32*lane + j at [j][lane] */
     const uint32_t*mel_mask;     /* [32] bit j: interval index advances at bin 32*lane + j */
     const int32_t*mel_src;       /* [128][3] partial-sum slots of each filter (32*mel_ps = zero slot) */
-    const float  *chroma;        /* [100][12][1056] */
+    const uint16_t*chroma16;     /* [100][2][12][1056] IEEE half: bank = hi + 2^-11 * lo (tensor-core operands) */
+    const float  *chroma_ny;     /* [100][12] float32 weights of the Nyquist bin */
     const double *dct;           /* [128][128] */
     const double *edges;         /* [101] */
 } sfx_tables_host;

@@ -155,7 +155,7 @@ int sfx_release(int device) {
 
 int sfx_init_tables(int device, const sfx_tables_host* t) {
     if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
-    if (!t || !t->hann || !t->tw1 || !t->tw2 || !t->mel_ab || !t->mel_mask || !t->mel_src || !t->chroma || !t->dct ||
+    if (!t || !t->hann || !t->tw1 || !t->tw2 || !t->mel_ab || !t->mel_mask || !t->mel_src || !t->chroma16 || !t->chroma_ny || !t->dct ||
         !t->edges || t->sr <= 0)
         return fail(SFX_ERR_ARG, "null table pointer or bad sizes");
     if (t->mel_ps < 3 || (t->mel_ps & 1) == 0 || sfx::kPartOff + 32 * t->mel_ps + 1 > sfx::kExFloats)
@@ -187,7 +187,8 @@ int sfx_init_tables(int device, const sfx_tables_host* t) {
     set.tb.mel_ab = reinterpret_cast<const float2*>(f);
     if ((rc = upload(c, t->mel_mask, 32, &set.tb.mel_mask))) return rc;
     if ((rc = upload(c, t->mel_src, 128 * 3, &set.tb.mel_src))) return rc;
-    if ((rc = upload(c, t->chroma, static_cast<size_t>(sfx::kTunings) * sfx::kChroma * sfx::kPStride, &set.tb.chroma))) return rc;
+    if ((rc = upload(c, t->chroma16, static_cast<size_t>(sfx::kTunings) * 2 * sfx::kChroma * sfx::kP16Stride, &set.tb.chroma16))) return rc;
+    if ((rc = upload(c, t->chroma_ny, static_cast<size_t>(sfx::kTunings) * sfx::kChroma, &set.tb.chroma_ny))) return rc;
     std::vector<double> dctT(static_cast<size_t>(sfx::kMels) * sfx::kMels);
     for (int k = 0; k < sfx::kMels; ++k)
         for (int m = 0; m < sfx::kMels; ++m) dctT[static_cast<size_t>(m) * sfx::kMels + k] = t->dct[static_cast<size_t>(k) * sfx::kMels + m];

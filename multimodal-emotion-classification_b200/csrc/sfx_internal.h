@@ -18,7 +18,7 @@ constexpr int kTunings = SFX_N_TUNINGS;
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kExFloats = 32 * 33 * 2;   // per-warp float2[32][33] exchange tile, reused as the padded |X|^2 tile
-constexpr int kWStride = 1072;           // shared-memory row stride of the chroma bank (= 16 mod 32: conflict-free LDS.128)
+constexpr int kP16Stride = 1056;         // halves per FP16 |X|^2 row (2112 B = 64 mod 128: conflict-free LDS.128 of the bank rows)
 constexpr int kChromaTiles = 20;         // 8-frame tiles whose K-half partial sums fit beside the bank in the warp tiles
 constexpr int kPartOff = 1088;           // offset of the mel partial-sum slots inside a warp's tile
 constexpr int kKeyCap = 13312;           // peak keys (u32) + bins (u8) kept in shared memory during the median select
@@ -32,7 +32,8 @@ struct DevTables {
     const unsigned* mel_mask;   // [32]
     const int* mel_src;     // [128][3]
     int mel_ps, mel_flush32;
-    const float* chroma;    // [100][12][1056]
+    const uint16_t* chroma16;   // [100][2][12][1056] half: hi, lo * 2^11
+    const float* chroma_ny;     // [100][12]
     const double* dctT;     // [128 mel][128 k]  (transposed: coalesced over k)
     const double* edges;    // [101]
     int sr, kmin, kmax;
@@ -58,8 +59,9 @@ struct Params {
 
 // bytes of scratch one CTA needs for clips of up to Tmax frames (multiple of 256)
 inline size_t cta_scratch_bytes(int Tmax, int max_pk) {
-    // |X|^2 rows, log-mel rows, peak records (float4), peak keys (u32, overflow path), hop energies, peak bins (u8)
-    size_t b = static_cast<size_t>(Tmax) * (kPStride * 4 + kMels * 4 + 4 + static_cast<size_t>(max_pk) * (16 + 4 + 1));
+    // FP16 |X|^2 rows, log-mel rows, peak records (float4), peak keys (u32, overflow path), hop energy + Nyquist + 1/scale
+    // per frame, peak bins (u8)
+    size_t b = static_cast<size_t>(Tmax) * (kP16Stride * 2 + kMels * 4 + 12 + static_cast<size_t>(max_pk) * (16 + 4 + 1));
     return (b + 255) & ~static_cast<size_t>(255);
 }
 

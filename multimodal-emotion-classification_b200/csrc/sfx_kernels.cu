@@ -13,6 +13,7 @@
 //           tuning's filter bank, per-frame inf-norm, frame mean; pooled spectral descriptors.
 // Output row: [mfcc_0..n_mfcc-1 | chroma C..B | zcr, centroid, rolloff, rms]  (reference :45-46).
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <cfloat>
 #include <cstdint>
 #include <type_traits>
@@ -243,6 +244,18 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// D(16x8, f32) += A(16x16, f16, row) * B(16x8, f16, col): warp-level tensor-core MMA, FP32 accumulate
+__device__ __forceinline__ void mma_f16(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+                                        unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ unsigned pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const unsigned*>(&h);
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
 // One chroma tile: NF consecutive frames x 12 chroma for the warp; lane owns bins 4*lane + 128*j.  The |X|^2 rows come
@@ -357,12 +370,14 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
 
     // scratch slice of this CTA
     unsigned char* slice = p.ws + kWsHeader + static_cast<size_t>(blockIdx.x) * p.cta_scratch_bytes;
-    float* gP = reinterpret_cast<float*>(slice);
-    float* gL = gP + static_cast<size_t>(p.Tmax) * kPStride;
+    __half* gP16 = reinterpret_cast<__half*>(slice);                                             // [Tmax][kP16Stride]
+    float* gL = reinterpret_cast<float*>(gP16 + static_cast<size_t>(p.Tmax) * kP16Stride);       // [Tmax][128]
     float4* gRec = reinterpret_cast<float4*>(gL + static_cast<size_t>(p.Tmax) * kMels);
     unsigned* gKey = reinterpret_cast<unsigned*>(gRec + static_cast<size_t>(p.Tmax) * p.max_pk);
     float* gE = reinterpret_cast<float*>(gKey + static_cast<size_t>(p.Tmax) * p.max_pk);        // hop energies [Tmax]
-    unsigned char* gBin = reinterpret_cast<unsigned char*>(gE + p.Tmax);
+    float* gNy = gE + p.Tmax;                                                                    // scaled Nyquist |X|^2 [Tmax]
+    float* gInvS = gNy + p.Tmax;                                                                 // 1 / row scale [Tmax]
+    unsigned char* gBin = reinterpret_cast<unsigned char*>(gInvS + p.Tmax);
     int* counter = reinterpret_cast<int*>(p.ws);
 
     float* Pb = s_ex + warp * kExFloats;               // this warp's exchange / |X|^2 tile
@@ -468,9 +483,6 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
             //      lane 0 pairs with its own register (32-k2)&31).  Bin 512 (self-paired) is lane 0's register 16.
             float pmax = 0.0f;
             {
-                float* Pg = gP + static_cast<size_t>(t) * kPStride;
-                float* PgL = Pg + lane;
-                float* PgU = Pg + 1024 - lane;
                 float* PbL = Pb + lane;
                 float* PbU = Pb + (lane == 0 ? 1056 : 1055 - lane);
                 const int plane = (32 - lane) & 31;
@@ -491,15 +503,12 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                     const float Q = fmaf(yr, yr, yi * yi);
                     pmax = fmaxf(pmax, fmaxf(P, Q));
                     PbL[33 * k2] = P;
-                    PgL[32 * k2] = P;
                     PbU[-33 * k2] = Q;
-                    PgU[-32 * k2] = Q;
                 });
                 if (lane == 0) {
                     constexpr int h = brev5(16);
                     const float P512 = fmaf(re[h], re[h], im[h] * im[h]);
                     Pb[512 + 16] = P512;
-                    Pg[512] = P512;
                     pmax = fmaxf(pmax, P512);
                 }
             }
@@ -527,9 +536,18 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 float run = 0.0f, ks = 0.0f, accA = 0.0f, accB = 0.0f;
                 float* pq = part + lane * mel_ps;
                 const float* Prow = Pb + 33 * lane;
+                // the chroma phase reads this frame's |X|^2 back as FP16 scaled by an exact power of two that puts the
+                // frame maximum in [2^14, 2^15) (the per-frame inf-norm of chroma_stft cancels the scale)
+                // biased exponent of the scale = 14 - (E - 127) + 127 = 268 - E, clamped to a finite power of two
+                const unsigned sbits = min(268u - ((__float_as_uint(pmax) >> 23) & 255u), 254u) << 23;
+                const float scale = __uint_as_float(sbits);
+                unsigned h2[16];
+                float hprev = 0.0f;
                 sfor<32>([&](auto J) {
                     constexpr int j = decltype(J)::value;
                     const float P = Prow[j];
+                    if constexpr ((j & 1) == 0) hprev = P * scale;
+                    else h2[j >> 1] = pack_half2(hprev, P * scale);
                     if (j > 0 && ((mel_mask >> j) & 1u)) { *pq++ = accA; accA = accB; accB = 0.0f; }
                     const float2 ab = s_melab[j * 32 + lane];
                     accA = fmaf(ab.x, P, accA);
@@ -554,6 +572,13 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 pq[0] = accA;
                 pq[1] = accB;
                 if (lane == 0) part[32 * mel_ps] = 0.0f;   // zero slot read by filters with < 3 contributing lanes
+                {
+                    uint4* dst = reinterpret_cast<uint4*>(gP16 + static_cast<size_t>(t) * kP16Stride + 32 * lane);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
+                    if (lane == 31) gNy[t] = Pb[1024 + 32] * scale;
+                    if (lane == 0) gInvS[t] = __uint_as_float((254u << 23) - sbits);      // 1/scale, exact
+                }
                 float inc = run;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -773,14 +798,12 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         }
 
         // ===================================== phase 3a: MFCC ======================================
-        // (also stages the tuning's TF32 chroma bank into shared memory, row stride 1072 floats: the warp tiles are free)
-        float* sW = s_ex;                                   // [12][kWStride]
+        // (also stages the tuning's FP16 hi/lo chroma bank into shared memory: the warp tiles are free now)
+        __half* sW = reinterpret_cast<__half*>(s_ex);       // [2][12][kP16Stride]
         {
-            const float4* Wg = reinterpret_cast<const float4*>(tb.chroma + static_cast<size_t>(tuning_idx) * kChroma * kPStride);
-            for (int i = tid; i < kChroma * (kPStride / 4); i += kThreads) {
-                const int c = i / (kPStride / 4), k4 = i - c * (kPStride / 4);
-                *reinterpret_cast<float4*>(sW + c * kWStride + 4 * k4) = __ldg(Wg + i);
-            }
+            const uint4* Wg = reinterpret_cast<const uint4*>(tb.chroma16 + static_cast<size_t>(tuning_idx) * 2 * kChroma * kP16Stride);
+            uint4* Ws = reinterpret_cast<uint4*>(sW);
+            for (int i = tid; i < 2 * kChroma * kP16Stride / 8; i += kThreads) Ws[i] = __ldg(Wg + i);
             const float clampv = __fsub_rn(gmx, 80.0f);
             if (tid < 256) {
                 const int m = tid & 127, h = tid >> 7;
@@ -799,16 +822,20 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         }
 
         // ===================================== phase 3b: chroma ====================================
-        // raw[c][t] = sum_k W[c][k] |X|^2[k][t] on the tensor cores (TF32 operands, FP32 accumulate): one unit = 8 frames x
-        // 512 bins = 32 steps of two m16n8k8 MMAs; lane (g = lane/4, t4 = lane%4) feeds frame g's bins k0+4*t4..+3 as the
-        // B fragments and rows g, g+8 of the bank as the A fragments.  Units are dealt round-robin to the warps, the two
-        // K-halves of a tile are added in a fixed order, then each frame is normalised by its max (librosa norm=inf).
+        // raw[c][t] = sum_k W[c][k] |X|^2[k][t] on the tensor cores: m16n8k16 FP16 MMAs with FP32 accumulators.  A = bank
+        // (hi and 2^11*lo halves, separate accumulators), B = the frame's scaled FP16 |X|^2 row.  One unit = 8 frames x
+        // 512 bins = 16 steps of 1 LDG.128 + 4 LDS.128 + 4 MMA; lane (g = lane/4, t4 = lane%4) feeds frame g's bins
+        // k0+8*t4..+7 and rows g, g+8 of the bank.  Units are dealt round-robin to the warps, the two K-halves of a tile
+        // are added in a fixed order, then each frame is normalised by its max (librosa norm=inf).
         {
-            float* part = s_ex + kChroma * kWStride;        // [kChromaTiles][2][96]
+            float* part2 = s_ex + (2 * kChroma * kP16Stride) / 2;        // [kChromaTiles][2][96] floats after the bank
             const int g = lane >> 2, t4 = lane & 3;
-            double csum[kChroma];                           // per-thread sums over its frames
+            double csum[kChroma];                                        // per-thread sums over its frames
 #pragma unroll
             for (int c = 0; c < kChroma; ++c) csum[c] = 0.0;
+            float wny[kChroma];
+#pragma unroll
+            for (int c = 0; c < kChroma; ++c) wny[c] = __ldg(tb.chroma_ny + tuning_idx * kChroma + c);
             const int ntiles = (T + 7) >> 3;
             for (int tile0 = 0; tile0 < ntiles; tile0 += kChromaTiles) {
                 const int nt = min(kChromaTiles, ntiles - tile0);
@@ -816,48 +843,59 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                     const int tl = u >> 1, kh = u & 1;
                     const int f = (tile0 + tl) * 8 + g;
                     const bool valid = f < T;
-                    const float* prow = gP + static_cast<size_t>(valid ? f : 0) * kPStride + kh * 512 + 4 * t4;
-                    const float* w0p = sW + g * kWStride + kh * 512 + 4 * t4;
-                    const float* w1p = sW + (g < 4 ? g + 8 : g) * kWStride + kh * 512 + 4 * t4;
-                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                    const __half* prow = gP16 + static_cast<size_t>(valid ? f : 0) * kP16Stride + kh * 512 + 8 * t4;
+                    const int r1 = (g < 4) ? g + 8 : g;                  // bank rows 12..15 do not exist
+                    const __half* whi0 = sW + g * kP16Stride + kh * 512 + 8 * t4;
+                    const __half* whi1 = sW + r1 * kP16Stride + kh * 512 + 8 * t4;
+                    const __half* wlo0 = whi0 + kChroma * kP16Stride;
+                    const __half* wlo1 = whi1 + kChroma * kP16Stride;
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-                    for (int kb0 = 0; kb0 < 32; kb0 += 8) {
-                        float4 pv[8];
+                    for (int kb0 = 0; kb0 < 16; kb0 += 8) {
+                        uint4 pv[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            pv[i] = valid ? *reinterpret_cast<const float4*>(prow + (kb0 + i) * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            pv[i] = valid ? *reinterpret_cast<const uint4*>(prow + (kb0 + i) * 32) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float4 w0 = *reinterpret_cast<const float4*>(w0p + (kb0 + i) * 16);
-                            float4 w1 = *reinterpret_cast<const float4*>(w1p + (kb0 + i) * 16);
-                            if (g >= 4) w1 = make_float4(0.f, 0.f, 0.f, 0.f);           // bank rows 12..15 do not exist
-                            mma_tf32(acc, __float_as_uint(w0.x), __float_as_uint(w1.x), __float_as_uint(w0.y), __float_as_uint(w1.y),
-                                     to_tf32(pv[i].x), to_tf32(pv[i].y));
-                            mma_tf32(acc, __float_as_uint(w0.z), __float_as_uint(w1.z), __float_as_uint(w0.w), __float_as_uint(w1.w),
-                                     to_tf32(pv[i].z), to_tf32(pv[i].w));
+                            const int o = (kb0 + i) * 32;
+                            const uint4 h0 = *reinterpret_cast<const uint4*>(whi0 + o);
+                            uint4 h1 = *reinterpret_cast<const uint4*>(whi1 + o);
+                            const uint4 l0 = *reinterpret_cast<const uint4*>(wlo0 + o);
+                            uint4 l1 = *reinterpret_cast<const uint4*>(wlo1 + o);
+                            if (g >= 4) { h1 = make_uint4(0u, 0u, 0u, 0u); l1 = h1; }
+                            mma_f16(acc, h0.x, h1.x, h0.y, h1.y, pv[i].x, pv[i].y);
+                            mma_f16(acc, h0.z, h1.z, h0.w, h1.w, pv[i].z, pv[i].w);
+                            mma_f16(acl, l0.x, l1.x, l0.y, l1.y, pv[i].x, pv[i].y);
+                            mma_f16(acl, l0.z, l1.z, l0.w, l1.w, pv[i].z, pv[i].w);
                         }
                     }
-                    // D fragment: acc[0..1] = (chroma g, frames 2*t4, 2*t4+1), acc[2..3] = (chroma g+8, same frames)
-                    float* dst = part + (tl * 2 + kh) * 96;
-                    *reinterpret_cast<float2*>(dst + g * 8 + 2 * t4) = make_float2(acc[0], acc[1]);
-                    if (g < 4) *reinterpret_cast<float2*>(dst + (g + 8) * 8 + 2 * t4) = make_float2(acc[2], acc[3]);
+                    // D fragment: [0..1] = (chroma g, frames 2*t4, 2*t4+1), [2..3] = (chroma g+8, same frames)
+                    constexpr float kLo = 1.0f / 2048.0f;
+                    float* dst = part2 + (tl * 2 + kh) * 96;
+                    *reinterpret_cast<float2*>(dst + g * 8 + 2 * t4) = make_float2(fmaf(acl[0], kLo, acc[0]), fmaf(acl[1], kLo, acc[1]));
+                    if (g < 4)
+                        *reinterpret_cast<float2*>(dst + (g + 8) * 8 + 2 * t4) = make_float2(fmaf(acl[2], kLo, acc[2]), fmaf(acl[3], kLo, acc[3]));
                 }
                 __syncthreads();
                 for (int fl = tid; fl < nt * 8; fl += kThreads) {
                     const int f = tile0 * 8 + fl;
                     if (f < T) {
-                        const float* q = part + (fl >> 3) * 192 + (fl & 7);
-                        const float pn = gP[static_cast<size_t>(f) * kPStride + 1024];     // Nyquist bin
+                        const float* q = part2 + (fl >> 3) * 192 + (fl & 7);
+                        const float pn = gNy[f];                            // scaled Nyquist bin
                         float raw[kChroma];
                         float mx = 0.0f;
 #pragma unroll
                         for (int c = 0; c < kChroma; ++c) {
-                            raw[c] = fmaf(sW[c * kWStride + 1024], pn, q[c * 8] + q[96 + c * 8]);
+                            raw[c] = fmaf(wny[c], pn, q[c * 8] + q[96 + c * 8]);
                             mx = fmaxf(mx, fabsf(raw[c]));
                         }
-                        if (mx < FLT_MIN) mx = 1.0f;
+                        // librosa.util.normalize: lengths below tiny(float32) are replaced by 1 (in unscaled units)
+                        const float inv_s = gInvS[f];
+                        const bool small = mx * inv_s < FLT_MIN;
 #pragma unroll
-                        for (int c = 0; c < kChroma; ++c) csum[c] += static_cast<double>(__fdiv_rn(raw[c], mx));
+                        for (int c = 0; c < kChroma; ++c)
+                            csum[c] += static_cast<double>(small ? raw[c] * inv_s : __fdiv_rn(raw[c], mx));
                     }
                 }
                 __syncthreads();

@@ -24,7 +24,7 @@ class TablesHost(C.Structure):
                 ("mel_flush32", C.c_int32),
                 ("hann", C.c_void_p), ("tw1", C.c_void_p), ("tw2", C.c_void_p), ("mel_ab", C.c_void_p),
                 ("mel_mask", C.c_void_p), ("mel_src", C.c_void_p),
-                ("chroma", C.c_void_p), ("dct", C.c_void_p), ("edges", C.c_void_p)]
+                ("chroma16", C.c_void_p), ("chroma_ny", C.c_void_p), ("dct", C.c_void_p), ("edges", C.c_void_p)]
 
 
 class DebugOut(C.Structure):
@@ -82,8 +82,8 @@ def check(rc: int):
 def make_tables_struct(tb: dict):
     """TablesHost pointing into the numpy arrays of tables.build_tables (keeps them alive via .keep)."""
     keep = {k: np.ascontiguousarray(tb[k]) for k in
-            ("hann", "tw1", "tw2", "mel_ab", "mel_mask", "mel_src", "chroma", "dct", "edges")}
-    assert keep["hann"].dtype == np.float32 and keep["chroma"].dtype == np.float32
+            ("hann", "tw1", "tw2", "mel_ab", "mel_mask", "mel_src", "chroma16", "chroma_ny", "dct", "edges")}
+    assert keep["hann"].dtype == np.float32 and keep["chroma16"].dtype == np.float16 and keep["chroma_ny"].dtype == np.float32
     assert keep["dct"].dtype == np.float64 and keep["edges"].dtype == np.float64
     assert keep["mel_ab"].dtype == np.float32 and keep["mel_mask"].dtype == np.uint32 and keep["mel_src"].dtype == np.int32
     t = TablesHost(sr=int(tb["sr"]), pip_kmin=int(tb["pip_kmin"]), pip_kmax=int(tb["pip_kmax"]),

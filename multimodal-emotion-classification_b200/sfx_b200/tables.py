@@ -14,8 +14,9 @@ Layouts are chosen for the kernels (see DESIGN.md "HBM / SMEM layout"), not for 
   mel_ab float32[33][32][2]   (falling, rising) Slaney weights of bin 32*lane + j at [j][lane]; mel_mask uint32[32]
                               flush bits, mel_src int32[128][3] partial-sum slots (see mel_chunk_layout)
   melw   float32[mel_rows][32] transposed/padded sparse mel weights (dense-bank audit layout, host tests only)
-  chroma float32[100][12][1056] one bank per tuning edge, bin axis zero-padded to 1056, values rounded to TF32
-                              (operand of the tensor-core chroma projection); chroma_f32 is the unrounded bank
+  chroma16 float16[100][2][12][1056] one bank per tuning edge as hi + 2^-11 * lo (operands of the tensor-core chroma
+                              projection), bin axis zero-padded to 1056; chroma_ny float32[100][12] Nyquist-bin weights;
+                              chroma_f32 is the dense float32 bank (host tests only)
   dct    float64[128][128]    rows k of the ortho DCT-II
   edges  float64[101]         np.linspace(-0.5, 0.5, 101)
 """
@@ -86,6 +87,14 @@ def round_to_tf32(x: np.ndarray) -> np.ndarray:
     """Round float32 to the TF32 grid (10-bit mantissa), nearest / ties away: what cvt.rna.tf32.f32 does."""
     b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
     return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def split_fp16(x: np.ndarray):
+    """x ~= hi + lo * 2^-11 with hi, lo in float16 (lo is pre-scaled by 2^11 so it stays in the normal range)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    hi = x.astype(np.float16)
+    lo = ((x.astype(np.float64) - hi.astype(np.float64)) * 2048.0).astype(np.float16)
+    return hi, lo
 
 
 def tuning_edges() -> np.ndarray:
@@ -214,6 +223,9 @@ def build_tables(sr: int = 22050) -> dict:
         chroma[i, :, :N_BINS] = chroma_bank(sr, float(edges[i]))
     kmin, kmax = piptrack_bin_range(sr)
     chunk = mel_chunk_layout(sr, mb)
+    c_hi, c_lo = split_fp16(chroma)
+    chroma16 = np.ascontiguousarray(np.stack([c_hi, c_lo], axis=1))          # [100][2][12][1056] float16
+    chroma_ny = np.ascontiguousarray(chroma[:, :, N_BINS - 1])               # [100][12] float32 (Nyquist bin)
     return dict(**chunk, sr=sr, hann=hann, tw1=np.ascontiguousarray(tw1), tw2=np.ascontiguousarray(tw2),
                 mel_dense=mb, melw=melw, mel_lo=mel_lo, mel_off=mel_off, mel_len=mel_len,
-                chroma=round_to_tf32(chroma), chroma_f32=chroma, dct=dct_matrix(), edges=edges, pip_kmin=kmin, pip_kmax=kmax)
+                chroma16=chroma16, chroma_ny=chroma_ny, chroma_f32=chroma, dct=dct_matrix(), edges=edges, pip_kmin=kmin, pip_kmax=kmax)

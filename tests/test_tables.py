@@ -16,11 +16,12 @@ def test_banks_bit_identical_to_oracle():
     for i in (0, 17, 50, 83, 99):
         ref = lp.chroma_filterbank(tuning=float(e[i]))
         assert np.array_equal(tb["chroma_f32"][i, :, :1025], ref)
-        assert not tb["chroma"][i, :, 1025:].any()
-        # device operand: TF32-rounded (10-bit mantissa, round to nearest): <= 2^-11 relative
-        dev = tb["chroma"][i, :, :1025]
-        assert np.all(np.abs(dev - ref) <= np.abs(ref) * 2.0 ** -11)
-        assert not (dev.view(np.uint32) & 0x1FFF).any()
+        # device operand: hi + 2^-11 * lo in float16 reproduces the bank to ~2^-21 relative (+ fp16 subnormal floor)
+        hi, lo = tb["chroma16"][i, 0].astype(np.float64), tb["chroma16"][i, 1].astype(np.float64)
+        rec = hi + lo / 2048.0
+        assert np.all(np.abs(rec[:, :1025] - ref) <= np.abs(ref) * 2.0 ** -20 + 2.0 ** -34)
+        assert not tb["chroma16"][i, :, :, 1025:].any()
+        assert np.array_equal(tb["chroma_ny"][i], ref[:, 1024])
     assert np.array_equal(tb["hann"], lp.hann_window().astype(np.float32))
     assert (tb["pip_kmin"], tb["pip_kmax"]) == (14, 371)
 
