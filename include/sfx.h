@@ -124,6 +124,34 @@ int         sfx_extract_host(int device, int32_t sr, const float *host_wave, int
 /* Release cached device buffers/tables of `device` (tests; process exit does it implicitly). */
 int         sfx_release(int device);
 
+/* ---- scope row f1: device-resident StandardScaler + speech DNN forward ------------------------------------------
+ * Consumer of the feature rows in the reference's inference/speech_inference.py:66-76 (scaler.transform + model.predict)
+ * and :85-105 (layers[-3] tap); architecture of model_training/train_speech_model.py:55-90.  FP32 kernels. */
+typedef struct {
+    int32_t             n_layers;      /* dense layers (6 for the reference model) */
+    const int32_t      *dims;          /* [n_layers + 1] widths, e.g. 56,512,512,256,128,64,7 */
+    const float *const *kernel;        /* [n_layers] Keras layout [in][out] */
+    const float *const *bias;          /* [n_layers] */
+    const float *const *bn_gamma;      /* [n_layers - 1] BatchNormalization after every hidden Dense (may be NULL) */
+    const float *const *bn_beta;
+    const float *const *bn_mean;
+    const float *const *bn_var;
+    float               bn_eps;        /* Keras default 1e-3 */
+    const double       *scaler_mean;   /* [dims[0]] sklearn StandardScaler.mean_  (NULL = no scaler) */
+    const double       *scaler_scale;  /* [dims[0]] sklearn StandardScaler.scale_ */
+} sfx_dnn_host;
+
+int         sfx_dnn_create(int device, const sfx_dnn_host *model, void **handle);
+int         sfx_dnn_destroy(void *handle);
+size_t      sfx_dnn_workspace_bytes(void *handle, int32_t B);
+int         sfx_dnn_launches_per_forward(void *handle);
+const char *sfx_dnn_last_error(void);
+/* feats [B] rows of dims[0] float32 (device, e.g. the output of sfx_extract); probs [B][dims[n]] softmax outputs;
+ * tap [B][dims[n-1]] last hidden activation or NULL.  Stream-ordered. */
+int         sfx_dnn_forward(void *handle, const float *feats, int64_t feat_stride, int32_t B, float *probs,
+                            int64_t probs_stride, float *tap, int64_t tap_stride, void *workspace,
+                            size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

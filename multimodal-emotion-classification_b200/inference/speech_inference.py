@@ -1,0 +1,46 @@
+"""
+Batched, device-resident speech inference -- the B200 counterpart of the reference's inference/speech_inference.py.
+
+The reference builds features per file with librosa, scales them with a joblib'd StandardScaler and runs a Keras .h5
+(speech_inference.py:60-105).  Here a whole batch of clips goes waveform -> 56-d features -> scaler -> DNN on the GPU
+(sfx_extract + sfx_dnn_forward) and only the 7 probabilities (and optionally the 64-d fusion tap) come back.
+The result dictionaries have the reference's keys.  Loading the reference's .h5/.pkl artefacts needs TensorFlow/h5py/
+joblib, which are not part of this build: weights are passed as a dict of numpy arrays (see sfx_b200/dnn.py).
+"""
+from typing import Dict, List
+
+import numpy as np
+
+from config import Config
+
+
+class BatchedSpeechInference:
+    def __init__(self, weights: dict, device=None, sr: int = Config.SAMPLE_RATE):
+        import torch
+        from sfx_b200 import get_extractor
+        from sfx_b200.dnn import SpeechDNN
+        self.emotions = Config.EMOTIONS
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.extractor = get_extractor(self.device, sr)
+        self.dnn = SpeechDNN(weights, self.device)
+
+    def forward(self, waves, lengths=None, n_samples=None):
+        """cuda float32 [B, L] -> (probs [B,7], tap [B,64], features [B,56]), all device tensors, stream-ordered."""
+        feats = self.extractor.extract(waves, lengths, n_samples=n_samples)
+        probs, tap = self.dnn.forward(feats)
+        return probs, tap, feats
+
+    def predict_batch(self, waves, lengths=None) -> List[Dict]:
+        """Reference SpeechInference.predict (:60-77) for every clip of the batch."""
+        probs, _, _ = self.forward(waves, lengths)
+        p = probs.cpu().numpy()
+        out = []
+        for row in p:
+            idx = int(np.argmax(row))
+            out.append({'emotion': self.emotions[idx], 'confidence': float(row[idx]), 'all_probabilities': row.tolist()})
+        return out
+
+    def extract_features_batch(self, waves, lengths=None):
+        """Reference SpeechInference.extract_features (:79-105): (intermediate [B,64], predictions [B,7]) as numpy."""
+        probs, tap, _ = self.forward(waves, lengths)
+        return tap.cpu().numpy(), probs.cpu().numpy()

@@ -32,7 +32,14 @@ class DebugOut(C.Structure):
                 ("clip_info", C.c_void_p), ("T_dbg", C.c_int32)]
 
 
-EXPORTS = ["sfx_abi_version", "sfx_last_error", "sfx_device_count", "sfx_init_tables", "sfx_workspace_bytes",
+class DnnHost(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_void_p), ("kernel", C.c_void_p), ("bias", C.c_void_p),
+                ("bn_gamma", C.c_void_p), ("bn_beta", C.c_void_p), ("bn_mean", C.c_void_p), ("bn_var", C.c_void_p),
+                ("bn_eps", C.c_float), ("scaler_mean", C.c_void_p), ("scaler_scale", C.c_void_p)]
+
+
+EXPORTS = ["sfx_dnn_create", "sfx_dnn_destroy", "sfx_dnn_workspace_bytes", "sfx_dnn_launches_per_forward",
+           "sfx_dnn_last_error", "sfx_dnn_forward", "sfx_abi_version", "sfx_last_error", "sfx_device_count", "sfx_init_tables", "sfx_workspace_bytes",
            "sfx_launches_per_extract", "sfx_extract", "sfx_extract_debug", "sfx_extract_host", "sfx_release"]
 
 
@@ -67,6 +74,18 @@ def load():
                                      C.c_void_p, C.c_int64, C.c_int32]
     lib.sfx_release.restype = C.c_int
     lib.sfx_release.argtypes = [C.c_int]
+    lib.sfx_dnn_create.restype = C.c_int
+    lib.sfx_dnn_create.argtypes = [C.c_int, C.POINTER(DnnHost), C.POINTER(C.c_void_p)]
+    lib.sfx_dnn_destroy.restype = C.c_int
+    lib.sfx_dnn_destroy.argtypes = [C.c_void_p]
+    lib.sfx_dnn_workspace_bytes.restype = C.c_size_t
+    lib.sfx_dnn_workspace_bytes.argtypes = [C.c_void_p, C.c_int32]
+    lib.sfx_dnn_launches_per_forward.restype = C.c_int
+    lib.sfx_dnn_launches_per_forward.argtypes = [C.c_void_p]
+    lib.sfx_dnn_last_error.restype = C.c_char_p
+    lib.sfx_dnn_forward.restype = C.c_int
+    lib.sfx_dnn_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
     if lib.sfx_abi_version() != 1:
         raise RuntimeError("libsfx_b200.so ABI version mismatch; rebuild with sfx_b200.build.build(force=True)")
     _LIB = lib
