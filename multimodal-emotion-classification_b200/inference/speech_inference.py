@@ -40,6 +40,25 @@ class BatchedSpeechInference:
             out.append({'emotion': self.emotions[idx], 'confidence': float(row[idx]), 'all_probabilities': row.tolist()})
         return out
 
+    def heuristic_predict_batch(self, waves, lengths=None) -> List[Dict]:
+        """Reference SpeechInference._heuristic_predict (:36-58) for a batch: thresholds on the frame-mean rms and
+        spectral centroid (columns 55 and 53 of the feature rows); used by the reference when no .h5 is present."""
+        feats = self.extractor.extract(waves, lengths)
+        spec = feats[:, Config.N_MFCC + 12:Config.N_MFCC + 16].cpu().numpy()
+        out = []
+        for zcr, centroid, rolloff, rms in spec:
+            if rms > 0.06 and centroid > 2000:
+                label = 'angry'
+            elif rms < 0.02 and centroid < 1500:
+                label = 'sad'
+            else:
+                label = 'neutral'
+            probs = np.ones(len(self.emotions)) * (0.1 / (len(self.emotions) - 1))
+            idx = self.emotions.index(label)
+            probs[idx] = 0.9
+            out.append({'emotion': label, 'confidence': float(probs[idx]), 'all_probabilities': probs.tolist()})
+        return out
+
     def extract_features_batch(self, waves, lengths=None):
         """Reference SpeechInference.extract_features (:79-105): (intermediate [B,64], predictions [B,7]) as numpy."""
         probs, tap, _ = self.forward(waves, lengths)

@@ -90,3 +90,20 @@ def test_config3_tess_shaped_features_feed_dnn_on_device():
     assert [r["emotion"] for r in res] == [od.EMOTIONS[i] for i in rp[:4].argmax(axis=1)]
     t64, p7 = eng.extract_features_batch(w[:4])
     assert t64.shape == (4, 64) and p7.shape == (4, 7)
+
+
+@pytest.mark.gpu
+def test_heuristic_predict_batch_thresholds():
+    """speech_inference.py:36-58: rms > 0.06 & centroid > 2000 -> angry; rms < 0.02 & centroid < 1500 -> sad; else neutral."""
+    from inference.speech_inference import BatchedSpeechInference
+    n = 66150
+    t = np.arange(n) / 22050.0
+    loud_bright = (0.3 * np.random.default_rng(0).standard_normal(n)).clip(-1, 1).astype(np.float32)      # rms .3, centroid ~5.5k
+    quiet_low = (0.01 * np.sin(2 * np.pi * 200 * t)).astype(np.float32)                                   # rms .007, centroid ~200
+    mid = (0.05 * np.sin(2 * np.pi * 300 * t)).astype(np.float32)                                         # rms .035
+    eng = BatchedSpeechInference(od.random_model(0), torch.device("cuda", 0))
+    res = eng.heuristic_predict_batch(torch.from_numpy(np.stack([loud_bright, quiet_low, mid])).cuda())
+    assert [r["emotion"] for r in res] == ["angry", "sad", "neutral"]
+    assert all(abs(sum(r["all_probabilities"]) - 1.0) < 1e-9 and r["confidence"] == 0.9 for r in res)
+    spec = lp.extract_spectral_features(quiet_low, 22050)
+    assert spec[3] < 0.02 and spec[1] < 1500
