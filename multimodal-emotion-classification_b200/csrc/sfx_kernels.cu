@@ -411,6 +411,47 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         for (int t = warp; t < T; t += kWarps) {
             float re[32], im[32];
             load_frame(x, n, t, lane, aligned8, re, im);
+            // ---- all-zero frame (the zero tail load_audio pads short clips with, reference :15-16): every result is
+            //      known in closed form and equals what the general path computes from zeros, so the FFT is skipped:
+            //      |X|^2 = 0, log-mel = 10*log10(1e-10) in all bands, no peaks, centroid = rolloff = 0, hop energy 0,
+            //      no sign changes.
+            {
+                unsigned any_bits = 0;
+#pragma unroll
+                for (int m1 = 0; m1 < 32; ++m1) any_bits |= __float_as_uint(re[m1]) | __float_as_uint(im[m1]);
+                if (!__any_sync(0xffffffffu, (any_bits & 0x7fffffffu) != 0u)) {
+                    const float lm0 = 3.01029995663981195f * __log2f(1e-10f);
+                    float* Lg = gL + static_cast<size_t>(t) * kMels;
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4) Lg[32 * s4 + lane] = lm0;
+                    uint4* dst = reinterpret_cast<uint4*>(gP16 + static_cast<size_t>(t) * kP16Stride + 32 * lane);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(0u, 0u, 0u, 0u);
+                    if (lane == 0) {
+                        gE[t] = 0.0f;
+                        gNy[t] = 0.0f;
+                        gInvS[t] = 0.0f;
+                        s_f[warp] = fmaxf(s_f[warp], lm0);
+                    }
+                    if (kDebug) {
+                        if (t < p.dbg.T_dbg) {
+                            if (p.dbg.P) {
+                                float* dP = p.dbg.P + (static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kPStride;
+                                for (int k = lane; k < kBins; k += 32) dP[k] = 0.0f;
+                            }
+                            if (p.dbg.logmel)
+                                for (int m = lane; m < kMels; m += 32)
+                                    p.dbg.logmel[(static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kMels + m] = lm0;
+                            if (p.dbg.frame_feat && lane == 0) {
+                                float* ff = p.dbg.frame_feat + (static_cast<size_t>(clip) * p.dbg.T_dbg + t) * 4;
+                                ff[0] = 0.f; ff[1] = 0.f; ff[3] = 0.f;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
+            }
             // ---- energy of hop t (samples [512t, 512t+512) = rows 16..23); librosa.feature.rms of frame t is
             //      sqrt((E[t-2] + E[t-1] + E[t] + E[t+1]) / 2048) and is pooled in the epilogue
             {
