@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     float2* s_tw1 = s_hann + 1024;
     float2* s_tw2 = s_tw1 + 1024;
     float2* s_melab = s_tw2 + 512;                                           // [33*32]  (tw2: rows k2 < 16 only)
-    float* s_ex = reinterpret_cast<float*>(s_melab + 33 * 32);               // [kWarps][kExFloats]
+    float* s_ex = reinterpret_cast<float*>(s_melab + 17 * 64);               // [kWarps][kExFloats]
     double* s_pool = reinterpret_cast<double*>(s_ex + kWarps * kExFloats);   // [256]
     double* s_wacc = s_pool + 256;                                           // [kWarps][16]
     double* s_edges = s_wacc + kWarps * 16;                                  // [104]
@@ -352,12 +352,19 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevTables& tb = p.tb;
 
+    // tables are stored row-paired: element (row r, lane) sits at float2 index (r/2)*64 + 2*lane + (r&1), so one LDS.128
+    // serves rows r, r+1 of a lane (conflict-free: consecutive lanes are 16 B apart)
     for (int i = tid; i < 1024; i += kThreads) {
-        s_hann[i] = tb.hann[i];
-        s_tw1[i] = tb.tw1[i];
-        if (i < 512) s_tw2[i] = tb.tw2[i];
+        const int r = i >> 5, l = i & 31;
+        const int d = (r >> 1) * 64 + 2 * l + (r & 1);
+        s_hann[d] = tb.hann[i];
+        s_tw1[d] = tb.tw1[i];
+        if (i < 512) s_tw2[d] = tb.tw2[i];
     }
-    for (int i = tid; i < 33 * 32; i += kThreads) s_melab[i] = tb.mel_ab[i];
+    for (int i = tid; i < 33 * 32; i += kThreads) {
+        const int r = i >> 5, l = i & 31;
+        s_melab[(r >> 1) * 64 + 2 * l + (r & 1)] = tb.mel_ab[i];      // row 32 (Nyquist) lands at 16*64 + 2*lane
+    }
     for (int i = tid; i <= kTunings; i += kThreads) s_edges[i] = tb.edges[i];
     const unsigned mel_mask = tb.mel_mask[lane];
     const int mel_ps = tb.mel_ps;
@@ -494,27 +501,36 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
 
             // ---- Hann window (periodic, scipy.signal.get_window('hann', 2048))
 #pragma unroll
-            for (int m1 = 0; m1 < 32; ++m1) {
-                const float2 w = s_hann[32 * m1 + lane];
+            for (int m1 = 0; m1 < 32; m1 += 2) {
+                const float4 w = *reinterpret_cast<const float4*>(s_hann + (m1 >> 1) * 64 + 2 * lane);
                 re[m1] *= w.x;
                 im[m1] *= w.y;
+                re[m1 + 1] *= w.z;
+                im[m1 + 1] *= w.w;
             }
             // ---- 1024-pt complex FFT: radix-32 over m1, twiddle, transpose, radix-32 over m2
             fft32(re, im);
-            sfor<32>([&](auto K) {
-                constexpr int k1 = decltype(K)::value;
-                constexpr int a = brev5(k1);
-                const float2 w = s_tw1[k1 * 32 + lane];
-                const float r = fmaf(re[a], w.x, -(im[a] * w.y));
-                const float i = fmaf(re[a], w.y, im[a] * w.x);
-                ex[k1 * 33 + lane] = make_float2(r, i);
+            // exchange tile: float4 slot (k1/2)*33 + lane holds rows k1, k1+1 of column `lane`
+            sfor<16>([&](auto K) {
+                constexpr int k1 = 2 * decltype(K)::value;
+                constexpr int a = brev5(k1), b = brev5(k1 + 1);
+                const float4 w = *reinterpret_cast<const float4*>(s_tw1 + (k1 >> 1) * 64 + 2 * lane);
+                float4 v;
+                v.x = fmaf(re[a], w.x, -(im[a] * w.y));
+                v.y = fmaf(re[a], w.y, im[a] * w.x);
+                v.z = fmaf(re[b], w.z, -(im[b] * w.w));
+                v.w = fmaf(re[b], w.w, im[b] * w.z);
+                reinterpret_cast<float4*>(ex)[(k1 >> 1) * 33 + lane] = v;
             });
             __syncwarp();
+            {
+                const float2* src = ex + ((lane >> 1) * 33) * 2 + (lane & 1);      // row `lane`: half of the float4 slots
 #pragma unroll
-            for (int m2 = 0; m2 < 32; ++m2) {
-                const float2 v = ex[lane * 33 + m2];
-                re[m2] = v.x;
-                im[m2] = v.y;
+                for (int m2 = 0; m2 < 32; ++m2) {
+                    const float2 v = src[2 * m2];
+                    re[m2] = v.x;
+                    im[m2] = v.y;
+                }
             }
             __syncwarp();
             fft32(re, im);
@@ -527,6 +543,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 float* PbL = Pb + lane;
                 float* PbU = Pb + (lane == 0 ? 1056 : 1055 - lane);
                 const int plane = (32 - lane) & 31;
+                float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 sfor<16>([&](auto K) {
                     constexpr int k2 = decltype(K)::value;
                     constexpr int a = brev5(k2), b = brev5(31 - k2), c = brev5((32 - k2) & 31);
@@ -534,7 +551,8 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                     float pr = __shfl_sync(0xffffffffu, re[b], plane);
                     float pi = __shfl_sync(0xffffffffu, im[b], plane);
                     if (lane == 0) { pr = re[c]; pi = im[c]; }
-                    const float2 w = s_tw2[k2 * 32 + lane];          // (0.5 cos, 0.5 sin)(2 pi k / 2048)
+                    if constexpr ((k2 & 1) == 0) w4 = *reinterpret_cast<const float4*>(s_tw2 + (k2 >> 1) * 64 + 2 * lane);
+                    const float2 w = (k2 & 1) ? make_float2(w4.z, w4.w) : make_float2(w4.x, w4.y);   // (0.5 cos, 0.5 sin)(2 pi k / 2048)
                     const float er = zr + pr, ei = zi - pi, orr = zr - pr, oi = zi + pi;
                     const float u = fmaf(w.x, orr, w.y * oi);         // Re(w O)/2
                     const float v = fmaf(w.x, oi, -(w.y * orr));      // Im(w O)/2
@@ -584,15 +602,16 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 const float scale = __uint_as_float(sbits);
                 unsigned h2[16];
                 float hprev = 0.0f;
+                float4 ab4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 sfor<32>([&](auto J) {
                     constexpr int j = decltype(J)::value;
                     const float P = Prow[j];
                     if constexpr ((j & 1) == 0) hprev = P * scale;
                     else h2[j >> 1] = pack_half2(hprev, P * scale);
                     if (j > 0 && ((mel_mask >> j) & 1u)) { *pq++ = accA; accA = accB; accB = 0.0f; }
-                    const float2 ab = s_melab[j * 32 + lane];
-                    accA = fmaf(ab.x, P, accA);
-                    accB = fmaf(ab.y, P, accB);
+                    if constexpr ((j & 1) == 0) ab4 = *reinterpret_cast<const float4*>(s_melab + (j >> 1) * 64 + 2 * lane);
+                    accA = fmaf((j & 1) ? ab4.z : ab4.x, P, accA);
+                    accB = fmaf((j & 1) ? ab4.w : ab4.y, P, accB);
                     const float sv = sqrt_approx(P);
                     run += sv;
                     s[j] = run;
@@ -602,7 +621,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 if (lane == 31) {
                     const float P = Pb[1024 + 32];
                     if (tb.mel_flush32) { *pq++ = accA; accA = accB; accB = 0.0f; }
-                    const float2 ab = s_melab[32 * 32 + 31];
+                    const float2 ab = s_melab[16 * 64 + 2 * 31];
                     accA = fmaf(ab.x, P, accA);
                     accB = fmaf(ab.y, P, accB);
                     const float sv = sqrt_approx(P);
@@ -992,7 +1011,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
 
 // ------------------------------------------------------------------------------------------------
 size_t smem_bytes() {
-    return sizeof(float2) * (2560 + 33 * 32) + sizeof(float) * kWarps * kExFloats +
+    return sizeof(float2) * (2560 + 17 * 64) + sizeof(float) * kWarps * kExFloats +
            sizeof(double) * (256 + kWarps * 16 + 104) + sizeof(int) * (256 + 32) + sizeof(float) * 32;
 }
 
