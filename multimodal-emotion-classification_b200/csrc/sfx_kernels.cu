@@ -200,50 +200,6 @@ __device__ unsigned radix_select(const unsigned* keys, int np, int r, int* s_his
     return prefix;
 }
 
-// reduce-scatter of 32 per-lane values: afterwards lane l holds sum over lanes of v[l] in v[0]
-__device__ __forceinline__ float reduce_scatter32(float (&v)[32], int lane) {
-#pragma unroll
-    for (int h = 16; h >= 1; h >>= 1) {
-        const bool up = (lane & h) != 0;
-#pragma unroll
-        for (int i = 0; i < h; ++i) {
-            const float send = up ? v[i] : v[i + h];
-            const float keep = up ? v[i + h] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-        }
-    }
-    return v[0];
-}
-// 16 per-lane values: lanes l and l^16 both end with the warp total of v[l & 15]
-__device__ __forceinline__ float reduce_scatter16(float (&v)[16], int lane) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
-#pragma unroll
-    for (int h = 8; h >= 1; h >>= 1) {
-        const bool up = (lane & h) != 0;
-#pragma unroll
-        for (int i = 0; i < h; ++i) {
-            const float send = up ? v[i] : v[i + h];
-            const float keep = up ? v[i + h] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-        }
-    }
-    return v[0];
-}
-
-__device__ __forceinline__ unsigned to_tf32(float x) {
-    unsigned u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return u;
-}
-// D(16x8, f32) += A(16x8, tf32, row) * B(8x8, tf32, col): warp-level tensor-core MMA, FP32 accumulate
-__device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
-                                         unsigned b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
 // D(16x8, f32) += A(16x16, f16, row) * B(16x8, f16, col): warp-level tensor-core MMA, FP32 accumulate
 __device__ __forceinline__ void mma_f16(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
                                         unsigned b1) {
@@ -255,61 +211,7 @@ __device__ __forceinline__ unsigned pack_half2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const unsigned*>(&h);
 }
-
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
-
-// One chroma tile: NF consecutive frames x 12 chroma for the warp; lane owns bins 4*lane + 128*j.  The |X|^2 rows come
-// from the scratch slice (L2/HBM): the loads of step j+1 are issued before the FMAs of step j.  Returns through `red`
-// (shared, >= 48 floats): red[f*12 + c] = sum over bins < 1024 of W[c][k] * P[f][k].
-template <int NF>
-__device__ __forceinline__ void chroma_tile(const float* __restrict__ sW, const float* Pt, float* red, int lane) {
-    float acc[NF * kChroma];
-#pragma unroll
-    for (int i = 0; i < NF * kChroma; ++i) acc[i] = 0.0f;
-    float4 pn[NF];
-#pragma unroll
-    for (int f = 0; f < NF; ++f) pn[f] = *reinterpret_cast<const float4*>(Pt + f * kPStride + 4 * lane);
-#pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
-        const int k = 4 * lane + 128 * j;
-        float4 pv[NF];
-#pragma unroll
-        for (int f = 0; f < NF; ++f) pv[f] = pn[f];
-        if (j < 7) {
-#pragma unroll
-            for (int f = 0; f < NF; ++f) pn[f] = *reinterpret_cast<const float4*>(Pt + f * kPStride + k + 128);
-        }
-#pragma unroll
-        for (int c = 0; c < kChroma; ++c) {
-            const float4 w = *reinterpret_cast<const float4*>(sW + c * kPStride + k);
-#pragma unroll
-            for (int f = 0; f < NF; ++f) {
-                float a = acc[f * kChroma + c];
-                a = fmaf(w.x, pv[f].x, a);
-                a = fmaf(w.y, pv[f].y, a);
-                a = fmaf(w.z, pv[f].z, a);
-                a = fmaf(w.w, pv[f].w, a);
-                acc[f * kChroma + c] = a;
-            }
-        }
-    }
-    // warp totals: value i ends up in lane i (i < 32) resp. lanes (i-32), (i-32)^16
-    constexpr int NV = NF * kChroma;
-    {
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = (i < NV) ? acc[i] : 0.0f;
-        const float r = reduce_scatter32(v, lane);
-        if (lane < NV) red[lane] = r;
-    }
-    if constexpr (NV > 32) {
-        float u[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) u[i] = (32 + i < NV) ? acc[32 + i] : 0.0f;
-        const float r16 = reduce_scatter16(u, lane);
-        if (lane < NV - 32) red[32 + lane] = r16;
-    }
-}
 
 // raw samples of STFT frame t (zero padded) -> re[m1] = x[2m], im[m1] = x[2m+1], m = 32*m1 + lane
 __device__ __forceinline__ void load_frame(const float* __restrict__ x, long long n, int t, int lane, bool aligned8,
@@ -651,9 +553,10 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 const float thr = __fmul_rn(0.85f, total);
                 // first bin whose cumulative |X| reaches the threshold = number of (monotone) prefix sums below it
                 const float thrL = thr - exc;
-                int cnt = 0;
+                float cntf = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) cnt += (s[j] < thrL) ? 1 : 0;
+                for (int j = 0; j < 32; ++j) cntf += (s[j] < thrL) ? 1.0f : 0.0f;
+                const int cnt = static_cast<int>(cntf);
                 int first = (cnt < 32) ? 32 * lane + cnt : 1024;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
@@ -696,12 +599,14 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 const int d0 = pidx(kfirst) - pidx(kfirst - 1), d1 = pidx(kfirst + 1) - pidx(kfirst - 1);
                 const int nrows = (tb.kmax - tb.kmin + 32) >> 5;          // <= 16 (bins 1..1023, 32 per row)
                 unsigned flags = 0;                                      // bit r: this lane's bin of row r is a peak
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    if (r < nrows) {
-                        const float* q = q0 + 33 * r;
+                {
+                    const float* q = q0;
+                    const int rlast = tb.kmax - kfirst;                  // rows with 32*r <= rlast hold a bin of the range
+#pragma unroll 4
+                    for (int r = 0; r < nrows; ++r, q += 33) {
                         const float pm = q[0], pc = q[d0], pp = q[d1];
-                        if (kfirst + 32 * r <= tb.kmax && pc > ref && pc > pm && pc >= pp) flags |= 1u << r;
+                        const bool pk = (32 * r <= rlast) && pc > ref && pc > pm && pc >= pp;
+                        flags |= (pk ? 1u : 0u) << r;
                     }
                 }
                 // lane-wise compaction: exclusive prefix of the per-lane peak counts, one atomic per frame

@@ -1,7 +1,8 @@
 """numpy model of the kernel's per-warp 2048-point real FFT (lane/register structure, same tables).
 
-Mirrors csrc/sfx_kernels.cu::frame_fft: z[m] = x[2m] + i x[2m+1]; m = 32*m1 + lane;
-stage 1: radix-2 DIF FFT-32 over m1 in registers (bit-reversed outputs), twiddle tw1[k1][lane],
+Mirrors the frame loop of csrc/sfx_kernels.cu: z[m] = x[2m] + i x[2m+1]; m = 32*m1 + lane;
+stage 1: radix-2 FFT-32 over m1 in registers, outputs in bit-reversed slots (the kernel uses the DIT form on the
+bit-reversed register view, this model the equivalent DIF form), twiddle tw1[k1][lane],
 exchange through a [32][33] tile, stage 2: FFT-32 over m2, then the real-FFT unpack with the
 partner bin held by lane (32-lane)&31, register 31-k2 (lane 0: register (32-k2)&31).
 """
