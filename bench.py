@@ -97,7 +97,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------- synthetic pool on device
@@ -200,7 +200,17 @@ def ncu_traffic_per_clip():
 
 
 # --------------------------------------------------------------------------------------------- main arm
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL banner, library chatter)
+    was redirected to stderr at the file-descriptor level."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+
+
 def main():
+    os.dup2(2, 1)                  # C-level writers (e.g. "NCCL version ...") must not precede the JSON line on stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -348,7 +358,7 @@ def main():
             "cpu_baseline": cpu_baseline,
             "parity": parity,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
