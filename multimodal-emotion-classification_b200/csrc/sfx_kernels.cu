@@ -213,6 +213,33 @@ __device__ __forceinline__ unsigned pack_half2(float a, float b) {
 }
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
+// ---- TMA bulk copy (global -> shared) completing on an mbarrier
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000ll) __trap();     // ~2 s: a lost completion must fail loudly, not hang the GPU
+    }
+}
+
 // raw samples of STFT frame t (zero padded) -> re[m1] = x[2m], im[m1] = x[2m+1], m = 32*m1 + lane
 __device__ __forceinline__ void load_frame(const float* __restrict__ x, long long n, int t, int lane, bool aligned8,
                                            float (&re)[32], float (&im)[32]) {
@@ -247,7 +274,8 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     double* s_pool = reinterpret_cast<double*>(s_ex + kWarps * kExFloats);   // [256]
     double* s_wacc = s_pool + 256;                                           // [kWarps][16]
     double* s_edges = s_wacc + kWarps * 16;                                  // [104]
-    int* s_hist = reinterpret_cast<int*>(s_edges + 104);                     // [256]
+    unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_edges + 104);   // chroma-bank TMA barrier
+    int* s_hist = reinterpret_cast<int*>(s_mbar + 1);                        // [256]
     int* s_i = s_hist + 256;                                                 // [32]
     float* s_f = reinterpret_cast<float*>(s_i + 32);                         // [32]
 
@@ -268,6 +296,8 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         s_melab[(r >> 1) * 64 + 2 * l + (r & 1)] = tb.mel_ab[i];      // row 32 (Nyquist) lands at 16*64 + 2*lane
     }
     for (int i = tid; i <= kTunings; i += kThreads) s_edges[i] = tb.edges[i];
+    if (tid == 0) mbar_init(s_mbar, 1);
+    unsigned bank_parity = 0;
     const unsigned mel_mask = tb.mel_mask[lane];
     const int mel_ps = tb.mel_ps;
     int msrc[4];                                   // 3 x 10-bit partial-sum slots per filter 32*s + lane
@@ -763,12 +793,15 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         }
 
         // ===================================== phase 3a: MFCC ======================================
-        // (also stages the tuning's FP16 hi/lo chroma bank into shared memory: the warp tiles are free now)
+        // The tuning's FP16 hi/lo chroma bank (50 688 B) is staged into the now-free warp tiles by one TMA bulk copy
+        // (cp.async.bulk, completes on an mbarrier) that runs underneath the MFCC pooling.
         __half* sW = reinterpret_cast<__half*>(s_ex);       // [2][12][kP16Stride]
+        fence_proxy_async_smem();                           // generic-proxy accesses of the tiles precede the async write
+        __syncthreads();
+        if (tid == 0)
+            bulk_copy_g2s(sW, tb.chroma16 + static_cast<size_t>(tuning_idx) * 2 * kChroma * kP16Stride,
+                          2 * kChroma * kP16Stride * 2, s_mbar);
         {
-            const uint4* Wg = reinterpret_cast<const uint4*>(tb.chroma16 + static_cast<size_t>(tuning_idx) * 2 * kChroma * kP16Stride);
-            uint4* Ws = reinterpret_cast<uint4*>(sW);
-            for (int i = tid; i < 2 * kChroma * kP16Stride / 8; i += kThreads) Ws[i] = __ldg(Wg + i);
             const float clampv = __fsub_rn(gmx, 80.0f);
             if (tid < 256) {
                 const int m = tid & 127, h = tid >> 7;
@@ -785,6 +818,8 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 out[tid] = static_cast<float>(d);
             }
         }
+        mbar_wait(s_mbar, bank_parity);                     // chroma bank has landed in shared memory
+        bank_parity ^= 1u;
 
         // ===================================== phase 3b: chroma ====================================
         // raw[c][t] = sum_k W[c][k] |X|^2[k][t] on the tensor cores: m16n8k16 FP16 MMAs with FP32 accumulators.  A = bank
@@ -917,7 +952,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
 // ------------------------------------------------------------------------------------------------
 size_t smem_bytes() {
     return sizeof(float2) * (2560 + 17 * 64) + sizeof(float) * kWarps * kExFloats +
-           sizeof(double) * (256 + kWarps * 16 + 104) + sizeof(int) * (256 + 32) + sizeof(float) * 32;
+           sizeof(double) * (256 + kWarps * 16 + 104 + 1) + sizeof(int) * (256 + 32) + sizeof(float) * 32;
 }
 
 cudaError_t configure_kernels(int* blocks_per_sm) {
