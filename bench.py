@@ -321,6 +321,36 @@ def main():
     e2e_value = Be * world * e2e_steps / e2e_s
     e2e_match = bool(torch.equal(h_out, out[:Be].cpu()))
 
+    # ---------------- small-batch behaviour (rank 0): single-clip latency through the host path (what one request of the
+    # reference's Flask app costs), and device-resident throughput at the batch sizes of configs[0] / configs[1]
+    small = None
+    if rank == 0:
+        small = {}
+        one_in = h_in[:1].numpy()
+        one_out = h_out[:1].numpy()
+        for _ in range(5):
+            ex.extract_host(one_in, out=one_out)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            ex.extract_host(one_in, out=one_out)
+        small["single_clip_host_latency_ms"] = (time.perf_counter() - t0) / 50 * 1e3
+        for nb, tag in ((64, "config1_64_clips"), (1440, "config2_1440_clips")):
+            sub = pool[:nb]
+            sub_out = out[:nb]
+            for _ in range(3):
+                ex.extract(sub, out=sub_out)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(20):
+                ex.extract(sub, out=sub_out)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / 20
+            small[tag] = {"ms_per_batch": ms, "clips_per_s": nb / (ms * 1e-3)}
+        ex.extract(pool, out=out)          # restore the full-batch output for the parity check below
+        torch.cuda.synchronize()
+
     # ---------------- parity spot check against the oracle on identical waveforms (rank 0)
     parity = None
     if rank == 0:
@@ -356,6 +386,7 @@ def main():
                          "note": f"{peak_src}; algorithmic bytes/launch = {B} clips x {BYTES_PER_CLIP} B; kernel avg "
                                  f"{kern_ms:.3f} ms (CUDA events); path is FP32-issue/SMEM bound (DESIGN.md), not HBM bound"},
             "cpu_baseline": cpu_baseline,
+            "small_batch": small,
             "parity": parity,
         }
         emit(line)
