@@ -89,8 +89,15 @@ int         sfx_init_tables(int device, const sfx_tables_host *tables);
  * Independent of the batch size (persistent CTAs each own a fixed scratch slice).  0 on error. */
 size_t      sfx_workspace_bytes(int device, int64_t max_samples);
 
-/* Number of kernels one sfx_extract call launches (for launch accounting). */
+/* Kernels launched by the most recent sfx_extract / sfx_extract_debug / sfx_extract_host call of this thread (1 before
+ * any call; fused pipeline: 1 per call or host chunk; split pipeline: 3 per chunk of <= 1024 clips). */
 int         sfx_launches_per_extract(void);
+
+/* Pipeline selection: 0 = auto (default: the frame-parallel two-kernel pipeline for batches <= 256 clips, where it has
+ * about half the latency, the fused persistent kernel above that, where it has the higher throughput), 1 = fused,
+ * 2 = split.  Also settable through the environment variable SFX_PIPELINE=auto|fused|split before the first call.
+ * Call sfx_workspace_bytes again after changing the mode. */
+int         sfx_set_pipeline(int mode);
 
 /* Batched extraction, device buffers.
  *   sr          sample rate of a table set uploaded with sfx_init_tables

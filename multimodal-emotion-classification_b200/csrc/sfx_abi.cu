@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -36,6 +37,7 @@ struct TableSet {               // one per sample rate
 struct DevCtx {
     bool ready = false;
     int sm_count = 0, blocks_per_sm = 0, grid_max = 0;
+    int frames_per_sm = 0, clips_per_sm = 0;      // split pipeline occupancies
     int max_pk = 0;             // max over table sets of local maxima that fit the piptrack bin range (multiple of 4)
     std::vector<TableSet> sets;
     std::vector<void*> allocs;
@@ -51,6 +53,27 @@ const TableSet* find_set(const DevCtx& c, int sr) {
 DevCtx g_ctx[kMaxDev];
 std::mutex g_mu;
 thread_local std::string g_err;
+thread_local int g_last_launches = 1;
+
+// Pipeline choice: 0 = auto (split for small batches, fused otherwise), 1 = fused, 2 = split.
+// Initial value from the environment variable SFX_PIPELINE (auto | fused | split); sfx_set_pipeline() overrides it.
+constexpr int kAutoSplitMaxB = 256;      // at or below this batch the frame-parallel split pipeline has lower latency
+int g_pipeline = [] {
+    const char* e = std::getenv("SFX_PIPELINE");
+    if (e && std::strcmp(e, "split") == 0) return 2;
+    if (e && std::strcmp(e, "fused") == 0) return 1;
+    return 0;
+}();
+bool use_split(int B) { return g_pipeline == 2 || (g_pipeline == 0 && B <= kAutoSplitMaxB); }
+
+// clips per chunk of the split pipeline: at most kSplitChunkMax, at most ~1 GiB of slices
+int split_chunk_for(size_t slice) {
+    const size_t budget = size_t(1) << 30;
+    size_t c = budget / slice;
+    if (c < 1) c = 1;
+    if (c > static_cast<size_t>(sfx::kSplitChunkMax)) c = sfx::kSplitChunkMax;
+    return static_cast<int>(c);
+}
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 int cuda_fail(cudaError_t e, const char* what) {
@@ -107,21 +130,45 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
     if (!ts) return fail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this (device, sample rate)");
     CK(cudaSetDevice(device));
     const int Tmax = 1 + static_cast<int>(max_samples / sfx::kHop);
-    const size_t slice = sfx::cta_scratch_bytes(Tmax, c.max_pk);
-    const int grid = std::min<int64_t>(B, c.grid_max);
-    if (ws_bytes < sfx::kWsHeader + slice * static_cast<size_t>(grid))
-        return fail(SFX_ERR_WORKSPACE, "workspace smaller than sfx_workspace_bytes(device, max_samples)");
     sfx::Params p{};
     p.wave = wave; p.row_stride = row_stride; p.lengths = lengths; p.n_default = n_default;
     p.B = B; p.n_mfcc = n_mfcc; p.out = out; p.out_stride = out_stride;
-    p.ws = static_cast<unsigned char*>(ws); p.cta_scratch_bytes = static_cast<long long>(slice); p.Tmax = Tmax;
+    p.ws = static_cast<unsigned char*>(ws); p.Tmax = Tmax;
     p.aligned8 = ((reinterpret_cast<uintptr_t>(wave) & 7u) == 0 && (row_stride & 1) == 0) ? 1 : 0;
     p.tb = ts->tb;
     p.max_pk = c.max_pk;
     if (dbg) p.dbg = *dbg;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (use_split(B)) {
+        const size_t slice = sfx::split_slice_bytes(Tmax, c.max_pk);
+        if (ws_bytes < sfx::kSplitHeader + slice)
+            return fail(SFX_ERR_WORKSPACE, "workspace smaller than sfx_workspace_bytes(device, max_samples)");
+        const int chunk = static_cast<int>(std::min<size_t>(split_chunk_for(slice), (ws_bytes - sfx::kSplitHeader) / slice));
+        p.cta_scratch_bytes = static_cast<long long>(slice);
+        int launches = 0;
+        for (int c0 = 0; c0 < B; c0 += chunk) {
+            sfx::SplitParams q{};
+            q.p = p;
+            q.chunk0 = c0;
+            q.nclips = std::min(chunk, B - c0);
+            q.T_uniform = lengths ? 0 : 1 + static_cast<int>(n_default / sfx::kHop);
+            const long long frames_ub = static_cast<long long>(q.nclips) * Tmax;
+            const int gf = static_cast<int>(std::min<long long>((frames_ub + sfx::kWarps - 1) / sfx::kWarps, c.sm_count * c.frames_per_sm));
+            const int gc = std::min(q.nclips, c.sm_count * c.clips_per_sm);
+            CK(sfx::launch_split_chunk(q, std::max(gf, 1), std::max(gc, 1), dbg != nullptr, st));
+            launches += 3;
+        }
+        g_last_launches = launches;
+        return SFX_OK;
+    }
+    const size_t slice = sfx::cta_scratch_bytes(Tmax, c.max_pk);
+    const int grid = std::min<int64_t>(B, c.grid_max);
+    if (ws_bytes < sfx::kWsHeader + slice * static_cast<size_t>(grid))
+        return fail(SFX_ERR_WORKSPACE, "workspace smaller than sfx_workspace_bytes(device, max_samples)");
+    p.cta_scratch_bytes = static_cast<long long>(slice);
     CK(cudaMemsetAsync(ws, 0, sfx::kWsHeader, st));
     CK(sfx::launch_extract(p, grid, dbg != nullptr, st));
+    g_last_launches = 1;
     return SFX_OK;
 }
 
@@ -139,7 +186,13 @@ int sfx_device_count(void) {
     return n;
 }
 
-int sfx_launches_per_extract(void) { return 1; }
+int sfx_launches_per_extract(void) { return g_last_launches; }
+
+int sfx_set_pipeline(int mode) {
+    if (mode < 0 || mode > 2) return fail(SFX_ERR_ARG, "pipeline mode must be 0 (auto), 1 (fused) or 2 (split)");
+    g_pipeline = mode;
+    return SFX_OK;
+}
 
 int sfx_release(int device) {
     if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
@@ -199,6 +252,8 @@ int sfx_init_tables(int device, const sfx_tables_host* t) {
     CK(sfx::configure_kernels(&c.blocks_per_sm));
     if (c.blocks_per_sm < 1) return fail(SFX_ERR_CUDA, "kernel does not fit on an SM");
     c.grid_max = c.sm_count * c.blocks_per_sm;
+    CK(sfx::configure_split(&c.frames_per_sm, &c.clips_per_sm));
+    if (c.frames_per_sm < 1 || c.clips_per_sm < 1) return fail(SFX_ERR_CUDA, "split kernels do not fit on an SM");
     c.max_pk = std::max(c.max_pk, (((t->pip_kmax - t->pip_kmin + 2) / 2) + 3) & ~3);
     c.sets.push_back(set);
     c.ready = true;
@@ -211,7 +266,12 @@ size_t sfx_workspace_bytes(int device, int64_t max_samples) {
         return 0;
     }
     const int Tmax = 1 + static_cast<int>(max_samples / sfx::kHop);
-    return sfx::kWsHeader + sfx::cta_scratch_bytes(Tmax, g_ctx[device].max_pk) * static_cast<size_t>(g_ctx[device].grid_max);
+    const size_t fused = sfx::kWsHeader + sfx::cta_scratch_bytes(Tmax, g_ctx[device].max_pk) * static_cast<size_t>(g_ctx[device].grid_max);
+    // covers either pipeline: the split one needs one slice per clip of a chunk (auto mode: at most kAutoSplitMaxB clips)
+    const size_t slice = sfx::split_slice_bytes(Tmax, g_ctx[device].max_pk);
+    const size_t nsplit = g_pipeline == 2 ? static_cast<size_t>(split_chunk_for(slice))
+                                          : std::min<size_t>(kAutoSplitMaxB, split_chunk_for(slice));
+    return std::max(fused, sfx::kSplitHeader + slice * nsplit);
 }
 
 int sfx_extract(int device, int32_t sr, const float* wave, int64_t row_stride, const int32_t* lengths, int64_t n_default,
@@ -276,6 +336,7 @@ int sfx_extract_host(int device, int32_t sr, const float* host_wave, int64_t row
         hp.wave_elems = need_wave; hp.ws_bytes = need_ws; hp.out_elems = need_out; hp.chunk = chunk;
     }
     int nchunks = (B + chunk - 1) / chunk;
+    int launches_total = 0;
     std::vector<int> pend_c0(kHostStreams, -1), pend_nb(kHostStreams, 0);
     auto drain = [&](int s) -> int {      // copy a finished chunk's rows out of pinned staging
         if (pend_c0[s] < 0) return SFX_OK;
@@ -311,6 +372,7 @@ int sfx_extract_host(int device, int32_t sr, const float* host_wave, int64_t row
         rc = do_extract(device, sr, hp.d_wave[s], dev_stride, dlen, n_default, max_samples, nb, n_mfcc, hp.d_out[s], out_w,
                         hp.d_ws[s], hp.ws_bytes, st, nullptr);
         if (rc) return rc;
+        launches_total += g_last_launches;
         if (out_pinned) {
             CK(cudaMemcpy2DAsync(host_out + static_cast<int64_t>(c0) * out_stride, out_stride * 4, hp.d_out[s], out_w * 4,
                                  static_cast<size_t>(out_w) * 4, nb, cudaMemcpyDeviceToHost, st));
@@ -324,6 +386,7 @@ int sfx_extract_host(int device, int32_t sr, const float* host_wave, int64_t row
         int rc = drain(s);
         if (rc) return rc;
     }
+    g_last_launches = launches_total;
     return SFX_OK;
 }
 

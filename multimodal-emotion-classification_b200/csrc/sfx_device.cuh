@@ -1,0 +1,255 @@
+// sfx_device.cuh -- device helpers shared by the fused kernel (sfx_kernels.cu) and the split kernels (sfx_split.cu):
+// compile-time unrolling, the register-resident 32-point FFT, warp reductions, the CTA radix select, MMA / TMA wrappers,
+// and the frame loader.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cfloat>
+#include <cstdint>
+#include <type_traits>
+#include <utility>
+
+#include "sfx_internal.h"
+
+namespace sfx {
+
+// ------------------------------------------------------------------------------------------------
+// compile-time helpers
+template <int... I, class F>
+__device__ __forceinline__ void sfor_impl(std::integer_sequence<int, I...>, F&& f) {
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void sfor(F&& f) {
+    sfor_impl(std::make_integer_sequence<int, N>{}, static_cast<F&&>(f));
+}
+
+__host__ __device__ constexpr int brev5(int k) {
+    return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
+}
+
+__host__ __device__ constexpr float cos32(int q) {
+    constexpr float t[16] = {1.0f,
+                             0.98078528040323044913f,
+                             0.92387953251128675613f,
+                             0.83146961230254523708f,
+                             0.70710678118654752440f,
+                             0.55557023301960222474f,
+                             0.38268343236508977173f,
+                             0.19509032201612826785f,
+                             0.0f,
+                             -0.19509032201612826785f,
+                             -0.38268343236508977173f,
+                             -0.55557023301960222474f,
+                             -0.70710678118654752440f,
+                             -0.83146961230254523708f,
+                             -0.92387953251128675613f,
+                             -0.98078528040323044913f};
+    return t[q];
+}
+// sin(2*pi*q/32) = cos(2*pi*(8-q)/32) for q <= 8, cos(2*pi*(q-8)/32) for q in (8,16)
+__host__ __device__ constexpr float sin32x(int q) { return q <= 8 ? cos32(8 - q) : cos32(q - 8); }
+
+// DIT butterfly on (a, b) with twiddle w = exp(-2*pi*i*Q/32) = (c, -s):  a' = a + w*b,  b' = a - w*b.
+// Non-trivial twiddles use the 6-FMA "tangent" form: w*b = c*(br + t*bi, bi - t*br) with t = s/c when |c| >= |s|,
+// and w*b = s*(t*br + bi, t*bi - br) with t = c/s otherwise (|t| <= 1 in both cases).
+template <int Q>
+__device__ __forceinline__ void dit_bfly(float& ar, float& ai, float& br, float& bi) {
+    if constexpr (Q == 0) {
+        const float xr = ar - br, xi = ai - bi;
+        ar += br; ai += bi; br = xr; bi = xi;
+    } else if constexpr (Q == 8) {          // w = -i: w*b = (bi, -br)
+        const float xr = ar - bi, xi = ai + br;
+        ar += bi; ai -= br; br = xr; bi = xi;
+    } else {
+        constexpr float c = cos32(Q), sn = sin32x(Q);
+        constexpr bool use_c = (c >= 0 ? c : -c) >= sn;        // sn >= 0 for Q in (0, 16)
+        if constexpr (use_c) {
+            constexpr float t = sn / c;
+            const float pr = fmaf(t, bi, br);
+            const float pi = fmaf(-t, br, bi);
+            br = fmaf(-c, pr, ar); bi = fmaf(-c, pi, ai);
+            ar = fmaf(c, pr, ar);  ai = fmaf(c, pi, ai);
+        } else {
+            constexpr float t = c / sn;
+            const float pr = fmaf(t, br, bi);
+            const float pi = fmaf(t, bi, -br);
+            br = fmaf(-sn, pr, ar); bi = fmaf(-sn, pi, ai);
+            ar = fmaf(sn, pr, ar);  ai = fmaf(sn, pi, ai);
+        }
+    }
+}
+
+// radix-2 DIT stage of half-size H on the bit-reversed view v[p] = reg[brev5(p)]
+template <int H>
+__device__ __forceinline__ void dit_stage(float (&re)[32], float (&im)[32]) {
+    sfor<16 / H>([&](auto B) {
+        sfor<H>([&](auto J) {
+            constexpr int p0 = decltype(B)::value * 2 * H + decltype(J)::value;
+            constexpr int i0 = brev5(p0), i1 = brev5(p0 + H);
+            constexpr int Q = decltype(J)::value * (16 / H);
+            dit_bfly<Q>(re[i0], im[i0], re[i1], im[i1]);
+        });
+    });
+}
+
+// 32-point complex FFT in registers: natural-order input x[n] in slot n, output X[k] in slot brev5(k)
+__device__ __forceinline__ void fft32(float (&re)[32], float (&im)[32]) {
+    dit_stage<1>(re, im);
+    dit_stage<2>(re, im);
+    dit_stage<4>(re, im);
+    dit_stage<8>(re, im);
+    dit_stage<16>(re, im);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ unsigned fkey(float f) {      // order-preserving float -> uint
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ int pidx(int k) { return k + (k >> 5); }   // padded index of bin k in the P tile
+
+// ------------------------------------------------------------------------------------------------
+// CTA-wide radix select over the clip's peak magnitudes: key of the element of ascending rank r.
+// count_le = number of elements <= that key.  All threads must call; uses s_hist[256], s_sel[4].
+static __device__ unsigned radix_select(const unsigned* keys, int np, int r, int* s_hist, int* s_sel, int& count_le) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned prefix = 0, mask = 0;
+    int less = 0, equal = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = tid; i < 256; i += kThreads) s_hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < np; i += kThreads) {
+            const unsigned key = keys[i];
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255], 1);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int loc[8];
+            int sum = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { loc[q] = s_hist[lane * 8 + q]; sum += loc[q]; }
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            const int exc = inc - sum;
+            const unsigned bal = __ballot_sync(0xffffffffu, inc > r);
+            const int L = __ffs(bal) - 1;
+            if (lane == L) {
+                int rr = r - exc, cum = 0, sel = 0, eq = 0;
+                bool done = false;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (!done) {
+                        if (cum + loc[u] > rr) { done = true; sel = u; eq = loc[u]; }
+                        else cum += loc[u];
+                    }
+                }
+                s_sel[0] = lane * 8 + sel;
+                s_sel[1] = rr - cum;
+                s_sel[2] = exc + cum;
+                s_sel[3] = eq;
+            }
+        }
+        __syncthreads();
+        const int bucket = s_sel[0];
+        r = s_sel[1];
+        less += s_sel[2];
+        equal = s_sel[3];
+        prefix |= static_cast<unsigned>(bucket) << shift;
+        mask |= 0xFFu << shift;
+        __syncthreads();
+    }
+    count_le = less + equal;
+    return prefix;
+}
+
+// D(16x8, f32) += A(16x16, f16, row) * B(16x8, f16, col): warp-level tensor-core MMA, FP32 accumulate
+__device__ __forceinline__ void mma_f16(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+                                        unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ unsigned pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const unsigned*>(&h);
+}
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+// ---- TMA bulk copy (global -> shared) completing on an mbarrier
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000ll) __trap();     // ~2 s: a lost completion must fail loudly, not hang the GPU
+    }
+}
+
+// raw samples of STFT frame t (zero padded) -> re[m1] = x[2m], im[m1] = x[2m+1], m = 32*m1 + lane
+__device__ __forceinline__ void load_frame(const float* __restrict__ x, long long n, int t, int lane, bool aligned8,
+                                           float (&re)[32], float (&im)[32]) {
+    const long long s0 = static_cast<long long>(kHop) * t - kNfft / 2;
+    if (s0 >= 0 && s0 + kNfft <= n && aligned8) {
+        const float2* src = reinterpret_cast<const float2*>(x + s0) + lane;
+#pragma unroll
+        for (int m1 = 0; m1 < 32; ++m1) {
+            const float2 v = __ldg(src + 32 * m1);
+            re[m1] = v.x;
+            im[m1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int m1 = 0; m1 < 32; ++m1) {
+            const long long g = s0 + 2 * (32 * m1 + lane);
+            re[m1] = (g >= 0 && g < n) ? __ldg(x + g) : 0.0f;
+            im[m1] = (g + 1 >= 0 && g + 1 < n) ? __ldg(x + g + 1) : 0.0f;
+        }
+    }
+}
+
+}  // namespace sfx

@@ -65,7 +65,28 @@ inline size_t cta_scratch_bytes(int Tmax, int max_pk) {
     return (b + 255) & ~static_cast<size_t>(255);
 }
 
+// ---- split pipeline (sfx_split.cu): workspace = header | per-clip peak counters | frame prefix | slices
+constexpr int kSplitChunkMax = 1024;                        // clips per chunk (prep kernel = one 1024-thread block)
+constexpr size_t kSplitNpkOff = 256;
+constexpr size_t kSplitOffOff = kSplitNpkOff + 4 * kSplitChunkMax;
+constexpr size_t kSplitHeader = kSplitOffOff + 4 * (kSplitChunkMax + 64);      // 8704 + 256 B, multiple of 256
+
+struct SplitParams {
+    Params p;              // p.ws = workspace base, p.cta_scratch_bytes = slice bytes per clip
+    int chunk0;            // first clip of the chunk
+    int nclips;            // clips in the chunk (<= kSplitChunkMax)
+    int T_uniform;         // frames per clip when lengths == nullptr, else 0
+};
+
+// bytes of one clip's slice in the split pipeline (multiple of 256)
+inline size_t split_slice_bytes(int Tmax, int max_pk) {
+    size_t b = static_cast<size_t>(Tmax) * (kP16Stride * 2 + kMels * 4 + 12 + 16 + static_cast<size_t>(max_pk) * (16 + 4 + 1));
+    return (b + 255) & ~static_cast<size_t>(255);
+}
+
 size_t smem_bytes();
+cudaError_t configure_split(int* frames_per_sm, int* clips_per_sm);
+cudaError_t launch_split_chunk(const SplitParams& q, int grid_frames, int grid_clips, bool debug, cudaStream_t stream);
 cudaError_t configure_kernels(int* blocks_per_sm);
 cudaError_t launch_extract(const Params& p, int grid, bool debug, cudaStream_t stream);
 

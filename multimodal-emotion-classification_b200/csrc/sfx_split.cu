@@ -1,43 +1,87 @@
-// sfx_kernels.cu -- sm_100a kernels of the batched speech feature extractor.
-//
-// One persistent CTA per clip (dynamic clip queue), 8 warps, 2 CTAs per SM.  Replaces, for a whole batch,
-// the per-clip librosa calls of the reference's preprocessing/audio_preprocessing.py:22-37:
-//   phase 1 (warp per STFT frame): framing + Hann + 2048-pt real FFT (1024-pt complex FFT as two
-//           register-resident radix-32 passes with one shared-memory transpose) -> |X|^2;
-//           rms / zero crossings from the raw samples; |X| centroid + 0.85 roll-off (warp scan);
-//           piptrack peaks (librosa.piptrack on the POWER spectrum) appended to the clip's peak list;
-//           sparse Slaney mel projection + 10*log10.  |X|^2 and log-mel rows go to the CTA's scratch slice.
-//   phase 2 (CTA): estimate_tuning = median of peak magnitudes (radix select) -> 100-bin histogram
-//           arg-max; global log-mel max for power_to_db(top_db=80).
-//   phase 3 (CTA): clamp + frame-mean of log-mel, DCT-II (float64) -> MFCC; chroma projection with the
-//           tuning's filter bank, per-frame inf-norm, frame mean; pooled spectral descriptors.
-// Output row: [mfcc_0..n_mfcc-1 | chroma C..B | zcr, centroid, rolloff, rms]  (reference :45-46).
+// sfx_split.cu -- the same extractor as sfx_kernels.cu, split into two kernels per chunk of clips:
+//   sfx_frames_kernel : phase 1 as a pure stream.  Every warp pulls (clip, frame) items from one global queue; no
+//                       CTA-level barrier, no per-clip imbalance.  Per-frame results (FP16 |X|^2 row, log-mel row, peak
+//                       records, hop energy, centroid, roll-off, weighted zero crossings, row max) go to the clip's slice.
+//   sfx_clips_kernel  : phases 2-3 (tuning estimate, MFCC, tensor-core chroma, pooled row) with one persistent CTA per
+//                       clip, its own register budget and 3 CTAs/SM, because these phases are latency-bound.
+// The arithmetic is the code of sfx_kernels.cu verbatim (generated from it); only where results are kept differs.
 #include "sfx_device.cuh"
 
 namespace sfx {
 
-// ------------------------------------------------------------------------------------------------
+struct Slice {
+    __half* gP16; float* gL; float4* gRec; unsigned* gKey; float* gE; float* gNy; float* gInvS;
+    float* gCent; float* gRoll; float* gLmax; int* gZc; unsigned char* gBin;
+};
+
+__device__ __forceinline__ Slice slice_of(unsigned char* base, int Tmax, int max_pk) {
+    Slice s;
+    s.gP16 = reinterpret_cast<__half*>(base);
+    s.gL = reinterpret_cast<float*>(s.gP16 + static_cast<size_t>(Tmax) * kP16Stride);
+    s.gRec = reinterpret_cast<float4*>(s.gL + static_cast<size_t>(Tmax) * kMels);
+    s.gKey = reinterpret_cast<unsigned*>(s.gRec + static_cast<size_t>(Tmax) * max_pk);
+    s.gE = reinterpret_cast<float*>(s.gKey + static_cast<size_t>(Tmax) * max_pk);
+    s.gNy = s.gE + Tmax;
+    s.gInvS = s.gNy + Tmax;
+    s.gCent = s.gInvS + Tmax;
+    s.gRoll = s.gCent + Tmax;
+    s.gLmax = s.gRoll + Tmax;
+    s.gZc = reinterpret_cast<int*>(s.gLmax + Tmax);
+    s.gBin = reinterpret_cast<unsigned char*>(s.gZc + Tmax);
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------- prep
+// zero the queues / peak counters of the chunk and, for ragged batches, build the exclusive prefix of frame counts
+__global__ void __launch_bounds__(1024) sfx_prep_kernel(const SplitParams q) {
+    __shared__ int s_w[32];
+    const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
+    int* hdr = reinterpret_cast<int*>(q.p.ws);
+    int* npk = reinterpret_cast<int*>(q.p.ws + kSplitNpkOff);
+    int* off = reinterpret_cast<int*>(q.p.ws + kSplitOffOff);
+    if (c < q.nclips) npk[c] = 0;
+    int T = 0;
+    if (c < q.nclips) {
+        const long long n = q.p.lengths ? static_cast<long long>(q.p.lengths[q.chunk0 + c]) : q.p.n_default;
+        T = n > 0 ? 1 + static_cast<int>(n / kHop) : 0;
+    }
+    int inc = T;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_w[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += v;
+        }
+        s_w[lane] = w;
+    }
+    __syncthreads();
+    const int base = warp ? s_w[warp - 1] : 0;
+    if (c < q.nclips) off[c] = base + inc - T;
+    if (c == q.nclips - 1) { off[q.nclips] = base + inc; hdr[2] = base + inc; }
+    if (c == 0) { hdr[0] = 0; hdr[1] = 0; }
+}
+
+// ---------------------------------------------------------------------------------------------- frames
 template <bool kDebug>
-__global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, 2) sfx_frames_kernel(const SplitParams q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_hann = reinterpret_cast<float2*>(smem_raw);
     float2* s_tw1 = s_hann + 1024;
     float2* s_tw2 = s_tw1 + 1024;
-    float2* s_melab = s_tw2 + 512;                                           // [33*32]  (tw2: rows k2 < 16 only)
+    float2* s_melab = s_tw2 + 512;
     float* s_ex = reinterpret_cast<float*>(s_melab + 17 * 64);               // [kWarps][kExFloats]
-    double* s_pool = reinterpret_cast<double*>(s_ex + kWarps * kExFloats);   // [256]
-    double* s_wacc = s_pool + 256;                                           // [kWarps][16]
-    double* s_edges = s_wacc + kWarps * 16;                                  // [104]
-    unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_edges + 104);   // chroma-bank TMA barrier
-    int* s_hist = reinterpret_cast<int*>(s_mbar + 1);                        // [256]
-    int* s_i = s_hist + 256;                                                 // [32]
-    float* s_f = reinterpret_cast<float*>(s_i + 32);                         // [32]
 
+    const Params& p = q.p;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevTables& tb = p.tb;
-
-    // tables are stored row-paired: element (row r, lane) sits at float2 index (r/2)*64 + 2*lane + (r&1), so one LDS.128
-    // serves rows r, r+1 of a lane (conflict-free: consecutive lanes are 16 B apart)
     for (int i = tid; i < 1024; i += kThreads) {
         const int r = i >> 5, l = i & 31;
         const int d = (r >> 1) * 64 + 2 * l + (r & 1);
@@ -47,61 +91,54 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     }
     for (int i = tid; i < 33 * 32; i += kThreads) {
         const int r = i >> 5, l = i & 31;
-        s_melab[(r >> 1) * 64 + 2 * l + (r & 1)] = tb.mel_ab[i];      // row 32 (Nyquist) lands at 16*64 + 2*lane
+        s_melab[(r >> 1) * 64 + 2 * l + (r & 1)] = tb.mel_ab[i];
     }
-    for (int i = tid; i <= kTunings; i += kThreads) s_edges[i] = tb.edges[i];
-    if (tid == 0) mbar_init(s_mbar, 1);
-    unsigned bank_parity = 0;
     const unsigned mel_mask = tb.mel_mask[lane];
     const int mel_ps = tb.mel_ps;
-    int msrc[4];                                   // 3 x 10-bit partial-sum slots per filter 32*s + lane
+    int msrc[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        const int* q = tb.mel_src + (32 * s + lane) * 3;
-        msrc[s] = q[0] | (q[1] << 10) | (q[2] << 20);
+        const int* m3 = tb.mel_src + (32 * s + lane) * 3;
+        msrc[s] = m3[0] | (m3[1] << 10) | (m3[2] << 20);
     }
+    __syncthreads();
 
-    // scratch slice of this CTA
-    unsigned char* slice = p.ws + kWsHeader + static_cast<size_t>(blockIdx.x) * p.cta_scratch_bytes;
-    __half* gP16 = reinterpret_cast<__half*>(slice);                                             // [Tmax][kP16Stride]
-    float* gL = reinterpret_cast<float*>(gP16 + static_cast<size_t>(p.Tmax) * kP16Stride);       // [Tmax][128]
-    float4* gRec = reinterpret_cast<float4*>(gL + static_cast<size_t>(p.Tmax) * kMels);
-    unsigned* gKey = reinterpret_cast<unsigned*>(gRec + static_cast<size_t>(p.Tmax) * p.max_pk);
-    float* gE = reinterpret_cast<float*>(gKey + static_cast<size_t>(p.Tmax) * p.max_pk);        // hop energies [Tmax]
-    float* gNy = gE + p.Tmax;                                                                    // scaled Nyquist |X|^2 [Tmax]
-    float* gInvS = gNy + p.Tmax;                                                                 // 1 / row scale [Tmax]
-    unsigned char* gBin = reinterpret_cast<unsigned char*>(gInvS + p.Tmax);
-    int* counter = reinterpret_cast<int*>(p.ws);
-
-    float* Pb = s_ex + warp * kExFloats;               // this warp's exchange / |X|^2 tile
+    int* queue = reinterpret_cast<int*>(p.ws);
+    int* npk_all = reinterpret_cast<int*>(p.ws + kSplitNpkOff);
+    const int* off = reinterpret_cast<const int*>(p.ws + kSplitOffOff);
+    const int total = queue[2];
+    float* Pb = s_ex + warp * kExFloats;
     float2* ex = reinterpret_cast<float2*>(Pb);
-    float* part = Pb + kPartOff;                       // mel partial sums [32][mel_ps] + zero slot
+    float* part = Pb + kPartOff;
     const float bin_hz = static_cast<float>(static_cast<double>(tb.sr) / kNfft);
     const bool aligned8 = p.aligned8 != 0;
 
     for (;;) {
-        __syncthreads();
-        if (tid == 0) { s_i[0] = atomicAdd(counter, 1); s_i[1] = 0; }
-        __syncthreads();
-        const int clip = s_i[0];
-        if (clip >= p.B) break;
-        const long long n = p.lengths ? static_cast<long long>(p.lengths[clip]) : p.n_default;
-        float* out = p.out + static_cast<long long>(clip) * p.out_stride;
-        if (n <= 0) {
-            for (int i = tid; i < p.n_mfcc + 16; i += kThreads) out[i] = __int_as_float(0x7fc00000);
-            continue;
+        int item = 0;
+        if (lane == 0) item = atomicAdd(queue, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
+        int c;
+        if (q.T_uniform > 0) {
+            c = item / q.T_uniform;
+        } else {                                   // largest c with off[c] <= item
+            int lo = 0, hi = q.nclips;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (off[mid] <= item) lo = mid; else hi = mid;
+            }
+            c = lo;
         }
+        const int t = item - (q.T_uniform > 0 ? c * q.T_uniform : off[c]);
+        const int clip = q.chunk0 + c;
+        const long long n = p.lengths ? static_cast<long long>(p.lengths[clip]) : p.n_default;
         const int T = 1 + static_cast<int>(n / kHop);
         const float* x = p.wave + static_cast<long long>(clip) * p.row_stride;
-
-        // ===================================== phase 1: frames =====================================
-        // per-warp running sums live in shared memory (s_wacc[warp][0..2] = centroid, rolloff, rms; s_f = log-mel max)
-        if (lane < 2) s_wacc[warp * 16 + lane] = 0.0;
-        if (lane == 0) s_f[warp] = -FLT_MAX;
-        int acc_zc = 0;
-        __syncwarp();
-
-        for (int t = warp; t < T; t += kWarps) {
+        const Slice sl = slice_of(p.ws + kSplitHeader + static_cast<size_t>(c) * p.cta_scratch_bytes, p.Tmax, p.max_pk);
+        __half* gP16 = sl.gP16; float* gL = sl.gL; float4* gRec = sl.gRec; float* gE = sl.gE; float* gNy = sl.gNy;
+        float* gInvS = sl.gInvS; float* gCent = sl.gCent; float* gRoll = sl.gRoll; float* gLmax = sl.gLmax; int* gZc = sl.gZc;
+        int* npk = npk_all + c;
+        {
             float re[32], im[32];
             load_frame(x, n, t, lane, aligned8, re, im);
             // ---- all-zero frame (the zero tail load_audio pads short clips with, reference :15-16): every result is
@@ -124,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                         gE[t] = 0.0f;
                         gNy[t] = 0.0f;
                         gInvS[t] = 0.0f;
-                        s_f[warp] = fmaxf(s_f[warp], lm0);
+                        gCent[t] = 0.0f; gRoll[t] = 0.0f; gLmax[t] = lm0; gZc[t] = 0;
                     }
                     if (kDebug) {
                         if (t < p.dbg.T_dbg) {
@@ -142,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                         }
                     }
                     __syncwarp();
-                    continue;
+                    continue;   // next work item
                 }
             }
             // ---- energy of hop t (samples [512t, 512t+512) = rows 16..23); librosa.feature.rms of frame t is
@@ -156,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
             }
 
             // ---- zero crossings of hop t (samples [512t, 512t+512)), weighted by how many frames see them
-            int zc_hop = 0;
+            int zc_hop = 0, zc_w = 0;
             {
                 // librosa.zero_crossings(threshold=1e-10, zero_pos=True): sign(x) := (double)x < -1e-10, which for float32
                 // x is exactly x < -9.99999944e-11f (0xaedbe6fe, the smallest float32 not below -1e-10)
@@ -182,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 const int multA = min(T - 1, t + 2) - tlo + 1;
                 const int mult0 = min(T - 1, t + 1) - tlo + 1;
                 zc_hop = zc;
-                acc_zc += multA * zc - (multA - mult0) * zc_first;
+                zc_w = multA * zc - (multA - mult0) * zc_first;
             }
 
             // ---- Hann window (periodic, scipy.signal.get_window('hann', 2048))
@@ -259,12 +296,6 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
             }
             pmax = warp_max(pmax);
             __syncwarp();
-            // ---- warm L2 with the newest hop of this warp's next frame (its other three hops are shared with
-            //      frames the neighbouring warps are reading now)
-            {
-                const long long nh = static_cast<long long>(kHop) * (t + kWarps) + kHop + lane * 32;
-                if (lane < 16 && nh < n) prefetch_l2(x + nh);
-            }
             if (kDebug) {
                 if (p.dbg.P && t < p.dbg.T_dbg) {
                     float* dP = p.dbg.P + (static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kPStride;
@@ -348,9 +379,9 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 cent_t = (total < FLT_MIN) ? 0.0f : (num / total) * bin_hz;
                 roll_t = static_cast<float>(first) * bin_hz;
             }
-            if (lane == 0) {
-                s_wacc[warp * 16 + 0] += static_cast<double>(cent_t);
-                s_wacc[warp * 16 + 1] += static_cast<double>(roll_t);
+            {
+                const int zsum = warp_sum_i(zc_w);
+                if (lane == 0) { gCent[t] = cent_t; gRoll[t] = roll_t; gZc[t] = zsum; }
             }
             __syncwarp();
 
@@ -371,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                     }
                 }
                 gmax = warp_max(gmax);
-                if (lane == 0) s_f[warp] = fmaxf(s_f[warp], gmax);
+                if (lane == 0) gLmax[t] = gmax;
             }
 
             // ---- piptrack peak detection on the power spectrum (bins kmin..kmax); the per-peak arithmetic
@@ -404,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
                 const int total = __shfl_sync(0xffffffffu, inc, 31);
                 if (total) {
                     int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_i[1], total);
+                    if (lane == 0) base = atomicAdd(npk, total);
                     base = __shfl_sync(0xffffffffu, base, 0);
                     float4* dst = gRec + base + (inc - mine);
                     while (flags) {
@@ -425,11 +456,70 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
             (void)zc_hop;
             __syncwarp();
         }
+        __syncwarp();
+    }
+}
 
-        // per-warp partials
+// ---------------------------------------------------------------------------------------------- clips
+template <bool kDebug>
+__global__ void __launch_bounds__(kThreads, 3) sfx_clips_kernel(const SplitParams q) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_ex = reinterpret_cast<float*>(smem_raw);                        // [kWarps][kExFloats]
+    double* s_pool = reinterpret_cast<double*>(s_ex + kWarps * kExFloats);   // [256]
+    double* s_wacc = s_pool + 256;                                           // [kWarps][16]
+    double* s_edges = s_wacc + kWarps * 16;                                  // [104]
+    unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_edges + 104);
+    int* s_hist = reinterpret_cast<int*>(s_mbar + 1);                        // [256]
+    int* s_i = s_hist + 256;                                                 // [32]
+    float* s_f = reinterpret_cast<float*>(s_i + 32);                         // [32]
+
+    const Params& p = q.p;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DevTables& tb = p.tb;
+    for (int i = tid; i <= kTunings; i += kThreads) s_edges[i] = tb.edges[i];
+    if (tid == 0) mbar_init(s_mbar, 1);
+    unsigned bank_parity = 0;
+    int* queue = reinterpret_cast<int*>(p.ws);
+    const int* npk_all = reinterpret_cast<const int*>(p.ws + kSplitNpkOff);
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_i[0] = atomicAdd(queue + 1, 1);
+        __syncthreads();
+        const int c = s_i[0];
+        if (c >= q.nclips) break;
+        const int clip = q.chunk0 + c;
+        const long long n = p.lengths ? static_cast<long long>(p.lengths[clip]) : p.n_default;
+        float* out = p.out + static_cast<long long>(clip) * p.out_stride;
+        if (n <= 0) {
+            for (int i = tid; i < p.n_mfcc + 16; i += kThreads) out[i] = __int_as_float(0x7fc00000);
+            continue;
+        }
+        const int T = 1 + static_cast<int>(n / kHop);
+        const Slice sl = slice_of(p.ws + kSplitHeader + static_cast<size_t>(c) * p.cta_scratch_bytes, p.Tmax, p.max_pk);
+        __half* gP16 = sl.gP16; float* gL = sl.gL; float4* gRec = sl.gRec; unsigned* gKey = sl.gKey; float* gE = sl.gE;
+        float* gNy = sl.gNy; float* gInvS = sl.gInvS; unsigned char* gBin = sl.gBin;
+        // per-clip sums of the per-frame descriptors written by the frames kernel (fixed thread -> frame assignment:
+        // deterministic) into the slots the phases below read
         {
-            const int zc = warp_sum_i(acc_zc);
-            if (lane == 0) s_i[8 + warp] = zc;
+            double sc = 0.0, sr = 0.0;
+            int sz = 0;
+            float lm = -FLT_MAX;
+            for (int t = tid; t < T; t += kThreads) {
+                sc += static_cast<double>(sl.gCent[t]);
+                sr += static_cast<double>(sl.gRoll[t]);
+                sz += sl.gZc[t];
+                lm = fmaxf(lm, sl.gLmax[t]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sc += __shfl_xor_sync(0xffffffffu, sc, o);
+                sr += __shfl_xor_sync(0xffffffffu, sr, o);
+            }
+            sz = warp_sum_i(sz);
+            lm = warp_max(lm);
+            if (lane == 0) { s_wacc[warp * 16 + 0] = sc; s_wacc[warp * 16 + 1] = sr; s_i[8 + warp] = sz; s_f[warp] = lm; }
+            if (tid == 0) s_i[1] = npk_all[c];
         }
         __syncthreads();
 
@@ -703,25 +793,31 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-size_t smem_bytes() {
-    return sizeof(float2) * (2560 + 17 * 64) + sizeof(float) * kWarps * kExFloats +
-           sizeof(double) * (256 + kWarps * 16 + 104 + 1) + sizeof(int) * (256 + 32) + sizeof(float) * 32;
+// ---------------------------------------------------------------------------------------------- host
+size_t smem_frames() { return sizeof(float2) * (2560 + 17 * 64) + sizeof(float) * kWarps * kExFloats; }
+size_t smem_clips() {
+    return sizeof(float) * kWarps * kExFloats + sizeof(double) * (256 + kWarps * 16 + 104 + 1) + sizeof(int) * (256 + 32) +
+           sizeof(float) * 32;
 }
 
-cudaError_t configure_kernels(int* blocks_per_sm) {
-    const int smem = static_cast<int>(smem_bytes());
-    cudaError_t e = cudaFuncSetAttribute(sfx_extract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(sfx_extract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, sfx_extract_kernel<false>, kThreads, smem);
+cudaError_t configure_split(int* frames_per_sm, int* clips_per_sm) {
+    cudaError_t e;
+    const int sf = static_cast<int>(smem_frames()), sc = static_cast<int>(smem_clips());
+    if ((e = cudaFuncSetAttribute(sfx_frames_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sf)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(sfx_frames_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sf)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(sfx_clips_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sc)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(sfx_clips_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sc)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frames_per_sm, sfx_frames_kernel<false>, kThreads, sf)) != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(clips_per_sm, sfx_clips_kernel<false>, kThreads, sc);
 }
 
-cudaError_t launch_extract(const Params& p, int grid, bool debug, cudaStream_t stream) {
-    const size_t smem = smem_bytes();
-    if (debug) sfx_extract_kernel<true><<<grid, kThreads, smem, stream>>>(p);
-    else       sfx_extract_kernel<false><<<grid, kThreads, smem, stream>>>(p);
+// one chunk: prep -> frames -> clips on `stream`
+cudaError_t launch_split_chunk(const SplitParams& q, int grid_frames, int grid_clips, bool debug, cudaStream_t stream) {
+    sfx_prep_kernel<<<1, 1024, 0, stream>>>(q);
+    if (debug) sfx_frames_kernel<true><<<grid_frames, kThreads, smem_frames(), stream>>>(q);
+    else       sfx_frames_kernel<false><<<grid_frames, kThreads, smem_frames(), stream>>>(q);
+    if (debug) sfx_clips_kernel<true><<<grid_clips, kThreads, smem_clips(), stream>>>(q);
+    else       sfx_clips_kernel<false><<<grid_clips, kThreads, smem_clips(), stream>>>(q);
     return cudaGetLastError();
 }
 

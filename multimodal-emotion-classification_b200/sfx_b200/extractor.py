@@ -134,8 +134,7 @@ class SpeechFeatureExtractor:
         with torch.cuda.device(self.index):
             _lib.check(self.lib.sfx_extract_host(self.index, self.sr, waves.ctypes.data, waves.strides[0] // 4, lp, n_default,
                                                  B, n_mfcc, out.ctypes.data, out.strides[0] // 4, int(chunk_clips)))
-        nchunk = 1 if chunk_clips <= 0 else -(-B // chunk_clips)
-        self.launches += nchunk * self.lib.sfx_launches_per_extract()
+        self.launches += self.lib.sfx_launches_per_extract()      # summed over the call's chunks by the library
         return out
 
 
