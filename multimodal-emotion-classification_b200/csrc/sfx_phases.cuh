@@ -1,0 +1,655 @@
+// sfx_phases.cuh -- the two phase functions shared by the fused kernel (sfx_kernels.cu) and the split kernels
+// (sfx_split.cu):
+//   process_frame<kDebug, kSplit> : phase 1 for one STFT frame, executed by one warp
+//   clip_tail<kDebug>             : phases 2-3 + the pooled output row for one clip, executed by one CTA
+// kSplit selects where per-frame results are kept: the fused kernel accumulates centroid / roll-off / zero crossings /
+// log-mel max per warp in shared memory and counts peaks with a shared atomic; the split pipeline stores them per frame
+// in the clip's slice (summed later in a fixed order) and counts peaks with a global atomic.
+#pragma once
+#include "sfx_device.cuh"
+
+namespace sfx {
+
+// shared-memory tables and the calling warp's tile (phase 1)
+struct FrameSmem {
+    const float2* s_hann; const float2* s_tw1; const float2* s_tw2; const float2* s_melab;
+    float* Pb;            // this warp's exchange / |X|^2 tile [kExFloats]
+    float2* ex;           // the same tile as float2
+    float* part;          // mel partial sums inside the tile
+    unsigned mel_mask; int mel_ps; int msrc[4];
+    float bin_hz; bool aligned8;
+};
+
+// where phase 1 leaves its results
+struct FrameOut {
+    __half* gP16; float* gL; float4* gRec; float* gE; float* gNy; float* gInvS;     // the clip's scratch slice
+    int* npk;                                                                          // peak counter (shared or global)
+    double* s_wacc; float* s_f;                                                        // fused: per-warp accumulators
+    float* gCent; float* gRoll; float* gLmax; int* gZc;                                // split: per-frame values
+};
+
+// shared memory of phases 2-3
+struct ClipSmem {
+    float* s_ex; double* s_pool; double* s_wacc; double* s_edges; unsigned long long* s_mbar; int* s_hist; int* s_i; float* s_f;
+};
+
+struct ClipSlice {
+    __half* gP16; float* gL; float4* gRec; unsigned* gKey; float* gE; float* gNy; float* gInvS; unsigned char* gBin;
+};
+
+// ------------------------------------------------------------------------------------------------ phase 1
+template <bool kDebug, bool kSplit>
+__device__ __forceinline__ void process_frame(const Params& p, const DevTables& tb, const FrameSmem& fs, const FrameOut& fo,
+                                              const float* __restrict__ x, const long long n, const int T, const int t,
+                                              const int clip, const int lane, const int warp, int& acc_zc) {
+    float re[32], im[32];
+    load_frame(x, n, t, lane, fs.aligned8, re, im);
+    // ---- all-zero frame (the zero tail load_audio pads short clips with, reference :15-16): every result is
+    //      known in closed form and equals what the general path computes from zeros, so the FFT is skipped:
+    //      |X|^2 = 0, log-mel = 10*log10(1e-10) in all bands, no peaks, centroid = rolloff = 0, hop energy 0,
+    //      no sign changes.
+    {
+        unsigned any_bits = 0;
+#pragma unroll
+        for (int m1 = 0; m1 < 32; ++m1) any_bits |= __float_as_uint(re[m1]) | __float_as_uint(im[m1]);
+        if (!__any_sync(0xffffffffu, (any_bits & 0x7fffffffu) != 0u)) {
+            const float lm0 = 3.01029995663981195f * __log2f(1e-10f);
+            float* Lg = fo.gL + static_cast<size_t>(t) * kMels;
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) Lg[32 * s4 + lane] = lm0;
+            uint4* dst = reinterpret_cast<uint4*>(fo.gP16 + static_cast<size_t>(t) * kP16Stride + 32 * lane);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(0u, 0u, 0u, 0u);
+            if (lane == 0) {
+                fo.gE[t] = 0.0f;
+                fo.gNy[t] = 0.0f;
+                fo.gInvS[t] = 0.0f;
+                if constexpr (kSplit) { fo.gCent[t] = 0.0f; fo.gRoll[t] = 0.0f; fo.gLmax[t] = lm0; fo.gZc[t] = 0; }
+                else fo.s_f[warp] = fmaxf(fo.s_f[warp], lm0);
+            }
+            if (kDebug) {
+                if (t < p.dbg.T_dbg) {
+                    if (p.dbg.P) {
+                        float* dP = p.dbg.P + (static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kPStride;
+                        for (int k = lane; k < kBins; k += 32) dP[k] = 0.0f;
+                    }
+                    if (p.dbg.logmel)
+                        for (int m = lane; m < kMels; m += 32)
+                            p.dbg.logmel[(static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kMels + m] = lm0;
+                    if (p.dbg.frame_feat && lane == 0) {
+                        float* ff = p.dbg.frame_feat + (static_cast<size_t>(clip) * p.dbg.T_dbg + t) * 4;
+                        ff[0] = 0.f; ff[1] = 0.f; ff[3] = 0.f;
+                    }
+                }
+            }
+            __syncwarp();
+            return;
+        }
+    }
+    // ---- energy of hop t (samples [512t, 512t+512) = rows 16..23); librosa.feature.rms of frame t is
+    //      sqrt((E[t-2] + E[t-1] + E[t] + E[t+1]) / 2048) and is pooled in the epilogue
+    {
+        float he = 0.0f;
+#pragma unroll
+        for (int m1 = 16; m1 < 24; ++m1) { he = fmaf(re[m1], re[m1], he); he = fmaf(im[m1], im[m1], he); }
+        he = warp_sum(he);
+        if (lane == 0) fo.gE[t] = he;
+    }
+
+    // ---- zero crossings of hop t (samples [512t, 512t+512)), weighted by how many frames see them
+    int zc_hop = 0, zc_w = 0;
+    {
+        // librosa.zero_crossings(threshold=1e-10, zero_pos=True): sign(x) := (double)x < -1e-10, which for float32
+        // x is exactly x < -9.99999944e-11f (0xaedbe6fe, the smallest float32 not below -1e-10)
+        const float zthr = __uint_as_float(0xaedbe6feu);
+        int zc = 0, zc_first = 0;
+        const int ib = kHop * t + 2 * lane;
+        const int nm1 = static_cast<int>(n) - 1;
+        sfor<8>([&](auto R) {
+            constexpr int r = decltype(R)::value;
+            constexpr int m1 = 16 + r;
+            const float e0 = re[m1], e1 = im[m1];
+            const float up = __shfl_up_sync(0xffffffffu, e1, 1);
+            const float wrap = __shfl_sync(0xffffffffu, im[m1 - 1], 31);
+            const float prev = lane == 0 ? wrap : up;
+            const int i0 = ib + 64 * r;
+            const bool sp = prev < zthr, sa = e0 < zthr, sb = e1 < zthr;
+            const int c0 = (i0 >= 1 && i0 <= nm1 && sa != sp) ? 1 : 0;
+            const int c1 = (i0 + 1 <= nm1 && sb != sa) ? 1 : 0;
+            zc += c0 + c1;
+            if (r == 0 && lane == 0) zc_first = c0;
+        });
+        const int tlo = max(0, t - 1);
+        const int multA = min(T - 1, t + 2) - tlo + 1;
+        const int mult0 = min(T - 1, t + 1) - tlo + 1;
+        zc_hop = zc;
+        zc_w = multA * zc - (multA - mult0) * zc_first;
+    }
+
+    // ---- Hann window (periodic, scipy.signal.get_window('hann', 2048))
+#pragma unroll
+    for (int m1 = 0; m1 < 32; m1 += 2) {
+        const float4 w = *reinterpret_cast<const float4*>(fs.s_hann + (m1 >> 1) * 64 + 2 * lane);
+        re[m1] *= w.x;
+        im[m1] *= w.y;
+        re[m1 + 1] *= w.z;
+        im[m1 + 1] *= w.w;
+    }
+    // ---- 1024-pt complex FFT: radix-32 over m1, twiddle, transpose, radix-32 over m2
+    fft32(re, im);
+    // exchange tile: float4 slot (k1/2)*33 + lane holds rows k1, k1+1 of column `lane`
+    sfor<16>([&](auto K) {
+        constexpr int k1 = 2 * decltype(K)::value;
+        constexpr int a = brev5(k1), b = brev5(k1 + 1);
+        const float4 w = *reinterpret_cast<const float4*>(fs.s_tw1 + (k1 >> 1) * 64 + 2 * lane);
+        float4 v;
+        v.x = fmaf(re[a], w.x, -(im[a] * w.y));
+        v.y = fmaf(re[a], w.y, im[a] * w.x);
+        v.z = fmaf(re[b], w.z, -(im[b] * w.w));
+        v.w = fmaf(re[b], w.w, im[b] * w.z);
+        reinterpret_cast<float4*>(fs.ex)[(k1 >> 1) * 33 + lane] = v;
+    });
+    __syncwarp();
+    {
+        const float2* src = fs.ex + ((lane >> 1) * 33) * 2 + (lane & 1);      // row `lane`: half of the float4 slots
+#pragma unroll
+        for (int m2 = 0; m2 < 32; ++m2) {
+            const float2 v = src[2 * m2];
+            re[m2] = v.x;
+            im[m2] = v.y;
+        }
+    }
+    __syncwarp();
+    fft32(re, im);
+
+    // ---- real-FFT unpack, one conjugate pair per step: lane holds Z[lane + 32*k2]; for k2 < 16 it forms
+    //      X[k] and X[1024-k] (k = lane + 32*k2) from Z[k] and Z[1024-k] (lane (32-lane)&31, register 31-k2;
+    //      lane 0 pairs with its own register (32-k2)&31).  Bin 512 (self-paired) is lane 0's register 16.
+    float pmax = 0.0f;
+    {
+        float* PbL = fs.Pb + lane;
+        float* PbU = fs.Pb + (lane == 0 ? 1056 : 1055 - lane);
+        const int plane = (32 - lane) & 31;
+        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        sfor<16>([&](auto K) {
+            constexpr int k2 = decltype(K)::value;
+            constexpr int a = brev5(k2), b = brev5(31 - k2), c = brev5((32 - k2) & 31);
+            const float zr = re[a], zi = im[a];
+            float pr = __shfl_sync(0xffffffffu, re[b], plane);
+            float pi = __shfl_sync(0xffffffffu, im[b], plane);
+            if (lane == 0) { pr = re[c]; pi = im[c]; }
+            if constexpr ((k2 & 1) == 0) w4 = *reinterpret_cast<const float4*>(fs.s_tw2 + (k2 >> 1) * 64 + 2 * lane);
+            const float2 w = (k2 & 1) ? make_float2(w4.z, w4.w) : make_float2(w4.x, w4.y);   // (0.5 cos, 0.5 sin)(2 pi k / 2048)
+            const float er = zr + pr, ei = zi - pi, orr = zr - pr, oi = zi + pi;
+            const float u = fmaf(w.x, orr, w.y * oi);         // Re(w O)/2
+            const float v = fmaf(w.x, oi, -(w.y * orr));      // Im(w O)/2
+            const float xr = fmaf(0.5f, er, v), xi = fmaf(0.5f, ei, -u);       // X[k]
+            const float yr = fmaf(0.5f, er, -v), yi = fmaf(-0.5f, ei, -u);     // X[1024-k]
+            const float P = fmaf(xr, xr, xi * xi);
+            const float Q = fmaf(yr, yr, yi * yi);
+            pmax = fmaxf(pmax, fmaxf(P, Q));
+            PbL[33 * k2] = P;
+            PbU[-33 * k2] = Q;
+        });
+        if (lane == 0) {
+            constexpr int h = brev5(16);
+            const float P512 = fmaf(re[h], re[h], im[h] * im[h]);
+            fs.Pb[512 + 16] = P512;
+            pmax = fmaxf(pmax, P512);
+        }
+    }
+    pmax = warp_max(pmax);
+    __syncwarp();
+    // ---- warm L2 with the newest hop of this warp's next frame (its other three hops are shared with
+    //      frames the neighbouring warps are reading now)
+    {
+        const long long nh = static_cast<long long>(kHop) * (t + kWarps) + kHop + lane * 32;
+        if (!kSplit && lane < 16 && nh < n) prefetch_l2(x + nh);
+    }
+    if (kDebug) {
+        if (p.dbg.P && t < p.dbg.T_dbg) {
+            float* dP = p.dbg.P + (static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kPStride;
+            for (int k = lane; k < kBins; k += 32) dP[k] = fs.Pb[pidx(k)];
+        }
+    }
+
+    // ---- contiguous pass: lane owns bins [32*lane, 32*lane+32) (+1024 for lane 31):
+    //      |X| prefix sums (centroid, 0.85 roll-off) and the Slaney mel projection as running
+    //      falling/rising partial sums flushed whenever the filter interval advances
+    float cent_t, roll_t;
+    {
+        float s[33];
+        float run = 0.0f, ks = 0.0f, accA = 0.0f, accB = 0.0f;
+        float* pq = fs.part + lane * fs.mel_ps;
+        const float* Prow = fs.Pb + 33 * lane;
+        // the chroma phase reads this frame's |X|^2 back as FP16 scaled by an exact power of two that puts the
+        // frame maximum in [2^14, 2^15) (the per-frame inf-norm of chroma_stft cancels the scale)
+        // biased exponent of the scale = 14 - (E - 127) + 127 = 268 - E, clamped to a finite power of two
+        const unsigned sbits = min(268u - ((__float_as_uint(pmax) >> 23) & 255u), 254u) << 23;
+        const float scale = __uint_as_float(sbits);
+        unsigned h2[16];
+        float hprev = 0.0f;
+        float4 ab4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        sfor<32>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            const float P = Prow[j];
+            if constexpr ((j & 1) == 0) hprev = P * scale;
+            else h2[j >> 1] = pack_half2(hprev, P * scale);
+            if (j > 0 && ((fs.mel_mask >> j) & 1u)) { *pq++ = accA; accA = accB; accB = 0.0f; }
+            if constexpr ((j & 1) == 0) ab4 = *reinterpret_cast<const float4*>(fs.s_melab + (j >> 1) * 64 + 2 * lane);
+            accA = fmaf((j & 1) ? ab4.z : ab4.x, P, accA);
+            accB = fmaf((j & 1) ? ab4.w : ab4.y, P, accB);
+            const float sv = sqrt_approx(P);
+            run += sv;
+            s[j] = run;
+            ks = fmaf(static_cast<float>(j), sv, ks);
+        });
+        s[32] = run;
+        if (lane == 31) {
+            const float P = fs.Pb[1024 + 32];
+            if (tb.mel_flush32) { *pq++ = accA; accA = accB; accB = 0.0f; }
+            const float2 ab = fs.s_melab[16 * 64 + 2 * 31];
+            accA = fmaf(ab.x, P, accA);
+            accB = fmaf(ab.y, P, accB);
+            const float sv = sqrt_approx(P);
+            run += sv;
+            s[32] = run;
+            ks = fmaf(32.0f, sv, ks);
+        }
+        pq[0] = accA;
+        pq[1] = accB;
+        if (lane == 0) fs.part[32 * fs.mel_ps] = 0.0f;   // zero slot read by filters with < 3 contributing lanes
+        {
+            uint4* dst = reinterpret_cast<uint4*>(fo.gP16 + static_cast<size_t>(t) * kP16Stride + 32 * lane);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
+            if (lane == 31) fo.gNy[t] = fs.Pb[1024 + 32] * scale;
+            if (lane == 0) fo.gInvS[t] = __uint_as_float((254u << 23) - sbits);      // 1/scale, exact
+        }
+        float inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) exc = 0.0f;
+        const float total = __shfl_sync(0xffffffffu, inc, 31);
+        const float thr = __fmul_rn(0.85f, total);
+        // first bin whose cumulative |X| reaches the threshold = number of (monotone) prefix sums below it
+        const float thrL = thr - exc;
+        float cntf = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cntf += (s[j] < thrL) ? 1.0f : 0.0f;
+        const int cnt = static_cast<int>(cntf);
+        int first = (cnt < 32) ? 32 * lane + cnt : 1024;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        const float num = warp_sum(fmaf(32.0f * lane, run, ks));
+        cent_t = (total < FLT_MIN) ? 0.0f : (num / total) * fs.bin_hz;
+        roll_t = static_cast<float>(first) * fs.bin_hz;
+    }
+    if constexpr (kSplit) {
+        const int zsum = warp_sum_i(zc_w);
+        if (lane == 0) { fo.gCent[t] = cent_t; fo.gRoll[t] = roll_t; fo.gZc[t] = zsum; }
+    } else {
+        acc_zc += zc_w;
+        if (lane == 0) {
+            fo.s_wacc[warp * 16 + 0] += static_cast<double>(cent_t);
+            fo.s_wacc[warp * 16 + 1] += static_cast<double>(roll_t);
+        }
+    }
+    __syncwarp();
+
+    // ---- log-mel rows: filter m = 32*s + lane adds its (<= 3) partial sums in a fixed order
+    {
+        float* Lg = fo.gL + static_cast<size_t>(t) * kMels;
+        float gmax = -FLT_MAX;
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            const int ms = fs.msrc[s4];
+            const float mel = (fs.part[ms & 1023] + fs.part[(ms >> 10) & 1023]) + fs.part[ms >> 20];
+            const float lm = 3.01029995663981195f * __log2f(fmaxf(1e-10f, mel));   // 10*log10(x)
+            Lg[32 * s4 + lane] = lm;
+            gmax = fmaxf(gmax, lm);
+            if (kDebug) {
+                if (p.dbg.logmel && t < p.dbg.T_dbg)
+                    p.dbg.logmel[(static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kMels + 32 * s4 + lane] = lm;
+            }
+        }
+        gmax = warp_max(gmax);
+        if (lane == 0) {
+            if constexpr (kSplit) fo.gLmax[t] = gmax;
+            else fo.s_f[warp] = fmaxf(fo.s_f[warp], gmax);
+        }
+    }
+
+    // ---- piptrack peak detection on the power spectrum (bins kmin..kmax); the per-peak arithmetic
+    //      (parabolic shift, pitch, tuning residual) is done in phase 2 on the compacted records
+    {
+        const float ref = __fmul_rn(0.1f, pmax);
+        const int kfirst = tb.kmin + lane;
+        const float* q0 = fs.Pb + pidx(kfirst - 1);
+        const int d0 = pidx(kfirst) - pidx(kfirst - 1), d1 = pidx(kfirst + 1) - pidx(kfirst - 1);
+        const int nrows = (tb.kmax - tb.kmin + 32) >> 5;          // <= 16 (bins 1..1023, 32 per row)
+        unsigned flags = 0;                                      // bit r: this lane's bin of row r is a peak
+        {
+            const float* q = q0;
+            const int rlast = tb.kmax - kfirst;                  // rows with 32*r <= rlast hold a bin of the range
+#pragma unroll 4
+            for (int r = 0; r < nrows; ++r, q += 33) {
+                const float pm = q[0], pc = q[d0], pp = q[d1];
+                const bool pk = (32 * r <= rlast) && pc > ref && pc > pm && pc >= pp;
+                flags |= (pk ? 1u : 0u) << r;
+            }
+        }
+        // lane-wise compaction: exclusive prefix of the per-lane peak counts, one atomic per frame
+        const int mine = __popc(flags);
+        int inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        if (total) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(fo.npk, total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            float4* dst = fo.gRec + base + (inc - mine);
+            while (flags) {
+                const int r = __ffs(flags) - 1;
+                flags &= flags - 1;
+                const float* q = q0 + 33 * r;
+                *dst++ = make_float4(q[0], q[d0], q[d1], __int_as_float(kfirst + 32 * r));
+            }
+        }
+    }
+    if (kDebug) {
+        const int zch = warp_sum_i(zc_hop);
+        if (p.dbg.frame_feat && t < p.dbg.T_dbg && lane == 0) {
+            float* ff = p.dbg.frame_feat + (static_cast<size_t>(clip) * p.dbg.T_dbg + t) * 4;
+            ff[0] = cent_t; ff[1] = roll_t; ff[3] = static_cast<float>(zch);
+        }
+    }
+    (void)zc_hop;
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------ phases 2-3
+// Expects (set up by the caller, followed by __syncthreads): cs.s_i[1] = number of peak records, cs.s_f[w] = per-warp log-mel
+// max, cs.s_wacc[w*16 + 0/1] = per-warp centroid / roll-off sums, cs.s_i[8+w] = per-warp weighted zero-crossing counts.
+template <bool kDebug>
+__device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, const ClipSmem& cs, const ClipSlice& sl,
+                                          const int clip, const int T, float* __restrict__ out, unsigned& bank_parity,
+                                          const int tid, const int lane, const int warp) {
+    // ===================================== phase 2: tuning =====================================
+    const int np = cs.s_i[1];
+    float gmx = cs.s_f[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) gmx = fmaxf(gmx, cs.s_f[w]);
+
+    int tuning_idx = kTunings / 2;       // edges[50] == 0.0: librosa returns 0.0 for an empty pitch set
+    float thr = 0.0f;
+    int nsel = 0;
+    if (np > 0) {
+        // ---- per-peak arithmetic of librosa.piptrack / pitch_tuning at full lane occupancy
+        const bool in_smem = np <= kKeyCap;
+        unsigned* keys = in_smem ? reinterpret_cast<unsigned*>(cs.s_ex) : sl.gKey;
+        unsigned char* bins = in_smem ? reinterpret_cast<unsigned char*>(cs.s_ex + kKeyCap) : sl.gBin;
+        for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
+            float4 recs[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kThreads;
+                recs[u] = (i < np) ? sl.gRec[i] : make_float4(0.f, 1.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kThreads;
+                if (i >= np) break;
+                const float pm = recs[u].x, pc = recs[u].y, pp = recs[u].z;
+                const int k = __float_as_int(recs[u].w);
+                const float sum = __fadd_rn(pp, pm);
+                const float dif = __fsub_rn(pp, pm);
+                const double a = static_cast<double>(sum) - 2.0 * static_cast<double>(pc);
+                const double b = static_cast<double>(dif) * 0.5;
+                const float shift = (fabs(b) >= fabs(a)) ? 0.0f : static_cast<float>(-b / a);
+                const float avg = dif * 0.5f;
+                const float dskew = __fmul_rn(__fmul_rn(0.5f, avg), shift);
+                const float mag = __fadd_rn(pc, dskew);
+                const double pitch_d = (static_cast<double>(k) + static_cast<double>(shift)) *
+                                       static_cast<double>(tb.sr) / static_cast<double>(kNfft);
+                const float pitch = static_cast<float>(pitch_d);
+                // pitch_tuning: mod(12*log2(f/27.5), 1) in float32, wrapped to [-0.5, 0.5)
+                const float o = log2f(__fdiv_rn(pitch, 27.5f));
+                const float v = __fmul_rn(12.0f, o);
+                float res = v - floorf(v);
+                if (res >= 0.5f) res = res - 1.0f;
+                const double rd = static_cast<double>(res);
+                int bi = static_cast<int>(floor((rd + 0.5) * 100.0));
+                bi = max(0, min(kTunings - 1, bi));
+                while (bi > 0 && rd < cs.s_edges[bi]) --bi;
+                while (bi < kTunings - 1 && rd >= cs.s_edges[bi + 1]) ++bi;
+                keys[i] = fkey(mag);
+                bins[i] = static_cast<unsigned char>(bi);
+            }
+        }
+        __syncthreads();
+        int cle = 0;
+        const int r0 = (np - 1) >> 1;
+        const unsigned ka = radix_select(keys, np, r0, cs.s_hist, cs.s_i + 4, cle);
+        unsigned kb = ka;
+        if ((np & 1) == 0 && cle <= (np >> 1)) {
+            // upper median = smallest key above ka
+            if (tid == 0) cs.s_i[4] = static_cast<int>(0xffffffffu);
+            __syncthreads();
+            unsigned best = 0xffffffffu;
+            for (int i = tid; i < np; i += kThreads) {
+                const unsigned key = keys[i];
+                if (key > ka && key < best) best = key;
+            }
+            atomicMin(reinterpret_cast<unsigned*>(&cs.s_i[4]), best);
+            __syncthreads();
+            kb = static_cast<unsigned>(cs.s_i[4]);
+            __syncthreads();
+        }
+        const float fa = fkey_inv(ka), fb = fkey_inv(kb);
+        thr = ((np & 1) == 0) ? __fmul_rn(__fadd_rn(fa, fb), 0.5f) : fa;
+        const unsigned kthr = fkey(thr);
+        // histogram of the residual bins of peaks with mag >= median
+        for (int i = tid; i < 128; i += kThreads) cs.s_hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < np; i += kThreads)
+            if (keys[i] >= kthr) atomicAdd(&cs.s_hist[bins[i]], 1);
+        __syncthreads();
+        if (warp == 0) {
+            int bc = -1, bi = 1 << 20, tot = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int b = lane * 4 + q;
+                if (b < kTunings) {
+                    const int c = cs.s_hist[b];
+                    tot += c;
+                    if (c > bc) { bc = c; bi = b; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oc > bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+            }
+            tot = warp_sum_i(tot);
+            if (lane == 0) { cs.s_i[2] = bi; cs.s_i[3] = tot; }
+        }
+        __syncthreads();
+        tuning_idx = cs.s_i[2];
+        nsel = cs.s_i[3];
+    }
+    if (kDebug) {
+        if (p.dbg.clip_info && tid == 0) {
+            float* ci = p.dbg.clip_info + static_cast<size_t>(clip) * 8;
+            ci[0] = static_cast<float>(cs.s_edges[tuning_idx]);
+            ci[1] = gmx; ci[2] = static_cast<float>(np); ci[3] = thr;
+            ci[4] = static_cast<float>(nsel); ci[5] = static_cast<float>(T); ci[6] = 0.f; ci[7] = 0.f;
+        }
+    }
+
+    // ===================================== phase 3a: MFCC ======================================
+    // The tuning's FP16 hi/lo chroma bank (50 688 B) is staged into the now-free warp tiles by one TMA bulk copy
+    // (cp.async.bulk, completes on an mbarrier) that runs underneath the MFCC pooling.
+    __half* sW = reinterpret_cast<__half*>(cs.s_ex);       // [2][12][kP16Stride]
+    fence_proxy_async_smem();                           // generic-proxy accesses of the tiles precede the async write
+    __syncthreads();
+    if (tid == 0)
+        bulk_copy_g2s(sW, tb.chroma16 + static_cast<size_t>(tuning_idx) * 2 * kChroma * kP16Stride,
+                      2 * kChroma * kP16Stride * 2, cs.s_mbar);
+    {
+        const float clampv = __fsub_rn(gmx, 80.0f);
+        if (tid < 256) {
+            const int m = tid & 127, h = tid >> 7;
+            double a = 0.0;
+            for (int t = h; t < T; t += 2) a += static_cast<double>(fmaxf(sl.gL[static_cast<size_t>(t) * kMels + m], clampv));
+            cs.s_pool[h * 128 + m] = a;
+        }
+        __syncthreads();
+        if (tid < 128) cs.s_pool[tid] = (cs.s_pool[tid] + cs.s_pool[128 + tid]) / static_cast<double>(T);
+        __syncthreads();
+        if (tid < p.n_mfcc) {
+            double d = 0.0;
+            for (int q = 0; q < kMels; ++q) d = fma(tb.dctT[q * kMels + tid], cs.s_pool[q], d);
+            out[tid] = static_cast<float>(d);
+        }
+    }
+    mbar_wait(cs.s_mbar, bank_parity);                     // chroma bank has landed in shared memory
+    bank_parity ^= 1u;
+
+    // ===================================== phase 3b: chroma ====================================
+    // raw[c][t] = sum_k W[c][k] |X|^2[k][t] on the tensor cores: m16n8k16 FP16 MMAs with FP32 accumulators.  A = bank
+    // (hi and 2^11*lo halves, separate accumulators), B = the frame's scaled FP16 |X|^2 row.  One unit = 8 frames x
+    // 512 bins = 16 steps of 1 LDG.128 + 4 LDS.128 + 4 MMA; lane (g = lane/4, t4 = lane%4) feeds frame g's bins
+    // k0+8*t4..+7 and rows g, g+8 of the bank.  Units are dealt round-robin to the warps, the two K-halves of a tile
+    // are added in a fixed order, then each frame is normalised by its max (librosa norm=inf).
+    {
+        float* part2 = cs.s_ex + (2 * kChroma * kP16Stride) / 2;        // [kChromaTiles][2][96] floats after the bank
+        const int g = lane >> 2, t4 = lane & 3;
+        double csum[kChroma];                                        // per-thread sums over its frames
+#pragma unroll
+        for (int c = 0; c < kChroma; ++c) csum[c] = 0.0;
+        float wny[kChroma];
+#pragma unroll
+        for (int c = 0; c < kChroma; ++c) wny[c] = __ldg(tb.chroma_ny + tuning_idx * kChroma + c);
+        const int ntiles = (T + 7) >> 3;
+        for (int tile0 = 0; tile0 < ntiles; tile0 += kChromaTiles) {
+            const int nt = min(kChromaTiles, ntiles - tile0);
+            for (int u = warp; u < 2 * nt; u += kWarps) {
+                const int tl = u >> 1, kh = u & 1;
+                const int f = (tile0 + tl) * 8 + g;
+                const bool valid = f < T;
+                const __half* prow = sl.gP16 + static_cast<size_t>(valid ? f : 0) * kP16Stride + kh * 512 + 8 * t4;
+                const int r1 = (g < 4) ? g + 8 : g;                  // bank rows 12..15 do not exist
+                const __half* whi0 = sW + g * kP16Stride + kh * 512 + 8 * t4;
+                const __half* whi1 = sW + r1 * kP16Stride + kh * 512 + 8 * t4;
+                const __half* wlo0 = whi0 + kChroma * kP16Stride;
+                const __half* wlo1 = whi1 + kChroma * kP16Stride;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+                for (int kb0 = 0; kb0 < 16; kb0 += 8) {
+                    uint4 pv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        pv[i] = valid ? *reinterpret_cast<const uint4*>(prow + (kb0 + i) * 32) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int o = (kb0 + i) * 32;
+                        const uint4 h0 = *reinterpret_cast<const uint4*>(whi0 + o);
+                        uint4 h1 = *reinterpret_cast<const uint4*>(whi1 + o);
+                        const uint4 l0 = *reinterpret_cast<const uint4*>(wlo0 + o);
+                        uint4 l1 = *reinterpret_cast<const uint4*>(wlo1 + o);
+                        if (g >= 4) { h1 = make_uint4(0u, 0u, 0u, 0u); l1 = h1; }
+                        mma_f16(acc, h0.x, h1.x, h0.y, h1.y, pv[i].x, pv[i].y);
+                        mma_f16(acc, h0.z, h1.z, h0.w, h1.w, pv[i].z, pv[i].w);
+                        mma_f16(acl, l0.x, l1.x, l0.y, l1.y, pv[i].x, pv[i].y);
+                        mma_f16(acl, l0.z, l1.z, l0.w, l1.w, pv[i].z, pv[i].w);
+                    }
+                }
+                // D fragment: [0..1] = (chroma g, frames 2*t4, 2*t4+1), [2..3] = (chroma g+8, same frames)
+                constexpr float kLo = 1.0f / 2048.0f;
+                float* dst = part2 + (tl * 2 + kh) * 96;
+                *reinterpret_cast<float2*>(dst + g * 8 + 2 * t4) = make_float2(fmaf(acl[0], kLo, acc[0]), fmaf(acl[1], kLo, acc[1]));
+                if (g < 4)
+                    *reinterpret_cast<float2*>(dst + (g + 8) * 8 + 2 * t4) = make_float2(fmaf(acl[2], kLo, acc[2]), fmaf(acl[3], kLo, acc[3]));
+            }
+            __syncthreads();
+            for (int fl = tid; fl < nt * 8; fl += kThreads) {
+                const int f = tile0 * 8 + fl;
+                if (f < T) {
+                    const float* q = part2 + (fl >> 3) * 192 + (fl & 7);
+                    const float pn = sl.gNy[f];                            // scaled Nyquist bin
+                    float raw[kChroma];
+                    float mx = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < kChroma; ++c) {
+                        raw[c] = fmaf(wny[c], pn, q[c * 8] + q[96 + c * 8]);
+                        mx = fmaxf(mx, fabsf(raw[c]));
+                    }
+                    // librosa.util.normalize: lengths below tiny(float32) are replaced by 1 (in unscaled units)
+                    const float inv_s = sl.gInvS[f];
+                    const bool small = mx * inv_s < FLT_MIN;
+#pragma unroll
+                    for (int c = 0; c < kChroma; ++c)
+                        csum[c] += static_cast<double>(small ? raw[c] * inv_s : __fdiv_rn(raw[c], mx));
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int c = 0; c < kChroma; ++c) {
+            double v = csum[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) cs.s_wacc[warp * 16 + 3 + c] = v;
+        }
+    }
+    __syncthreads();
+
+    // ===================================== epilogue: pooled row ================================
+    if (warp == 1) {
+        // pooled rms from the hop energies (frame t spans hops t-2 .. t+1; hops outside [0, T) are zero padding)
+        double a = 0.0;
+        for (int t = lane; t < T; t += 32) {
+            float e = (t >= 2) ? sl.gE[t - 2] : 0.0f;
+            e += (t >= 1) ? sl.gE[t - 1] : 0.0f;
+            e += sl.gE[t];
+            e += (t + 1 < T) ? sl.gE[t + 1] : 0.0f;
+            const float r = sqrtf(e * (1.0f / kNfft));
+            a += static_cast<double>(r);
+            if (kDebug) {
+                if (p.dbg.frame_feat && t < p.dbg.T_dbg)
+                    p.dbg.frame_feat[(static_cast<size_t>(clip) * p.dbg.T_dbg + t) * 4 + 2] = r;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) out[p.n_mfcc + 15] = static_cast<float>(a / static_cast<double>(T));
+    }
+    if (tid < 15) {
+        const double invT = 1.0 / static_cast<double>(T);
+        if (tid < kChroma) {
+            double v = 0.0;
+            for (int w = 0; w < kWarps; ++w) v += cs.s_wacc[w * 16 + 3 + tid];
+            out[p.n_mfcc + tid] = static_cast<float>(v * invT);
+        } else if (tid == 12) {
+            long long z = 0;
+            for (int w = 0; w < kWarps; ++w) z += cs.s_i[8 + w];
+            out[p.n_mfcc + 12] = static_cast<float>(static_cast<double>(z) / (static_cast<double>(kNfft) * T));
+        } else {
+            double v = 0.0;
+            for (int w = 0; w < kWarps; ++w) v += cs.s_wacc[w * 16 + (tid - 13)];
+            out[p.n_mfcc + tid] = static_cast<float>(v * invT);
+        }
+    }
+}
+
+}  // namespace sfx
