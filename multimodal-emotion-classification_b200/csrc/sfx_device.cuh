@@ -102,6 +102,76 @@ __device__ __forceinline__ void fft32(float (&re)[32], float (&im)[32]) {
     dit_stage<16>(re, im);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Packed FP32 (sm_100 FFMA2 / FADD2 / FMUL2): a complex value lives in one aligned 64-bit register pair (re, im) and
+// every butterfly acts on both halves at once.  ptxas folds the (re, im) swap and the per-half sign of a multiplication
+// by +-i into the operand swizzle of the packed instruction (R.F32x2.LO_HI.NP), broadcast constants into its immediate
+// slot and broadcast registers into the R.F32 form, so a radix-2 butterfly costs 3 instructions (2 when the twiddle is
+// trivial) instead of 6 (4).  Rounding per half is that of the scalar fma/add, so the scalar model in
+// tests/fft_model.py describes this code as well.
+typedef unsigned long long c64;
+__device__ __forceinline__ c64 pk(float a, float b) { c64 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ void upk(c64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ c64 add2(c64 a, c64 b) { c64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ c64 sub2(c64 a, c64 b) { c64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ c64 mul2(c64 a, c64 b) { c64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ c64 fma2(c64 a, c64 b, c64 c) {
+    c64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ c64 rot_mi(c64 v) { float a, b; upk(v, a, b); return pk(b, -a); }   // -i * v
+__device__ __forceinline__ c64 rot_pi(c64 v) { float a, b; upk(v, a, b); return pk(-b, a); }   // +i * v
+__device__ __forceinline__ c64 bc2(float c) { return pk(c, c); }                                // (c, c)
+// v * w for complex v and w = (wr, wi): wr * v + wi * (i v)
+__device__ __forceinline__ c64 cmul(c64 v, float wr, float wi) { return fma2(rot_pi(v), bc2(wi), mul2(v, bc2(wr))); }
+
+// radix-2 DIT butterfly (a, b) <- (a + w b, a - w b), w = exp(-2 pi i Q / 32), same tangent forms as dit_bfly
+template <int Q>
+__device__ __forceinline__ void dit_bfly_p(c64& a, c64& b) {
+    if constexpr (Q == 0) {
+        const c64 x = sub2(a, b);
+        a = add2(a, b); b = x;
+    } else if constexpr (Q == 8) {
+        const c64 r = rot_mi(b);
+        const c64 x = sub2(a, r);
+        a = add2(a, r); b = x;
+    } else {
+        constexpr float c = cos32(Q), sn = sin32x(Q);
+        constexpr bool use_c = (c >= 0 ? c : -c) >= sn;
+        if constexpr (use_c) {
+            constexpr float t = sn / c;
+            const c64 p = fma2(rot_mi(b), bc2(t), b);          // (br + t bi, bi - t br)
+            b = fma2(p, bc2(-c), a);
+            a = fma2(p, bc2(c), a);
+        } else {
+            constexpr float t = c / sn;
+            const c64 p = rot_mi(fma2(rot_pi(b), bc2(t), b));  // (t br + bi, t bi - br)
+            b = fma2(p, bc2(-sn), a);
+            a = fma2(p, bc2(sn), a);
+        }
+    }
+}
+template <int H>
+__device__ __forceinline__ void dit_stage_p(c64 (&z)[32]) {
+    sfor<16 / H>([&](auto B) {
+        sfor<H>([&](auto J) {
+            constexpr int p0 = decltype(B)::value * 2 * H + decltype(J)::value;
+            constexpr int i0 = brev5(p0), i1 = brev5(p0 + H);
+            constexpr int Q = decltype(J)::value * (16 / H);
+            dit_bfly_p<Q>(z[i0], z[i1]);
+        });
+    });
+}
+// 32-point complex FFT on packed values: natural-order input x[n] in slot n, output X[k] in slot brev5(k)
+__device__ __forceinline__ void fft32p(c64 (&z)[32]) {
+    dit_stage_p<1>(z);
+    dit_stage_p<2>(z);
+    dit_stage_p<4>(z);
+    dit_stage_p<8>(z);
+    dit_stage_p<16>(z);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

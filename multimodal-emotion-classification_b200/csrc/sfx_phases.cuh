@@ -126,41 +126,37 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
         zc_w = multA * zc - (multA - mult0) * zc_first;
     }
 
-    // ---- Hann window (periodic, scipy.signal.get_window('hann', 2048))
+    // ---- Hann window (periodic, scipy.signal.get_window('hann', 2048)); from here on each complex sample
+    //      z[m1] = (x[2n], x[2n+1]), n = lane + 32 m1, is one packed register pair
+    c64 z[32];
 #pragma unroll
     for (int m1 = 0; m1 < 32; m1 += 2) {
-        const float4 w = *reinterpret_cast<const float4*>(fs.s_hann + (m1 >> 1) * 64 + 2 * lane);
-        re[m1] *= w.x;
-        im[m1] *= w.y;
-        re[m1 + 1] *= w.z;
-        im[m1 + 1] *= w.w;
+        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(fs.s_hann + (m1 >> 1) * 64 + 2 * lane);
+        z[m1] = mul2(pk(re[m1], im[m1]), w.x);
+        z[m1 + 1] = mul2(pk(re[m1 + 1], im[m1 + 1]), w.y);
     }
     // ---- 1024-pt complex FFT: radix-32 over m1, twiddle, transpose, radix-32 over m2
-    fft32(re, im);
+    fft32p(z);
     // exchange tile: float4 slot (k1/2)*33 + lane holds rows k1, k1+1 of column `lane`
     sfor<16>([&](auto K) {
         constexpr int k1 = 2 * decltype(K)::value;
         constexpr int a = brev5(k1), b = brev5(k1 + 1);
         const float4 w = *reinterpret_cast<const float4*>(fs.s_tw1 + (k1 >> 1) * 64 + 2 * lane);
-        float4 v;
-        v.x = fmaf(re[a], w.x, -(im[a] * w.y));
-        v.y = fmaf(re[a], w.y, im[a] * w.x);
-        v.z = fmaf(re[b], w.z, -(im[b] * w.w));
-        v.w = fmaf(re[b], w.w, im[b] * w.z);
-        reinterpret_cast<float4*>(fs.ex)[(k1 >> 1) * 33 + lane] = v;
+        ulonglong2 v;
+        v.x = cmul(z[a], w.x, w.y);
+        v.y = cmul(z[b], w.z, w.w);
+        reinterpret_cast<ulonglong2*>(fs.ex)[(k1 >> 1) * 33 + lane] = v;
     });
     __syncwarp();
     {
-        const float2* src = fs.ex + ((lane >> 1) * 33) * 2 + (lane & 1);      // row `lane`: half of the float4 slots
+        const c64* src = reinterpret_cast<const c64*>(fs.ex) + ((lane >> 1) * 33) * 2 + (lane & 1);   // row `lane`
 #pragma unroll
-        for (int m2 = 0; m2 < 32; ++m2) {
-            const float2 v = src[2 * m2];
-            re[m2] = v.x;
-            im[m2] = v.y;
-        }
+        for (int m2 = 0; m2 < 32; ++m2) z[m2] = src[2 * m2];
     }
     __syncwarp();
-    fft32(re, im);
+    fft32p(z);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) upk(z[i], re[i], im[i]);
 
     // ---- real-FFT unpack, one conjugate pair per step: lane holds Z[lane + 32*k2]; for k2 < 16 it forms
     //      X[k] and X[1024-k] (k = lane + 32*k2) from Z[k] and Z[1024-k] (lane (32-lane)&31, register 31-k2;
