@@ -123,6 +123,8 @@ __device__ __forceinline__ c64 fma2(c64 a, c64 b, c64 c) {
 __device__ __forceinline__ c64 rot_mi(c64 v) { float a, b; upk(v, a, b); return pk(b, -a); }   // -i * v
 __device__ __forceinline__ c64 rot_pi(c64 v) { float a, b; upk(v, a, b); return pk(-b, a); }   // +i * v
 __device__ __forceinline__ c64 bc2(float c) { return pk(c, c); }                                // (c, c)
+__device__ __forceinline__ c64 neg2(c64 v) { float a, b; upk(v, a, b); return pk(-a, -b); }
+__device__ __forceinline__ c64 conj2(c64 v) { float a, b; upk(v, a, b); return pk(a, -b); }
 // v * w for complex v and w = (wr, wi): wr * v + wi * (i v)
 __device__ __forceinline__ c64 cmul(c64 v, float wr, float wi) { return fma2(rot_pi(v), bc2(wi), mul2(v, bc2(wr))); }
 
@@ -164,8 +166,10 @@ __device__ __forceinline__ void dit_stage_p(c64 (&z)[32]) {
     });
 }
 // 32-point complex FFT on packed values: natural-order input x[n] in slot n, output X[k] in slot brev5(k)
+// (kFirst = 2 when the caller has already done the first stage, slots r and r + 16)
+template <int kFirst = 1>
 __device__ __forceinline__ void fft32p(c64 (&z)[32]) {
-    dit_stage_p<1>(z);
+    if constexpr (kFirst == 1) dit_stage_p<1>(z);
     dit_stage_p<2>(z);
     dit_stage_p<4>(z);
     dit_stage_p<8>(z);

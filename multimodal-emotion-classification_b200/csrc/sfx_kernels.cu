@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     for (int i = tid; i < 1024; i += kThreads) {
         const int r = i >> 5, l = i & 31;
         const int d = (r >> 1) * 64 + 2 * l + (r & 1);
-        s_hann[d] = tb.hann[i];
+        s_hann[(r & 15) * 64 + 2 * l + (r >> 4)] = tb.hann[i];        // rows r, r + 16 side by side
         s_tw1[d] = tb.tw1[i];
         if (i < 512) s_tw2[d] = tb.tw2[i];
     }

@@ -126,17 +126,20 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
         zc_w = multA * zc - (multA - mult0) * zc_first;
     }
 
-    // ---- Hann window (periodic, scipy.signal.get_window('hann', 2048)); from here on each complex sample
-    //      z[m1] = (x[2n], x[2n+1]), n = lane + 32 m1, is one packed register pair
+    // ---- Hann window (periodic, scipy.signal.get_window('hann', 2048)) fused into the first radix-2 stage of the
+    //      radix-32 pass over m1.  From here on each complex sample z[m1] = (x[2n], x[2n+1]), n = lane + 32 m1, is one
+    //      packed register pair; the window table holds rows r and r + 16 of a lane side by side.
     c64 z[32];
-#pragma unroll
-    for (int m1 = 0; m1 < 32; m1 += 2) {
-        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(fs.s_hann + (m1 >> 1) * 64 + 2 * lane);
-        z[m1] = mul2(pk(re[m1], im[m1]), w.x);
-        z[m1 + 1] = mul2(pk(re[m1 + 1], im[m1 + 1]), w.y);
-    }
+    sfor<16>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+        const ulonglong2 h = *reinterpret_cast<const ulonglong2*>(fs.s_hann + r * 64 + 2 * lane);
+        const c64 za = mul2(pk(re[r], im[r]), h.x);
+        const c64 xb = pk(re[r + 16], im[r + 16]);
+        z[r] = fma2(xb, h.y, za);
+        z[r + 16] = fma2(xb, neg2(h.y), za);
+    });
     // ---- 1024-pt complex FFT: radix-32 over m1, twiddle, transpose, radix-32 over m2
-    fft32p(z);
+    fft32p<2>(z);
     // exchange tile: float4 slot (k1/2)*33 + lane holds rows k1, k1+1 of column `lane`
     sfor<16>([&](auto K) {
         constexpr int k1 = 2 * decltype(K)::value;
@@ -155,12 +158,12 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
     }
     __syncwarp();
     fft32p(z);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) upk(z[i], re[i], im[i]);
 
     // ---- real-FFT unpack, one conjugate pair per step: lane holds Z[lane + 32*k2]; for k2 < 16 it forms
     //      X[k] and X[1024-k] (k = lane + 32*k2) from Z[k] and Z[1024-k] (lane (32-lane)&31, register 31-k2;
     //      lane 0 pairs with its own register (32-k2)&31).  Bin 512 (self-paired) is lane 0's register 16.
+    //      With E = Z[k] + conj(Z[1024-k]), O = Z[k] - conj(Z[1024-k]) and w = exp(-2 pi i k / 2048):
+    //      X[k] = E/2 - i w O/2 and conj(X[1024-k]) = E/2 + i w O/2; only |.|^2 is kept.
     float pmax = 0.0f;
     {
         float* PbL = fs.Pb + lane;
@@ -170,17 +173,21 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
         sfor<16>([&](auto K) {
             constexpr int k2 = decltype(K)::value;
             constexpr int a = brev5(k2), b = brev5(31 - k2), c = brev5((32 - k2) & 31);
-            const float zr = re[a], zi = im[a];
-            float pr = __shfl_sync(0xffffffffu, re[b], plane);
-            float pi = __shfl_sync(0xffffffffu, im[b], plane);
-            if (lane == 0) { pr = re[c]; pi = im[c]; }
+            float br_, bi_, cr_, ci_;
+            upk(z[b], br_, bi_);
+            upk(z[c], cr_, ci_);
+            float pr = __shfl_sync(0xffffffffu, br_, plane);
+            float pi = __shfl_sync(0xffffffffu, bi_, plane);
+            if (lane == 0) { pr = cr_; pi = ci_; }
             if constexpr ((k2 & 1) == 0) w4 = *reinterpret_cast<const float4*>(fs.s_tw2 + (k2 >> 1) * 64 + 2 * lane);
-            const float2 w = (k2 & 1) ? make_float2(w4.z, w4.w) : make_float2(w4.x, w4.y);   // (0.5 cos, 0.5 sin)(2 pi k / 2048)
-            const float er = zr + pr, ei = zi - pi, orr = zr - pr, oi = zi + pi;
-            const float u = fmaf(w.x, orr, w.y * oi);         // Re(w O)/2
-            const float v = fmaf(w.x, oi, -(w.y * orr));      // Im(w O)/2
-            const float xr = fmaf(0.5f, er, v), xi = fmaf(0.5f, ei, -u);       // X[k]
-            const float yr = fmaf(0.5f, er, -v), yi = fmaf(-0.5f, ei, -u);     // X[1024-k]
+            const float wc = (k2 & 1) ? w4.z : w4.x, ws = (k2 & 1) ? w4.w : w4.y;   // (0.5 cos, 0.5 sin)(2 pi k / 2048)
+            const c64 pc = pk(pr, -pi);                                  // conj(Z[1024-k])
+            const c64 E = add2(z[a], pc), O = sub2(z[a], pc);
+            const c64 q = fma2(rot_mi(O), bc2(wc), mul2(O, bc2(-ws)));   // -i w O / 2
+            const c64 X = fma2(E, bc2(0.5f), q), Y = fma2(E, bc2(0.5f), neg2(q));
+            float xr, xi, yr, yi;
+            upk(X, xr, xi);
+            upk(Y, yr, yi);
             const float P = fmaf(xr, xr, xi * xi);
             const float Q = fmaf(yr, yr, yi * yi);
             pmax = fmaxf(pmax, fmaxf(P, Q));
@@ -189,7 +196,9 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
         });
         if (lane == 0) {
             constexpr int h = brev5(16);
-            const float P512 = fmaf(re[h], re[h], im[h] * im[h]);
+            float hr, hi;
+            upk(z[h], hr, hi);
+            const float P512 = fmaf(hr, hr, hi * hi);
             fs.Pb[512 + 16] = P512;
             pmax = fmaxf(pmax, P512);
         }
