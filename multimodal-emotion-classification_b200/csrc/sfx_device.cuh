@@ -203,7 +203,7 @@ __device__ __forceinline__ unsigned fkey(float f) {      // order-preserving flo
 __device__ __forceinline__ float fkey_inv(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
-__device__ __forceinline__ int pidx(int k) { return k + (k >> 5); }   // padded index of bin k in the P tile
+__device__ __forceinline__ int pidx(int k) { return k + 4 * (k >> 5); }   // padded index of bin k in the P tile
 
 // ------------------------------------------------------------------------------------------------
 // CTA-wide radix select over the clip's peak magnitudes: key of the element of ascending rank r.

@@ -102,23 +102,26 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
         // librosa.zero_crossings(threshold=1e-10, zero_pos=True): sign(x) := (double)x < -1e-10, which for float32
         // x is exactly x < -9.99999944e-11f (0xaedbe6fe, the smallest float32 not below -1e-10)
         const float zthr = __uint_as_float(0xaedbe6feu);
-        int zc = 0, zc_first = 0;
+        // sign bits of the hop's samples: SA bit r = sample 512t + 64r + 2*lane, SB bit r+1 = the sample after it,
+        // SB bit 0 = this lane's last sample of the previous row (row 15 = the 64 samples before the hop)
+        unsigned SA = 0u, SB = (im[15] < zthr) ? 1u : 0u;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            SA |= (re[16 + r] < zthr) ? (1u << r) : 0u;
+            SB |= (im[16 + r] < zthr) ? (2u << r) : 0u;
+        }
+        const unsigned up = __shfl_up_sync(0xffffffffu, SB, 1);
+        const unsigned wrap = __shfl_sync(0xffffffffu, SB, 31);
+        const unsigned PB = (lane == 0) ? wrap : (up >> 1);          // bit r: sign of the sample before row r's first
         const int ib = kHop * t + 2 * lane;
         const int nm1 = static_cast<int>(n) - 1;
-        sfor<8>([&](auto R) {
-            constexpr int r = decltype(R)::value;
-            constexpr int m1 = 16 + r;
-            const float e0 = re[m1], e1 = im[m1];
-            const float up = __shfl_up_sync(0xffffffffu, e1, 1);
-            const float wrap = __shfl_sync(0xffffffffu, im[m1 - 1], 31);
-            const float prev = lane == 0 ? wrap : up;
-            const int i0 = ib + 64 * r;
-            const bool sp = prev < zthr, sa = e0 < zthr, sb = e1 < zthr;
-            const int c0 = (i0 >= 1 && i0 <= nm1 && sa != sp) ? 1 : 0;
-            const int c1 = (i0 + 1 <= nm1 && sb != sa) ? 1 : 0;
-            zc += c0 + c1;
-            if (r == 0 && lane == 0) zc_first = c0;
-        });
+        // crossings are counted at positions 1 <= i <= n-1: rows r with ib + 64 r (+1) <= n-1
+        const int v0 = min(max((nm1 - ib + 64) >> 6, 0), 8), v1 = min(max((nm1 - ib + 63) >> 6, 0), 8);
+        unsigned m0 = (1u << v0) - 1u;
+        if (ib == 0) m0 &= ~1u;
+        const unsigned c0 = (SA ^ PB) & m0, c1 = (SA ^ (SB >> 1)) & ((1u << v1) - 1u);
+        const int zc = __popc(c0) + __popc(c1);
+        const int zc_first = (lane == 0) ? static_cast<int>(c0 & 1u) : 0;
         const int tlo = max(0, t - 1);
         const int multA = min(T - 1, t + 2) - tlo + 1;
         const int mult0 = min(T - 1, t + 1) - tlo + 1;
@@ -167,7 +170,7 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
     float pmax = 0.0f;
     {
         float* PbL = fs.Pb + lane;
-        float* PbU = fs.Pb + (lane == 0 ? 1056 : 1055 - lane);
+        float* PbU = fs.Pb + (lane == 0 ? 1152 : 1148 - lane);
         const int plane = (32 - lane) & 31;
         float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
         sfor<16>([&](auto K) {
@@ -191,15 +194,15 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             const float P = fmaf(xr, xr, xi * xi);
             const float Q = fmaf(yr, yr, yi * yi);
             pmax = fmaxf(pmax, fmaxf(P, Q));
-            PbL[33 * k2] = P;
-            PbU[-33 * k2] = Q;
+            PbL[kPRow * k2] = P;
+            PbU[-kPRow * k2] = Q;
         });
         if (lane == 0) {
             constexpr int h = brev5(16);
             float hr, hi;
             upk(z[h], hr, hi);
             const float P512 = fmaf(hr, hr, hi * hi);
-            fs.Pb[512 + 16] = P512;
+            fs.Pb[pidx(512)] = P512;
             pmax = fmaxf(pmax, P512);
         }
     }
@@ -224,38 +227,53 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
     float cent_t, roll_t;
     {
         float s[33];
-        float run = 0.0f, ks = 0.0f, accA = 0.0f, accB = 0.0f;
+        float run = 0.0f, ks = 0.0f;
+        c64 acc = pk(0.0f, 0.0f);                        // (falling, rising) partial sums of the current interval
         float* pq = fs.part + lane * fs.mel_ps;
-        const float* Prow = fs.Pb + 33 * lane;
+        const float4* Prow = reinterpret_cast<const float4*>(fs.Pb + kPRow * lane);
         // the chroma phase reads this frame's |X|^2 back as FP16 scaled by an exact power of two that puts the
         // frame maximum in [2^14, 2^15) (the per-frame inf-norm of chroma_stft cancels the scale)
         // biased exponent of the scale = 14 - (E - 127) + 127 = 268 - E, clamped to a finite power of two
         const unsigned sbits = min(268u - ((__float_as_uint(pmax) >> 23) & 255u), 254u) << 23;
         const float scale = __uint_as_float(sbits);
         unsigned h2[16];
-        float hprev = 0.0f;
-        float4 ab4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        sfor<32>([&](auto J) {
-            constexpr int j = decltype(J)::value;
-            const float P = Prow[j];
-            if constexpr ((j & 1) == 0) hprev = P * scale;
-            else h2[j >> 1] = pack_half2(hprev, P * scale);
-            if (j > 0 && ((fs.mel_mask >> j) & 1u)) { *pq++ = accA; accA = accB; accB = 0.0f; }
-            if constexpr ((j & 1) == 0) ab4 = *reinterpret_cast<const float4*>(fs.s_melab + (j >> 1) * 64 + 2 * lane);
-            accA = fmaf((j & 1) ? ab4.z : ab4.x, P, accA);
-            accB = fmaf((j & 1) ? ab4.w : ab4.y, P, accB);
-            const float sv = sqrt_approx(P);
-            run += sv;
-            s[j] = run;
-            ks = fmaf(static_cast<float>(j), sv, ks);
+        ulonglong2 ab = make_ulonglong2(0ull, 0ull);
+        sfor<8>([&](auto G) {
+            constexpr int g = decltype(G)::value;
+            const float4 P4 = Prow[g];
+            {
+                float a, b;
+                upk(mul2(pk(P4.x, P4.y), bc2(scale)), a, b);
+                h2[2 * g] = pack_half2(a, b);
+                upk(mul2(pk(P4.z, P4.w), bc2(scale)), a, b);
+                h2[2 * g + 1] = pack_half2(a, b);
+            }
+            sfor<4>([&](auto Q4) {
+                constexpr int q = decltype(Q4)::value, j = 4 * g + q;
+                const float P = q == 0 ? P4.x : q == 1 ? P4.y : q == 2 ? P4.z : P4.w;
+                if (j > 0 && ((fs.mel_mask >> j) & 1u)) {
+                    float lo, hi;
+                    upk(acc, lo, hi);
+                    *pq++ = lo;
+                    acc = pk(hi, 0.0f);
+                }
+                if constexpr ((j & 1) == 0) ab = *reinterpret_cast<const ulonglong2*>(fs.s_melab + (j >> 1) * 64 + 2 * lane);
+                acc = fma2(bc2(P), (j & 1) ? ab.y : ab.x, acc);
+                const float sv = sqrt_approx(P);
+                run += sv;
+                s[j] = run;
+                ks = fmaf(static_cast<float>(j), sv, ks);
+            });
         });
         s[32] = run;
+        float accA, accB;
+        upk(acc, accA, accB);
         if (lane == 31) {
-            const float P = fs.Pb[1024 + 32];
+            const float P = fs.Pb[pidx(1024)];
             if (tb.mel_flush32) { *pq++ = accA; accA = accB; accB = 0.0f; }
-            const float2 ab = fs.s_melab[16 * 64 + 2 * 31];
-            accA = fmaf(ab.x, P, accA);
-            accB = fmaf(ab.y, P, accB);
+            const float2 ab1 = fs.s_melab[16 * 64 + 2 * 31];
+            accA = fmaf(ab1.x, P, accA);
+            accB = fmaf(ab1.y, P, accB);
             const float sv = sqrt_approx(P);
             run += sv;
             s[32] = run;
@@ -268,7 +286,7 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             uint4* dst = reinterpret_cast<uint4*>(fo.gP16 + static_cast<size_t>(t) * kP16Stride + 32 * lane);
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
-            if (lane == 31) fo.gNy[t] = fs.Pb[1024 + 32] * scale;
+            if (lane == 31) fo.gNy[t] = fs.Pb[pidx(1024)] * scale;
             if (lane == 0) fo.gInvS[t] = __uint_as_float((254u << 23) - sbits);      // 1/scale, exact
         }
         float inc = run;
@@ -342,7 +360,7 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             const float* q = q0;
             const int rlast = tb.kmax - kfirst;                  // rows with 32*r <= rlast hold a bin of the range
 #pragma unroll 4
-            for (int r = 0; r < nrows; ++r, q += 33) {
+            for (int r = 0; r < nrows; ++r, q += kPRow) {
                 const float pm = q[0], pc = q[d0], pp = q[d1];
                 const bool pk = (32 * r <= rlast) && pc > ref && pc > pm && pc >= pp;
                 flags |= (pk ? 1u : 0u) << r;
@@ -365,7 +383,7 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             while (flags) {
                 const int r = __ffs(flags) - 1;
                 flags &= flags - 1;
-                const float* q = q0 + 33 * r;
+                const float* q = q0 + kPRow * r;
                 *dst++ = make_float4(q[0], q[d0], q[d1], __int_as_float(kfirst + 32 * r));
             }
         }
