@@ -71,7 +71,8 @@ typedef struct {
     float   *P;          /* [B][T_dbg][1056] power spectrum |X|^2 */
     float   *logmel;     /* [B][T_dbg][128]  10*log10(max(1e-10, mel)) before the top_db clamp */
     float   *frame_feat; /* [B][T_dbg][4]    per-frame centroid(Hz), rolloff(Hz), rms, zc-count of the frame's hop */
-    float   *clip_info;  /* [B][8]           tuning, gmax, n_peaks, median threshold, n_selected, T, 0, 0 */
+    float   *clip_info;  /* [B][8]           tuning, gmax, n_peaks, median threshold, n_selected, T,
+                          *                   peaks whose fast-path result differs from the reference form (must be 0), 0 */
     int32_t  T_dbg;      /* frames allocated per clip in the arrays above */
 } sfx_debug_out;
 

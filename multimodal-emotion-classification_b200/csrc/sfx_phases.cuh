@@ -399,6 +399,29 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
     __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------------------ per-peak reference forms
+// librosa.piptrack's parabolic shift as numba types it: float32 sums, float64 quotient, float32 result
+static __device__ __noinline__ float peak_shift_exact(float pm, float pc, float pp) {
+    const float sum = __fadd_rn(pp, pm);
+    const float dif = __fsub_rn(pp, pm);
+    const double a = static_cast<double>(sum) - 2.0 * static_cast<double>(pc);
+    const double b = static_cast<double>(dif) * 0.5;
+    return (fabs(b) >= fabs(a)) ? 0.0f : static_cast<float>(-b / a);
+}
+// librosa.pitch_tuning: float32 mod(12*log2(f/27.5), 1) wrapped to [-0.5, 0.5), located in np.linspace(-0.5, 0.5, 101)
+static __device__ __noinline__ int peak_bin_exact(float pitch, const double* s_edges) {
+    const float o = log2f(__fdiv_rn(pitch, 27.5f));
+    const float v = __fmul_rn(12.0f, o);
+    float res = v - floorf(v);
+    if (res >= 0.5f) res = res - 1.0f;
+    const double rd = static_cast<double>(res);
+    int bi = static_cast<int>(floor((rd + 0.5) * 100.0));
+    bi = max(0, min(kTunings - 1, bi));
+    while (bi > 0 && rd < s_edges[bi]) --bi;
+    while (bi < kTunings - 1 && rd >= s_edges[bi + 1]) ++bi;
+    return bi;
+}
+
 // ------------------------------------------------------------------------------------------------ phases 2-3
 // Expects (set up by the caller, followed by __syncthreads): cs.s_i[1] = number of peak records, cs.s_f[w] = per-warp log-mel
 // max, cs.s_wacc[w*16 + 0/1] = per-warp centroid / roll-off sums, cs.s_i[8+w] = per-warp weighted zero-crossing counts.
@@ -415,47 +438,109 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
     int tuning_idx = kTunings / 2;       // edges[50] == 0.0: librosa returns 0.0 for an empty pitch set
     float thr = 0.0f;
     int nsel = 0;
+    if (kDebug) {                        // cs.s_i[16]: peaks whose fast-path shift or bin differs from the reference form
+        if (tid == 0) cs.s_i[16] = 0;
+        __syncthreads();
+    }
     if (np > 0) {
         // ---- per-peak arithmetic of librosa.piptrack / pitch_tuning at full lane occupancy
         const bool in_smem = np <= kKeyCap;
         unsigned* keys = in_smem ? reinterpret_cast<unsigned*>(cs.s_ex) : sl.gKey;
         unsigned char* bins = in_smem ? reinterpret_cast<unsigned char*>(cs.s_ex + kKeyCap) : sl.gBin;
+        // Four peaks per thread and step, all arithmetic branch-free so that the four dependency chains interleave.
+        // The two expensive pieces have fast forms whose result is provably the reference one unless a guard fires,
+        // in which case the peak is redone the slow way (peak_shift_exact / peak_bin_exact):
+        //   shift = float(-b/a): Newton quotient with |error| < 2^-50 relative, accepted unless it lies within 2^-45
+        //           of a float32 rounding boundary or the operands leave the normal float range;
+        //   bin:   residual from MUFU.LG2 (|error| < 4e-5 in 12*log2), accepted unless it falls within 0.8 % of a bin
+        //           width of an edge of the 100-bin grid (which includes the +-0.5 wrap).
+        const float4 kDummy = make_float4(0.f, 1.f, 1.f, __int_as_float(64));      // harmless stand-in past the end
+        float4 nxt[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = tid + u * kThreads;
+            nxt[u] = (i < np) ? sl.gRec[i] : kDummy;
+        }
         for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
             float4 recs[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * kThreads;
-                recs[u] = (i < np) ? sl.gRec[i] : make_float4(0.f, 1.f, 0.f, 0.f);
+                recs[u] = nxt[u];
+                const int i = i0 + (4 + u) * kThreads;                                // next step's records
+                nxt[u] = (i < np) ? sl.gRec[i] : kDummy;
             }
+            float shift[4];
+            bool redo = false;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * kThreads;
-                if (i >= np) break;
                 const float pm = recs[u].x, pc = recs[u].y, pp = recs[u].z;
-                const int k = __float_as_int(recs[u].w);
                 const float sum = __fadd_rn(pp, pm);
                 const float dif = __fsub_rn(pp, pm);
                 const double a = static_cast<double>(sum) - 2.0 * static_cast<double>(pc);
                 const double b = static_cast<double>(dif) * 0.5;
-                const float shift = (fabs(b) >= fabs(a)) ? 0.0f : static_cast<float>(-b / a);
-                const float avg = dif * 0.5f;
-                const float dskew = __fmul_rn(__fmul_rn(0.5f, avg), shift);
-                const float mag = __fadd_rn(pc, dskew);
-                const double pitch_d = (static_cast<double>(k) + static_cast<double>(shift)) *
+                const float af = static_cast<float>(a);
+                double r = static_cast<double>(__frcp_rn(af));
+                r = fma(fma(-a, r, 1.0), r, r);
+                const double q1 = b * r;
+                const double q = -fma(fma(-q1, a, b), r, q1);
+                const unsigned qlo = static_cast<unsigned>(__double2loint(q)) & 0x1fffffffu;     // bits dropped by float32
+                const unsigned qe = (static_cast<unsigned>(__double2hiint(q)) >> 20) & 0x7ffu;   // biased exponent
+                const unsigned ae = (__float_as_uint(af) >> 23) & 0xffu;
+                const bool zero = fabs(b) >= fabs(a);
+                const bool bad = !zero && b != 0.0 && ((qlo - 0x0fffff00u) < 0x200u || qe < 1023u - 100u || ae < 27u || ae > 227u);
+                redo |= bad;
+                shift[u] = zero ? 0.0f : static_cast<float>(q);
+            }
+            if (redo) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) shift[u] = peak_shift_exact(recs[u].x, recs[u].y, recs[u].z);
+            }
+            float pitch[4];
+            int bin[4];
+            unsigned key[4];
+            unsigned need = 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float pm = recs[u].x, pc = recs[u].y, pp = recs[u].z;
+                const int k = __float_as_int(recs[u].w);
+                const float avg = __fsub_rn(pp, pm) * 0.5f;
+                const float dskew = __fmul_rn(__fmul_rn(0.5f, avg), shift[u]);
+                key[u] = fkey(__fadd_rn(pc, dskew));
+                const double pitch_d = (static_cast<double>(k) + static_cast<double>(shift[u])) *
                                        static_cast<double>(tb.sr) / static_cast<double>(kNfft);
-                const float pitch = static_cast<float>(pitch_d);
-                // pitch_tuning: mod(12*log2(f/27.5), 1) in float32, wrapped to [-0.5, 0.5)
-                const float o = log2f(__fdiv_rn(pitch, 27.5f));
-                const float v = __fmul_rn(12.0f, o);
+                pitch[u] = static_cast<float>(pitch_d);
+                // pitch_tuning: mod(12*log2(f/27.5), 1) wrapped to [-0.5, 0.5), then its 0.01-wide bin
+                const float v = fmaf(12.0f, __log2f(pitch[u]), -57.3763165622959f);        // 12*log2(27.5)
                 float res = v - floorf(v);
-                if (res >= 0.5f) res = res - 1.0f;
-                const double rd = static_cast<double>(res);
-                int bi = static_cast<int>(floor((rd + 0.5) * 100.0));
-                bi = max(0, min(kTunings - 1, bi));
-                while (bi > 0 && rd < cs.s_edges[bi]) --bi;
-                while (bi < kTunings - 1 && rd >= cs.s_edges[bi + 1]) ++bi;
-                keys[i] = fkey(mag);
-                bins[i] = static_cast<unsigned char>(bi);
+                if (res >= 0.5f) res -= 1.0f;
+                const float uf = fmaf(res, 100.0f, 50.0f);
+                const float fl = floorf(uf);
+                const float fr = uf - fl;
+                bin[u] = max(0, min(kTunings - 1, static_cast<int>(fl)));
+                need |= (fr > 0.008f && fr < 0.992f) ? 0u : (1u << u);
+            }
+            while (need) {                                       // usually at most one of the four
+                const int u = __ffs(need) - 1;
+                need &= need - 1u;
+                const float pt = u == 0 ? pitch[0] : u == 1 ? pitch[1] : u == 2 ? pitch[2] : pitch[3];
+                const int be = peak_bin_exact(pt, cs.s_edges);
+                if (u == 0) bin[0] = be;
+                if (u == 1) bin[1] = be;
+                if (u == 2) bin[2] = be;
+                if (u == 3) bin[3] = be;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kThreads;
+                if (i < np) {
+                    keys[i] = key[u];
+                    bins[i] = static_cast<unsigned char>(bin[u]);
+                    if (kDebug) {
+                        const float se = peak_shift_exact(recs[u].x, recs[u].y, recs[u].z);
+                        const bool same = __float_as_uint(se) == __float_as_uint(shift[u]) || (se == 0.0f && shift[u] == 0.0f);
+                        if (!same || peak_bin_exact(pitch[u], cs.s_edges) != bin[u]) atomicAdd(&cs.s_i[16], 1);
+                    }
+                }
             }
         }
         __syncthreads();
@@ -515,7 +600,8 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             float* ci = p.dbg.clip_info + static_cast<size_t>(clip) * 8;
             ci[0] = static_cast<float>(cs.s_edges[tuning_idx]);
             ci[1] = gmx; ci[2] = static_cast<float>(np); ci[3] = thr;
-            ci[4] = static_cast<float>(nsel); ci[5] = static_cast<float>(T); ci[6] = 0.f; ci[7] = 0.f;
+            ci[4] = static_cast<float>(nsel); ci[5] = static_cast<float>(T);
+            ci[6] = static_cast<float>(cs.s_i[16]); ci[7] = 0.f;
         }
     }
 

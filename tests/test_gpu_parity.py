@@ -288,6 +288,26 @@ def test_torture_signals(ex):
     assert ok, "\n" + report + "\n" + str(names)
 
 
+def test_fast_peak_arithmetic_equals_reference_forms(ex):
+    """Phase 2 evaluates librosa's parabolic shift (float64 quotient) and the tuning-residual bin with fast forms guarded
+    by exactness checks; the debug kernel re-evaluates every peak with the reference forms and counts disagreements
+    (clip_info[:, 6]).  The count must be zero on every kind of signal, in both pipelines."""
+    names, wt = torture_clips()
+    w = np.concatenate([synth.make_batch(96, N3S, seed=17), wt], axis=0)
+    total = 0
+    try:
+        for mode in (1, 2):
+            assert ex.lib.sfx_set_pipeline(mode) == 0
+            dbg = {}
+            ex.extract(dev(w), debug=dbg)
+            ci = dbg["clip_info"].cpu().numpy()
+            assert (ci[:, 6] == 0).all(), (mode, np.nonzero(ci[:, 6])[0], ci[ci[:, 6] != 0][:, [2, 6]])
+            total += int(ci[:, 2].sum())
+    finally:
+        ex.lib.sfx_set_pipeline(0)
+    assert total > 500_000          # the check saw a meaningful number of peaks
+
+
 def test_fused_and_split_pipelines_agree(ex):
     """The persistent fused kernel and the frame-parallel two-kernel pipeline run the same arithmetic; only the order of
     the per-clip float64 sums of the per-frame centroid / roll-off differs."""
