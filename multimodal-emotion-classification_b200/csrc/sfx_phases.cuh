@@ -423,7 +423,7 @@ static __device__ __noinline__ int peak_bin_exact(float pitch, const double* s_e
 }
 
 // ------------------------------------------------------------------------------------------------ phases 2-3
-// Expects (set up by the caller, followed by __syncthreads): cs.s_i[1] = number of peak records, cs.s_f[w] = per-warp log-mel
+// Expects (set up by the caller, followed by __syncthreads): cs.s_i[1] = number of peak records, cs.s_i[17] = 0, cs.s_f[w] = per-warp log-mel
 // max, cs.s_wacc[w*16 + 0/1] = per-warp centroid / roll-off sums, cs.s_i[8+w] = per-warp weighted zero-crossing counts.
 template <bool kDebug>
 __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, const ClipSmem& cs, const ClipSlice& sl,
@@ -444,104 +444,126 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
     }
     if (np > 0) {
         // ---- per-peak arithmetic of librosa.piptrack / pitch_tuning at full lane occupancy
+        // Four peaks per thread and step, branch-free so that the four dependency chains interleave.  The two expensive
+        // pieces have fast forms whose result is provably the reference one unless a guard fires:
+        //   shift = float(-b/a): Newton quotient (relative error < 2^-50), accepted unless it lies within 2^-44 of a
+        //           float32 rounding boundary or an operand leaves the normal float range; else redone at once with the
+        //           IEEE division (peak_shift_exact; rare);
+        //   bin:   residual from MUFU.LG2 of the mantissa (error < 1.5e-5 in 12*log2 against the reference form),
+        //           accepted unless it falls within 0.25 % of a bin width of an edge of the 100-bin grid (which includes
+        //           the +-0.5 wrap); else the peak is queued and redone after the loop (peak_bin_exact) by all threads.
         const bool in_smem = np <= kKeyCap;
         unsigned* keys = in_smem ? reinterpret_cast<unsigned*>(cs.s_ex) : sl.gKey;
         unsigned char* bins = in_smem ? reinterpret_cast<unsigned char*>(cs.s_ex + kKeyCap) : sl.gBin;
-        // Four peaks per thread and step, all arithmetic branch-free so that the four dependency chains interleave.
-        // The two expensive pieces have fast forms whose result is provably the reference one unless a guard fires,
-        // in which case the peak is redone the slow way (peak_shift_exact / peak_bin_exact):
-        //   shift = float(-b/a): Newton quotient with |error| < 2^-50 relative, accepted unless it lies within 2^-45
-        //           of a float32 rounding boundary or the operands leave the normal float range;
-        //   bin:   residual from MUFU.LG2 (|error| < 4e-5 in 12*log2), accepted unless it falls within 0.8 % of a bin
-        //           width of an edge of the 100-bin grid (which includes the +-0.5 wrap).
-        const float4 kDummy = make_float4(0.f, 1.f, 1.f, __int_as_float(64));      // harmless stand-in past the end
-        float4 nxt[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = tid + u * kThreads;
-            nxt[u] = (i < np) ? sl.gRec[i] : kDummy;
-        }
-        for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
-            float4 recs[4];
+        uint2* redo_list = reinterpret_cast<uint2*>(cs.s_pool);              // (peak index, pitch bits), kRedoCap entries
+        auto peaks = [&](auto SM) {
+            constexpr bool kSmem = decltype(SM)::value;
+            const float4 kDummy = make_float4(0.f, 1.f, 1.f, __int_as_float(64));      // harmless stand-in past the end
+            float4 nxt[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                recs[u] = nxt[u];
-                const int i = i0 + (4 + u) * kThreads;                                // next step's records
+                const int i = tid + u * kThreads;
                 nxt[u] = (i < np) ? sl.gRec[i] : kDummy;
             }
-            float shift[4];
-            bool redo = false;
+            for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
+                float4 recs[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float pm = recs[u].x, pc = recs[u].y, pp = recs[u].z;
-                const float sum = __fadd_rn(pp, pm);
-                const float dif = __fsub_rn(pp, pm);
-                const double a = static_cast<double>(sum) - 2.0 * static_cast<double>(pc);
-                const double b = static_cast<double>(dif) * 0.5;
-                const float af = static_cast<float>(a);
-                double r = static_cast<double>(__frcp_rn(af));
-                r = fma(fma(-a, r, 1.0), r, r);
-                const double q1 = b * r;
-                const double q = -fma(fma(-q1, a, b), r, q1);
-                const unsigned qlo = static_cast<unsigned>(__double2loint(q)) & 0x1fffffffu;     // bits dropped by float32
-                const unsigned qe = (static_cast<unsigned>(__double2hiint(q)) >> 20) & 0x7ffu;   // biased exponent
-                const unsigned ae = (__float_as_uint(af) >> 23) & 0xffu;
-                const bool zero = fabs(b) >= fabs(a);
-                const bool bad = !zero && b != 0.0 && ((qlo - 0x0fffff00u) < 0x200u || qe < 1023u - 100u || ae < 27u || ae > 227u);
-                redo |= bad;
-                shift[u] = zero ? 0.0f : static_cast<float>(q);
-            }
-            if (redo) {
+                for (int u = 0; u < 4; ++u) {
+                    recs[u] = nxt[u];
+                    const int i = i0 + (4 + u) * kThreads;                                // next step's records
+                    nxt[u] = (i < np) ? sl.gRec[i] : kDummy;
+                }
+                float shift[4];
+                bool redo = false;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) shift[u] = peak_shift_exact(recs[u].x, recs[u].y, recs[u].z);
-            }
-            float pitch[4];
-            int bin[4];
-            unsigned key[4];
-            unsigned need = 0u;
+                for (int u = 0; u < 4; ++u) {
+                    const float pm = recs[u].x, pc = recs[u].y, pp = recs[u].z;
+                    const float sum = __fadd_rn(pp, pm);
+                    const float dif = __fsub_rn(pp, pm);
+                    const double a = static_cast<double>(sum) - 2.0 * static_cast<double>(pc);
+                    const double b = static_cast<double>(dif) * 0.5;
+                    const float af = static_cast<float>(a);
+                    double r = static_cast<double>(rcp_approx(af));
+                    r = fma(fma(-a, r, 1.0), r, r);
+                    const double q1 = b * r;
+                    const double q = -fma(fma(-q1, a, b), r, q1);
+                    const unsigned qlo = static_cast<unsigned>(__double2loint(q)) & 0x1fffffffu;     // bits float32 drops
+                    const unsigned qe = (static_cast<unsigned>(__double2hiint(q)) >> 20) & 0x7ffu;   // biased exponent
+                    const unsigned ae = (__float_as_uint(af) >> 23) & 0xffu;
+                    const bool zero = fabs(b) >= fabs(a);
+                    const bool risky = ((qlo - 0x0fffff00u) < 0x200u) | (qe < 1023u - 100u) | ((ae - 27u) > 200u);
+                    redo |= risky & !zero & (dif != 0.0f);
+                    shift[u] = zero ? 0.0f : static_cast<float>(q);
+                }
+                if (redo) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float pm = recs[u].x, pc = recs[u].y, pp = recs[u].z;
-                const int k = __float_as_int(recs[u].w);
-                const float avg = __fsub_rn(pp, pm) * 0.5f;
-                const float dskew = __fmul_rn(__fmul_rn(0.5f, avg), shift[u]);
-                key[u] = fkey(__fadd_rn(pc, dskew));
-                const double pitch_d = (static_cast<double>(k) + static_cast<double>(shift[u])) *
-                                       static_cast<double>(tb.sr) / static_cast<double>(kNfft);
-                pitch[u] = static_cast<float>(pitch_d);
-                // pitch_tuning: mod(12*log2(f/27.5), 1) wrapped to [-0.5, 0.5), then its 0.01-wide bin
-                const float v = fmaf(12.0f, __log2f(pitch[u]), -57.3763165622959f);        // 12*log2(27.5)
-                float res = v - floorf(v);
-                if (res >= 0.5f) res -= 1.0f;
-                const float uf = fmaf(res, 100.0f, 50.0f);
-                const float fl = floorf(uf);
-                const float fr = uf - fl;
-                bin[u] = max(0, min(kTunings - 1, static_cast<int>(fl)));
-                need |= (fr > 0.008f && fr < 0.992f) ? 0u : (1u << u);
-            }
-            while (need) {                                       // usually at most one of the four
-                const int u = __ffs(need) - 1;
-                need &= need - 1u;
-                const float pt = u == 0 ? pitch[0] : u == 1 ? pitch[1] : u == 2 ? pitch[2] : pitch[3];
-                const int be = peak_bin_exact(pt, cs.s_edges);
-                if (u == 0) bin[0] = be;
-                if (u == 1) bin[1] = be;
-                if (u == 2) bin[2] = be;
-                if (u == 3) bin[3] = be;
-            }
+                    for (int u = 0; u < 4; ++u) shift[u] = peak_shift_exact(recs[u].x, recs[u].y, recs[u].z);
+                }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * kThreads;
-                if (i < np) {
-                    keys[i] = key[u];
-                    bins[i] = static_cast<unsigned char>(bin[u]);
-                    if (kDebug) {
-                        const float se = peak_shift_exact(recs[u].x, recs[u].y, recs[u].z);
-                        const bool same = __float_as_uint(se) == __float_as_uint(shift[u]) || (se == 0.0f && shift[u] == 0.0f);
-                        if (!same || peak_bin_exact(pitch[u], cs.s_edges) != bin[u]) atomicAdd(&cs.s_i[16], 1);
+                for (int u = 0; u < 4; ++u) {
+                    const float pm = recs[u].x, pc = recs[u].y, pp = recs[u].z;
+                    const int k = __float_as_int(recs[u].w);
+                    const float avg = __fsub_rn(pp, pm) * 0.5f;
+                    const float dskew = __fmul_rn(__fmul_rn(0.5f, avg), shift[u]);
+                    const unsigned key = fkey(__fadd_rn(pc, dskew));
+                    const double pitch_d = (static_cast<double>(k) + static_cast<double>(shift[u])) *
+                                           static_cast<double>(tb.sr) / static_cast<double>(kNfft);
+                    const float pitch = static_cast<float>(pitch_d);
+                    // pitch_tuning: mod(12*log2(f/27.5), 1) wrapped to [-0.5, 0.5), then its 0.01-wide bin.  Only the
+                    // fractional part matters, so the exponent of f drops out: 12*log2(mantissa) - frac-preserving const
+                    const unsigned pb = __float_as_uint(pitch);
+                    const float mant = __uint_as_float((pb & 0x007fffffu) | 0x3f800000u);
+                    const float w = fmaf(12.0f, lg2_approx(mant), -9.37631656229592f);    // 12*(log2(m) - (log2(27.5) - 4))
+                    float res = w - floorf(w);
+                    if (res >= 0.5f) res -= 1.0f;
+                    const float uf = fmaf(res, 100.0f, 50.0f);
+                    const float fl = floorf(uf);
+                    const float fr = uf - fl;
+                    int bin = max(0, min(kTunings - 1, static_cast<int>(fl)));
+                    const int i = i0 + u * kThreads;
+                    // normal positive pitch and clear of the bin edges, else redo (NaN-safe: comparisons false -> redo)
+                    const bool sure = (fr > 0.0025f) & (fr < 0.9975f) & ((pb - 0x00800000u) < 0x7f000000u);
+                    if (!sure && i < np) {
+                        const int slot = atomicAdd(&cs.s_i[17], 1);
+                        if (slot < kRedoCap) redo_list[slot] = make_uint2(static_cast<unsigned>(i), pb);
+                        else bin = peak_bin_exact(pitch, cs.s_edges);
+                    }
+                    if (i < np) {
+                        if constexpr (kSmem) {
+                            reinterpret_cast<unsigned*>(cs.s_ex)[i] = key;
+                            reinterpret_cast<unsigned char*>(cs.s_ex + kKeyCap)[i] = static_cast<unsigned char>(bin);
+                        } else {
+                            sl.gKey[i] = key;
+                            sl.gBin[i] = static_cast<unsigned char>(bin);
+                        }
                     }
                 }
             }
+        };
+        if (in_smem) peaks(std::true_type{}); else peaks(std::false_type{});
+        __syncthreads();
+        {
+            const int nredo = min(cs.s_i[17], kRedoCap);
+            for (int j = tid; j < nredo; j += kThreads) {
+                const uint2 e = redo_list[j];
+                bins[e.x] = static_cast<unsigned char>(peak_bin_exact(__uint_as_float(e.y), cs.s_edges));
+            }
+        }
+        if (kDebug) {
+            // every peak again with the reference forms only; keys / bins must be identical
+            __syncthreads();
+            int diff = 0;
+            for (int i = tid; i < np; i += kThreads) {
+                const float4 rc = sl.gRec[i];
+                const float sh = peak_shift_exact(rc.x, rc.y, rc.z);
+                const float avg = __fsub_rn(rc.z, rc.x) * 0.5f;
+                const unsigned key = fkey(__fadd_rn(rc.y, __fmul_rn(__fmul_rn(0.5f, avg), sh)));
+                const double pitch_d = (static_cast<double>(__float_as_int(rc.w)) + static_cast<double>(sh)) *
+                                       static_cast<double>(tb.sr) / static_cast<double>(kNfft);
+                const int be = peak_bin_exact(static_cast<float>(pitch_d), cs.s_edges);
+                diff += (key != keys[i]) || (be != static_cast<int>(bins[i]));
+            }
+            if (diff) atomicAdd(&cs.s_i[16], diff);
         }
         __syncthreads();
         int cle = 0;

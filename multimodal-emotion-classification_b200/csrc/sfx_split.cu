@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 3) sfx_clips_kernel(const SplitParam
             sz = warp_sum_i(sz);
             lm = warp_max(lm);
             if (lane == 0) { s_wacc[warp * 16 + 0] = sc; s_wacc[warp * 16 + 1] = sr; s_i[8 + warp] = sz; s_f[warp] = lm; }
-            if (tid == 0) s_i[1] = npk_all[c];
+            if (tid == 0) { s_i[1] = npk_all[c]; s_i[17] = 0; }
         }
         __syncthreads();
 
