@@ -196,6 +196,17 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// predicated 16-byte store of a peak record at base[idx] (one mad.wide + one predicated st, no branch)
+__device__ __forceinline__ void st_record_if(bool pred, float4* base, unsigned idx, float a, float b, float c, int k) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u64 ad;\n\t"
+        "setp.ne.u32 p, %0, 0;\n\t"
+        "mad.wide.u32 ad, %1, 16, %2;\n\t"
+        "@p st.global.v4.b32 [ad], {%3, %4, %5, %6};\n\t}"
+        :: "r"(static_cast<unsigned>(pred)), "r"(idx), "l"(base), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)),
+           "r"(__float_as_uint(c)), "r"(k)
+        : "memory");
+}
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -59,11 +59,15 @@ struct Params {
     sfx_debug_out dbg;
 };
 
+__host__ __device__ inline int rec_frames(int Tmax) { return (Tmax + kWarps - 1) / kWarps * kWarps; }
+
 // bytes of scratch one CTA needs for clips of up to Tmax frames (multiple of 256)
 inline size_t cta_scratch_bytes(int Tmax, int max_pk) {
     // FP16 |X|^2 rows, log-mel rows, peak records (float4), peak keys (u32, overflow path), hop energy + Nyquist + 1/scale
     // per frame, peak bins (u8)
-    size_t b = static_cast<size_t>(Tmax) * (kP16Stride * 2 + kMels * 4 + 12 + static_cast<size_t>(max_pk) * (16 + 4 + 1));
+    // (records are kept in one segment per warp: capacity rounded up to kWarps frames)
+    size_t b = static_cast<size_t>(Tmax) * (kP16Stride * 2 + kMels * 4 + 12 + static_cast<size_t>(max_pk) * (4 + 1)) +
+               static_cast<size_t>(rec_frames(Tmax)) * max_pk * 16;
     return (b + 255) & ~static_cast<size_t>(255);
 }
 

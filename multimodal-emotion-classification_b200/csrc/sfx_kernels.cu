@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     __half* gP16 = reinterpret_cast<__half*>(slice);                                             // [Tmax][kP16Stride]
     float* gL = reinterpret_cast<float*>(gP16 + static_cast<size_t>(p.Tmax) * kP16Stride);       // [Tmax][128]
     float4* gRec = reinterpret_cast<float4*>(gL + static_cast<size_t>(p.Tmax) * kMels);
-    unsigned* gKey = reinterpret_cast<unsigned*>(gRec + static_cast<size_t>(p.Tmax) * p.max_pk);
+    const int seg_cap = rec_frames(p.Tmax) / kWarps * p.max_pk;               // peak records per warp segment
+    unsigned* gKey = reinterpret_cast<unsigned*>(gRec + static_cast<size_t>(kWarps) * seg_cap);
     float* gE = reinterpret_cast<float*>(gKey + static_cast<size_t>(p.Tmax) * p.max_pk);        // hop energies [Tmax]
     float* gNy = gE + p.Tmax;                                                                    // scaled Nyquist |X|^2 [Tmax]
     float* gInvS = gNy + p.Tmax;                                                                 // 1 / row scale [Tmax]
@@ -85,14 +86,14 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     fs.aligned8 = p.aligned8 != 0;
     FrameOut fo;
     fo.gP16 = gP16; fo.gL = gL; fo.gRec = gRec; fo.gE = gE; fo.gNy = gNy; fo.gInvS = gInvS;
-    fo.npk = &s_i[1]; fo.s_wacc = s_wacc; fo.s_f = s_f;
+    fo.npk = nullptr; fo.gSeg = gRec + static_cast<size_t>(warp) * seg_cap; fo.s_wacc = s_wacc; fo.s_f = s_f;
     fo.gCent = nullptr; fo.gRoll = nullptr; fo.gLmax = nullptr; fo.gZc = nullptr;
     const ClipSmem cs{s_ex, s_pool, s_wacc, s_edges, s_mbar, s_hist, s_i, s_f};
-    const ClipSlice sl{gP16, gL, gRec, gKey, gE, gNy, gInvS, gBin};
+    const ClipSlice sl{gP16, gL, gRec, gKey, gE, gNy, gInvS, gBin, seg_cap};
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_i[0] = atomicAdd(counter, 1); s_i[1] = 0; s_i[17] = 0; }
+        if (tid == 0) { s_i[0] = atomicAdd(counter, 1); s_i[17] = 0; }
         __syncthreads();
         const int clip = s_i[0];
         if (clip >= p.B) break;
@@ -109,16 +110,16 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         // per-warp running sums live in shared memory (s_wacc[warp][0..2] = centroid, rolloff, rms; s_f = log-mel max)
         if (lane < 2) s_wacc[warp * 16 + lane] = 0.0;
         if (lane == 0) s_f[warp] = -FLT_MAX;
-        int acc_zc = 0;
+        int acc_zc = 0, wcount = 0;
         __syncwarp();
 
         for (int t = warp; t < T; t += kWarps)
-            process_frame<kDebug, false>(p, tb, fs, fo, x, n, T, t, clip, lane, warp, acc_zc);
+            process_frame<kDebug, false>(p, tb, fs, fo, x, n, T, t, clip, lane, warp, acc_zc, wcount);
 
         // per-warp partials
         {
             const int zc = warp_sum_i(acc_zc);
-            if (lane == 0) s_i[8 + warp] = zc;
+            if (lane == 0) { s_i[8 + warp] = zc; s_i[20 + warp] = wcount; }
         }
         __syncthreads();
 

@@ -23,7 +23,8 @@ struct FrameSmem {
 // where phase 1 leaves its results
 struct FrameOut {
     __half* gP16; float* gL; float4* gRec; float* gE; float* gNy; float* gInvS;     // the clip's scratch slice
-    int* npk;                                                                          // peak counter (shared or global)
+    int* npk;                                                                          // split: the clip's peak counter
+    float4* gSeg;                                                                      // fused: this warp's record segment
     double* s_wacc; float* s_f;                                                        // fused: per-warp accumulators
     float* gCent; float* gRoll; float* gLmax; int* gZc;                                // split: per-frame values
 };
@@ -35,13 +36,14 @@ struct ClipSmem {
 
 struct ClipSlice {
     __half* gP16; float* gL; float4* gRec; unsigned* gKey; float* gE; float* gNy; float* gInvS; unsigned char* gBin;
+    int seg_cap;          // peak records are kept in kWarps segments of this capacity (cs.s_i[20 + w] = records in segment w)
 };
 
 // ------------------------------------------------------------------------------------------------ phase 1
 template <bool kDebug, bool kSplit>
 __device__ __forceinline__ void process_frame(const Params& p, const DevTables& tb, const FrameSmem& fs, const FrameOut& fo,
                                               const float* __restrict__ x, const long long n, const int T, const int t,
-                                              const int clip, const int lane, const int warp, int& acc_zc) {
+                                              const int clip, const int lane, const int warp, int& acc_zc, int& wcount) {
     float re[32], im[32];
     load_frame(x, n, t, lane, fs.aligned8, re, im);
     // ---- all-zero frame (the zero tail load_audio pads short clips with, reference :15-16): every result is
@@ -349,42 +351,66 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
 
     // ---- piptrack peak detection on the power spectrum (bins kmin..kmax); the per-peak arithmetic
     //      (parabolic shift, pitch, tuning residual) is done in phase 2 on the compacted records
-    {
+    if constexpr (!kSplit) {
+        // one pass: a row of 32 bins is tested and its peaks are appended (ballot-compacted) to this warp's own record
+        // segment of the clip, whose fill level `wcount` the warp carries in a register -- no atomics, no second pass
         const float ref = __fmul_rn(0.1f, pmax);
         const int kfirst = tb.kmin + lane;
         const float* q0 = fs.Pb + pidx(kfirst - 1);
-        const int d0 = pidx(kfirst) - pidx(kfirst - 1), d1 = pidx(kfirst + 1) - pidx(kfirst - 1);
-        const int nrows = (tb.kmax - tb.kmin + 32) >> 5;          // <= 16 (bins 1..1023, 32 per row)
-        unsigned flags = 0;                                      // bit r: this lane's bin of row r is a peak
-        {
-            const float* q = q0;
-            const int rlast = tb.kmax - kfirst;                  // rows with 32*r <= rlast hold a bin of the range
+        const float* q1 = fs.Pb + pidx(kfirst);
+        const float* q2 = fs.Pb + pidx(kfirst + 1);
+        const int nrows = (tb.kmax - tb.kmin + 32) >> 5;          // <= 31 (bins 1..1023, 32 per row)
+        const int rmax = (tb.kmax - kfirst) >> 5;                 // this lane's last row inside the range (-1: none)
+        const unsigned lt = (1u << lane) - 1u;
+        unsigned cnt = static_cast<unsigned>(wcount);
 #pragma unroll 4
-            for (int r = 0; r < nrows; ++r, q += kPRow) {
-                const float pm = q[0], pc = q[d0], pp = q[d1];
-                const bool pk = (32 * r <= rlast) && pc > ref && pc > pm && pc >= pp;
-                flags |= (pk ? 1u : 0u) << r;
+        for (int r = 0; r < nrows; ++r) {
+            const int off = kPRow * r;
+            const float pm = q0[off], pc = q1[off], pp = q2[off];
+            const bool pk = (r <= rmax) & (pc > ref) & (pc > pm) & (pc >= pp);
+            const unsigned bal = __ballot_sync(0xffffffffu, pk);
+            st_record_if(pk, fo.gSeg, cnt + __popc(bal & lt), pm, pc, pp, kfirst + 32 * r);
+            cnt += __popc(bal);
+        }
+        wcount = static_cast<int>(cnt);
+    } else {
+        {
+            const float ref = __fmul_rn(0.1f, pmax);
+            const int kfirst = tb.kmin + lane;
+            const float* q0 = fs.Pb + pidx(kfirst - 1);
+            const int d0 = pidx(kfirst) - pidx(kfirst - 1), d1 = pidx(kfirst + 1) - pidx(kfirst - 1);
+            const int nrows = (tb.kmax - tb.kmin + 32) >> 5;          // <= 16 (bins 1..1023, 32 per row)
+            unsigned flags = 0;                                      // bit r: this lane's bin of row r is a peak
+            {
+                const float* q = q0;
+                const int rlast = tb.kmax - kfirst;                  // rows with 32*r <= rlast hold a bin of the range
+#pragma unroll 4
+                for (int r = 0; r < nrows; ++r, q += kPRow) {
+                    const float pm = q[0], pc = q[d0], pp = q[d1];
+                    const bool pk = (32 * r <= rlast) && pc > ref && pc > pm && pc >= pp;
+                    flags |= (pk ? 1u : 0u) << r;
+                }
             }
-        }
-        // lane-wise compaction: exclusive prefix of the per-lane peak counts, one atomic per frame
-        const int mine = __popc(flags);
-        int inc = mine;
+            // lane-wise compaction: exclusive prefix of the per-lane peak counts, one atomic per frame
+            const int mine = __popc(flags);
+            int inc = mine;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, inc, 31);
-        if (total) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(fo.npk, total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            float4* dst = fo.gRec + base + (inc - mine);
-            while (flags) {
-                const int r = __ffs(flags) - 1;
-                flags &= flags - 1;
-                const float* q = q0 + kPRow * r;
-                *dst++ = make_float4(q[0], q[d0], q[d1], __int_as_float(kfirst + 32 * r));
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, inc, 31);
+            if (total) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(fo.npk, total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                float4* dst = fo.gRec + base + (inc - mine);
+                while (flags) {
+                    const int r = __ffs(flags) - 1;
+                    flags &= flags - 1;
+                    const float* q = q0 + kPRow * r;
+                    *dst++ = make_float4(q[0], q[d0], q[d1], __int_as_float(kfirst + 32 * r));
+                }
             }
         }
     }
@@ -423,14 +449,17 @@ static __device__ __noinline__ int peak_bin_exact(float pitch, const double* s_e
 }
 
 // ------------------------------------------------------------------------------------------------ phases 2-3
-// Expects (set up by the caller, followed by __syncthreads): cs.s_i[1] = number of peak records, cs.s_i[17] = 0, cs.s_f[w] = per-warp log-mel
+// Expects (set up by the caller, followed by __syncthreads): cs.s_i[20 + w] = peak records in segment w, cs.s_i[17] = 0, cs.s_f[w] = per-warp log-mel
 // max, cs.s_wacc[w*16 + 0/1] = per-warp centroid / roll-off sums, cs.s_i[8+w] = per-warp weighted zero-crossing counts.
 template <bool kDebug>
 __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, const ClipSmem& cs, const ClipSlice& sl,
                                           const int clip, const int T, float* __restrict__ out, unsigned& bank_parity,
                                           const int tid, const int lane, const int warp) {
     // ===================================== phase 2: tuning =====================================
-    const int np = cs.s_i[1];
+    // peak records: segment w of the slice holds cs.s_i[20 + w] records (the split pipeline uses segment 0 only)
+    int np = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) np += cs.s_i[20 + w];
     float gmx = cs.s_f[0];
 #pragma unroll
     for (int w = 1; w < kWarps; ++w) gmx = fmaxf(gmx, cs.s_f[w]);
@@ -459,19 +488,26 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         auto peaks = [&](auto SM) {
             constexpr bool kSmem = decltype(SM)::value;
             const float4 kDummy = make_float4(0.f, 1.f, 1.f, __int_as_float(64));      // harmless stand-in past the end
+            // dense peak index -> record: a thread's indices only grow, so it walks the segment boundaries once
+            int seg_w = 0, seg_end = cs.s_i[20], seg_adj = 0;          // record of index i sits at gRec[i + seg_adj]
+            auto fetch = [&](int i) -> float4 {
+                if (i >= np) return kDummy;
+                while (i >= seg_end) {
+                    ++seg_w;
+                    seg_adj += sl.seg_cap - cs.s_i[20 + seg_w - 1];
+                    seg_end += cs.s_i[20 + seg_w];
+                }
+                return sl.gRec[i + seg_adj];
+            };
             float4 nxt[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = tid + u * kThreads;
-                nxt[u] = (i < np) ? sl.gRec[i] : kDummy;
-            }
+            for (int u = 0; u < 4; ++u) nxt[u] = fetch(tid + u * kThreads);
             for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
                 float4 recs[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     recs[u] = nxt[u];
-                    const int i = i0 + (4 + u) * kThreads;                                // next step's records
-                    nxt[u] = (i < np) ? sl.gRec[i] : kDummy;
+                    nxt[u] = fetch(i0 + (4 + u) * kThreads);                              // next step's records
                 }
                 float shift[4];
                 bool redo = false;
@@ -553,8 +589,14 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             // every peak again with the reference forms only; keys / bins must be identical
             __syncthreads();
             int diff = 0;
+            int seg_w = 0, seg_end = cs.s_i[20], seg_adj = 0;
             for (int i = tid; i < np; i += kThreads) {
-                const float4 rc = sl.gRec[i];
+                while (i >= seg_end) {
+                    ++seg_w;
+                    seg_adj += sl.seg_cap - cs.s_i[20 + seg_w - 1];
+                    seg_end += cs.s_i[20 + seg_w];
+                }
+                const float4 rc = sl.gRec[i + seg_adj];
                 const float sh = peak_shift_exact(rc.x, rc.y, rc.z);
                 const float avg = __fsub_rn(rc.z, rc.x) * 0.5f;
                 const unsigned key = fkey(__fadd_rn(rc.y, __fmul_rn(__fmul_rn(0.5f, avg), sh)));

@@ -143,10 +143,10 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_frames_kernel(const SplitPara
         const Slice sl = slice_of(p.ws + kSplitHeader + static_cast<size_t>(c) * p.cta_scratch_bytes, p.Tmax, p.max_pk);
         FrameOut fo;
         fo.gP16 = sl.gP16; fo.gL = sl.gL; fo.gRec = sl.gRec; fo.gE = sl.gE; fo.gNy = sl.gNy; fo.gInvS = sl.gInvS;
-        fo.npk = npk_all + c; fo.s_wacc = nullptr; fo.s_f = nullptr;
+        fo.npk = npk_all + c; fo.gSeg = nullptr; fo.s_wacc = nullptr; fo.s_f = nullptr;
         fo.gCent = sl.gCent; fo.gRoll = sl.gRoll; fo.gLmax = sl.gLmax; fo.gZc = sl.gZc;
-        int unused_zc = 0;
-        process_frame<kDebug, true>(p, tb, fs, fo, x, n, T, t, clip, lane, warp, unused_zc);
+        int unused_zc = 0, unused_cnt = 0;
+        process_frame<kDebug, true>(p, tb, fs, fo, x, n, T, t, clip, lane, warp, unused_zc, unused_cnt);
     }
 }
 
@@ -208,11 +208,12 @@ __global__ void __launch_bounds__(kThreads, 3) sfx_clips_kernel(const SplitParam
             sz = warp_sum_i(sz);
             lm = warp_max(lm);
             if (lane == 0) { s_wacc[warp * 16 + 0] = sc; s_wacc[warp * 16 + 1] = sr; s_i[8 + warp] = sz; s_f[warp] = lm; }
-            if (tid == 0) { s_i[1] = npk_all[c]; s_i[17] = 0; }
+            if (tid < kWarps) s_i[20 + tid] = tid == 0 ? npk_all[c] : 0;     // all records in segment 0
+            if (tid == 0) s_i[17] = 0;
         }
         __syncthreads();
 
-        const ClipSlice cl{sl.gP16, sl.gL, sl.gRec, sl.gKey, sl.gE, sl.gNy, sl.gInvS, sl.gBin};
+        const ClipSlice cl{sl.gP16, sl.gL, sl.gRec, sl.gKey, sl.gE, sl.gNy, sl.gInvS, sl.gBin, 0};
         clip_tail<kDebug>(p, tb, cs, cl, clip, T, out, bank_parity, tid, lane, warp);
     }
 }
