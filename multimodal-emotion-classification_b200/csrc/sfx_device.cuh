@@ -229,17 +229,26 @@ __device__ __forceinline__ int pidx(int k) { return k + 4 * (k >> 5); }   // pad
 // ------------------------------------------------------------------------------------------------
 // CTA-wide radix select over the clip's peak magnitudes: key of the element of ascending rank r.
 // count_le = number of elements <= that key.  All threads must call; uses s_hist[256], s_sel[4].
-static __device__ unsigned radix_select(const unsigned* keys, int np, int r, int* s_hist, int* s_sel, int& count_le) {
+// kor / kand = OR / AND of all keys: only the bits in which the keys differ are examined, 8 per pass from the top, so
+// the first pass already spreads over up to 256 bins (keys are order-preserving float bits and a clip's peak
+// magnitudes share their leading exponent bits) instead of piling shared-memory atomics onto a handful of bins.
+static __device__ unsigned radix_select(const unsigned* keys, int np, int r, int* s_hist, int* s_sel, int& count_le,
+                                        unsigned kor, unsigned kand) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned prefix = 0, mask = 0;
-    int less = 0, equal = 0;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
+    const unsigned diff = kor ^ kand;
+    int remaining = 32 - __clz(diff);                       // differing bits are [0, remaining)
+    unsigned mask = remaining >= 32 ? 0u : ~((1u << remaining) - 1u);
+    unsigned prefix = kand & mask;
+    int less = 0, equal = np;
+    while (remaining > 0) {
+        const int width = min(8, remaining);
+        const int shift = remaining - width;
+        const unsigned bmask = (1u << width) - 1u;
         for (int i = tid; i < 256; i += kThreads) s_hist[i] = 0;
         __syncthreads();
         for (int i = tid; i < np; i += kThreads) {
             const unsigned key = keys[i];
-            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255], 1);
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & bmask], 1);
         }
         __syncthreads();
         if (warp == 0) {
@@ -278,7 +287,8 @@ static __device__ unsigned radix_select(const unsigned* keys, int np, int r, int
         less += s_sel[2];
         equal = s_sel[3];
         prefix |= static_cast<unsigned>(bucket) << shift;
-        mask |= 0xFFu << shift;
+        mask |= bmask << shift;
+        remaining = shift;
         __syncthreads();
     }
     count_le = less + equal;

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_i[0] = atomicAdd(counter, 1); s_i[17] = 0; }
+        if (tid == 0) { s_i[0] = atomicAdd(counter, 1); s_i[17] = 0; s_i[18] = 0; s_i[19] = -1; }
         __syncthreads();
         const int clip = s_i[0];
         if (clip >= p.B) break;

@@ -449,7 +449,7 @@ static __device__ __noinline__ int peak_bin_exact(float pitch, const double* s_e
 }
 
 // ------------------------------------------------------------------------------------------------ phases 2-3
-// Expects (set up by the caller, followed by __syncthreads): cs.s_i[20 + w] = peak records in segment w, cs.s_i[17] = 0, cs.s_f[w] = per-warp log-mel
+// Expects (set up by the caller, followed by __syncthreads): cs.s_i[20 + w] = peak records in segment w, cs.s_i[17] = cs.s_i[18] = 0, cs.s_i[19] = ~0, cs.s_f[w] = per-warp log-mel
 // max, cs.s_wacc[w*16 + 0/1] = per-warp centroid / roll-off sums, cs.s_i[8+w] = per-warp weighted zero-crossing counts.
 template <bool kDebug>
 __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, const ClipSmem& cs, const ClipSlice& sl,
@@ -499,6 +499,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
                 }
                 return sl.gRec[i + seg_adj];
             };
+            unsigned kor = 0u, kand = 0xffffffffu;
             float4 nxt[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) nxt[u] = fetch(tid + u * kThreads);
@@ -565,6 +566,8 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
                         else bin = peak_bin_exact(pitch, cs.s_edges);
                     }
                     if (i < np) {
+                        kor |= key;
+                        kand &= key;
                         if constexpr (kSmem) {
                             reinterpret_cast<unsigned*>(cs.s_ex)[i] = key;
                             reinterpret_cast<unsigned char*>(cs.s_ex + kKeyCap)[i] = static_cast<unsigned char>(bin);
@@ -574,6 +577,12 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
                         }
                     }
                 }
+            }
+            kor = __reduce_or_sync(0xffffffffu, kor);
+            kand = __reduce_and_sync(0xffffffffu, kand);
+            if (lane == 0) {
+                atomicOr(reinterpret_cast<unsigned*>(&cs.s_i[18]), kor);
+                atomicAnd(reinterpret_cast<unsigned*>(&cs.s_i[19]), kand);
             }
         };
         if (in_smem) peaks(std::true_type{}); else peaks(std::false_type{});
@@ -610,7 +619,8 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         __syncthreads();
         int cle = 0;
         const int r0 = (np - 1) >> 1;
-        const unsigned ka = radix_select(keys, np, r0, cs.s_hist, cs.s_i + 4, cle);
+        const unsigned ka = radix_select(keys, np, r0, cs.s_hist, cs.s_i + 4, cle, static_cast<unsigned>(cs.s_i[18]),
+                                         static_cast<unsigned>(cs.s_i[19]));
         unsigned kb = ka;
         if ((np & 1) == 0 && cle <= (np >> 1)) {
             // upper median = smallest key above ka
@@ -726,7 +736,10 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
                 const __half* whi1 = sW + r1 * kP16Stride + kh * 512 + 8 * t4;
                 const __half* wlo0 = whi0 + kChroma * kP16Stride;
                 const __half* wlo1 = whi1 + kChroma * kP16Stride;
+                // two accumulator sets per bank half (even / odd steps) so that four MMA chains are in flight; lanes
+                // g >= 4 feed bank row g again as the non-existent rows 12..15, whose D rows are never read
                 float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f};
+                float acc2[4] = {0.f, 0.f, 0.f, 0.f}, acl2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
                 for (int kb0 = 0; kb0 < 16; kb0 += 8) {
                     uint4 pv[8];
@@ -737,16 +750,17 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
                     for (int i = 0; i < 8; ++i) {
                         const int o = (kb0 + i) * 32;
                         const uint4 h0 = *reinterpret_cast<const uint4*>(whi0 + o);
-                        uint4 h1 = *reinterpret_cast<const uint4*>(whi1 + o);
+                        const uint4 h1 = *reinterpret_cast<const uint4*>(whi1 + o);
                         const uint4 l0 = *reinterpret_cast<const uint4*>(wlo0 + o);
-                        uint4 l1 = *reinterpret_cast<const uint4*>(wlo1 + o);
-                        if (g >= 4) { h1 = make_uint4(0u, 0u, 0u, 0u); l1 = h1; }
+                        const uint4 l1 = *reinterpret_cast<const uint4*>(wlo1 + o);
                         mma_f16(acc, h0.x, h1.x, h0.y, h1.y, pv[i].x, pv[i].y);
-                        mma_f16(acc, h0.z, h1.z, h0.w, h1.w, pv[i].z, pv[i].w);
+                        mma_f16(acc2, h0.z, h1.z, h0.w, h1.w, pv[i].z, pv[i].w);
                         mma_f16(acl, l0.x, l1.x, l0.y, l1.y, pv[i].x, pv[i].y);
-                        mma_f16(acl, l0.z, l1.z, l0.w, l1.w, pv[i].z, pv[i].w);
+                        mma_f16(acl2, l0.z, l1.z, l0.w, l1.w, pv[i].z, pv[i].w);
                     }
                 }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { acc[q] += acc2[q]; acl[q] += acl2[q]; }
                 // D fragment: [0..1] = (chroma g, frames 2*t4, 2*t4+1), [2..3] = (chroma g+8, same frames)
                 constexpr float kLo = 1.0f / 2048.0f;
                 float* dst = part2 + (tl * 2 + kh) * 96;
