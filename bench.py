@@ -321,6 +321,29 @@ def main():
     e2e_value = Be * world * e2e_steps / e2e_s
     e2e_match = bool(torch.equal(h_out, out[:Be].cpu()))
 
+    # the same clips as 16-bit PCM (what a WAV file at 22.05 kHz holds): half the bytes over PCIe, dequantised on the
+    # device exactly as soundfile does for librosa.load; reported beside `e2e`, not instead of it
+    h_pcm = torch.empty((Be, N_SAMPLES), dtype=torch.int16).pin_memory()
+    h_pcm.copy_((pool[:Be] * 32768.0).round().clamp(-32768, 32767).to(torch.int16))
+    h_out16 = torch.empty((Be, 56), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        ex.extract_host(h_pcm.numpy(), out=h_out16.numpy())
+    barrier()
+    launches1 = ex.launches
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ex.extract_host(h_pcm.numpy(), out=h_out16.numpy())
+    pcm_s = time.perf_counter() - t0
+    launches += ex.launches - launches1
+    if world > 1:
+        tm = torch.tensor([pcm_s], device=device, dtype=torch.float64)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        pcm_s = tm.item()
+    e2e_pcm16 = {"value": Be * world * e2e_steps / pcm_s, "unit": "clips/s", "h2d_bytes_per_step": Be * N_SAMPLES * 2,
+                 "d2h_bytes_per_step": Be * 56 * 4, "clips_per_gpu_per_step": Be, "steps": e2e_steps,
+                 "path": "sfx_extract_host_pcm16: pinned int16 PCM rows -> H2D || device x/32768 + kernel || D2H",
+                 "finite": bool(torch.isfinite(h_out16).all())}
+
     # ---------------- small-batch behaviour (rank 0): single-clip latency through the host path (what one request of the
     # reference's Flask app costs), and device-resident throughput at the batch sizes of configs[0] / configs[1]
     small = None
@@ -380,6 +403,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": Be * N_SAMPLES * 4,
                     "d2h_bytes_per_step": Be * 56 * 4, "clips_per_gpu_per_step": Be, "steps": e2e_steps,
                     "path": "sfx_extract_host: pinned host rows -> chunked H2D || kernel || D2H on 2 streams"},
+            "e2e_pcm16": e2e_pcm16,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic * B) if traffic else None,

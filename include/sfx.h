@@ -6,6 +6,7 @@
  * batched device pass, the four calls the reference makes per clip:
  *
  *   sfx_extract / sfx_extract_host  <->  extract_mfcc             (audio_preprocessing.py:22-24)
+ *   / sfx_extract_host_pcm16
  *                                        extract_chroma           (audio_preprocessing.py:27-29)
  *                                        extract_spectral_features(audio_preprocessing.py:32-37)
  *                                        np.concatenate -> f32[56] (audio_preprocessing.py:45-46)
@@ -128,6 +129,13 @@ int         sfx_extract_debug(int device, int32_t sr, const float *wave, int64_t
 int         sfx_extract_host(int device, int32_t sr, const float *host_wave, int64_t row_stride,
                              const int32_t *host_lengths, int64_t n_default, int32_t B, int32_t n_mfcc,
                              float *host_out, int64_t out_stride, int32_t chunk_clips);
+
+/* Same for 16-bit PCM rows as they sit in a WAV file: converted on the device exactly as libsndfile does for librosa.load
+ * (x / 32768, reference :13), then extracted.  Half the host-to-device bytes of sfx_extract_host; valid for audio that is
+ * already at the sample rate `sr` (librosa.load then does no resampling) and mono. */
+int         sfx_extract_host_pcm16(int device, int32_t sr, const int16_t *host_pcm, int64_t row_stride,
+                                   const int32_t *host_lengths, int64_t n_default, int32_t B, int32_t n_mfcc,
+                                   float *host_out, int64_t out_stride, int32_t chunk_clips);
 
 /* Release cached device buffers/tables of `device` (tests; process exit does it implicitly). */
 int         sfx_release(int device);

@@ -19,6 +19,7 @@ constexpr int kHostStreams = 2;
 struct HostPath {               // cached buffers of sfx_extract_host
     cudaStream_t stream[kHostStreams] = {nullptr, nullptr};
     float* d_wave[kHostStreams] = {nullptr, nullptr};
+    int16_t* d_pcm[kHostStreams] = {nullptr, nullptr};   // raw PCM16 rows of sfx_extract_host_pcm16
     int* d_len[kHostStreams] = {nullptr, nullptr};
     float* d_out[kHostStreams] = {nullptr, nullptr};
     void* d_ws[kHostStreams] = {nullptr, nullptr};
@@ -98,6 +99,7 @@ int upload(DevCtx& c, const T* host, size_t count, const T** dev) {
 void free_host_path(HostPath& hp) {
     for (int s = 0; s < kHostStreams; ++s) {
         if (hp.d_wave[s]) cudaFree(hp.d_wave[s]);
+        if (hp.d_pcm[s]) cudaFree(hp.d_pcm[s]);
         if (hp.d_len[s]) cudaFree(hp.d_len[s]);
         if (hp.d_out[s]) cudaFree(hp.d_out[s]);
         if (hp.d_ws[s]) cudaFree(hp.d_ws[s]);
@@ -113,6 +115,16 @@ bool is_pinned(const void* p) {
     cudaPointerAttributes a{};
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
+}
+
+// PCM16 -> float32 exactly as libsndfile / soundfile do it for librosa.load: x / 32768 (two samples per thread)
+__global__ void pcm16_to_f32_kernel(const int16_t* __restrict__ src, float* __restrict__ dst, long long pairs) {
+    const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < pairs; i += step) {
+        const short2 v = reinterpret_cast<const short2*>(src)[i];
+        reinterpret_cast<float2*>(dst)[i] = make_float2(static_cast<float>(v.x) * (1.0f / 32768.0f),
+                                                        static_cast<float>(v.y) * (1.0f / 32768.0f));
+    }
 }
 
 int do_extract(int device, int sr, const float* wave, int64_t row_stride, const int32_t* lengths, int64_t n_default,
@@ -173,6 +185,120 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
 }
 
 }  // namespace
+
+template <class S>
+int extract_host_impl(int device, int32_t sr, const S* host_wave, int64_t row_stride, const int32_t* host_lengths,
+                      int64_t n_default, int32_t B, int32_t n_mfcc, float* host_out, int64_t out_stride,
+                      int32_t chunk_clips) {
+    constexpr bool kPcm = sizeof(S) == 2;
+    if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
+    if (B < 0 || n_mfcc < 1 || n_mfcc > sfx::kMels) return fail(SFX_ERR_ARG, "B < 0 or n_mfcc outside [1,128]");
+    if (B == 0) return SFX_OK;
+    if (!host_wave || !host_out) return fail(SFX_ERR_ARG, "null host pointer");
+    if (row_stride < 1 || out_stride < n_mfcc + 16) return fail(SFX_ERR_ARG, "bad row_stride/out_stride");
+    if (!host_lengths && (n_default < 1 || n_default > row_stride)) return fail(SFX_ERR_ARG, "n_default outside [1,row_stride]");
+    DevCtx& c = g_ctx[device];
+    if (!c.ready || !find_set(c, sr)) return fail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this (device, sample rate)");
+    CK(cudaSetDevice(device));
+    int64_t max_samples = n_default;
+    if (host_lengths) {
+        max_samples = 1;
+        for (int i = 0; i < B; ++i) {
+            if (host_lengths[i] <= 0 || host_lengths[i] > row_stride) return fail(SFX_ERR_BAD_CLIP, "clip length outside [1,row_stride]");
+            max_samples = std::max<int64_t>(max_samples, host_lengths[i]);
+        }
+    }
+    // rows are copied up to max_samples only (rounded to even for 8-byte alignment of every device row)
+    const int64_t dev_stride = (max_samples + 1) & ~int64_t(1);
+    int chunk = chunk_clips > 0 ? chunk_clips : static_cast<int>(std::max<int64_t>(64, (256ll << 20) / (dev_stride * 4)));
+    chunk = std::min(chunk, B);
+    const int out_w = n_mfcc + 16;
+    const size_t need_wave = static_cast<size_t>(chunk) * dev_stride;
+    const size_t need_ws = sfx_workspace_bytes(device, max_samples);
+    const size_t need_out = static_cast<size_t>(chunk) * out_w;
+    std::lock_guard<std::mutex> lk(g_mu);
+    HostPath& hp = c.hp;
+    const bool in_pinned = is_pinned(host_wave), out_pinned = is_pinned(host_out);
+    if (hp.wave_elems < need_wave || hp.ws_bytes < need_ws || hp.out_elems < need_out || hp.chunk < chunk ||
+        (!in_pinned && !hp.h_stage[0]) || (!out_pinned && !hp.h_out[0]) || (kPcm && !hp.d_pcm[0])) {
+        free_host_path(hp);
+        for (int s = 0; s < kHostStreams; ++s) {
+            CK(cudaStreamCreateWithFlags(&hp.stream[s], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&hp.ev_done[s], cudaEventDisableTiming));
+            CK(cudaMalloc(&hp.d_wave[s], need_wave * 4));
+            if (kPcm) CK(cudaMalloc(&hp.d_pcm[s], need_wave * 2));
+            CK(cudaMalloc(&hp.d_len[s], static_cast<size_t>(chunk) * 4));
+            CK(cudaMalloc(&hp.d_out[s], need_out * 4));
+            CK(cudaMalloc(&hp.d_ws[s], need_ws));
+            if (!in_pinned) CK(cudaMallocHost(&hp.h_stage[s], need_wave * 4));
+            if (!out_pinned) CK(cudaMallocHost(&hp.h_out[s], need_out * 4));
+        }
+        hp.wave_elems = need_wave; hp.ws_bytes = need_ws; hp.out_elems = need_out; hp.chunk = chunk;
+    }
+    int nchunks = (B + chunk - 1) / chunk;
+    int launches_total = 0;
+    std::vector<int> pend_c0(kHostStreams, -1), pend_nb(kHostStreams, 0);
+    auto drain = [&](int s) -> int {      // copy a finished chunk's rows out of pinned staging
+        if (pend_c0[s] < 0) return SFX_OK;
+        CK(cudaEventSynchronize(hp.ev_done[s]));
+        if (!out_pinned) {
+            for (int i = 0; i < pend_nb[s]; ++i)
+                std::memcpy(host_out + static_cast<int64_t>(pend_c0[s] + i) * out_stride, hp.h_out[s] + static_cast<size_t>(i) * out_w,
+                            sizeof(float) * out_w);
+        }
+        pend_c0[s] = -1;
+        return SFX_OK;
+    };
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int s = ci % kHostStreams;
+        const int c0 = ci * chunk, nb = std::min(chunk, B - c0);
+        int rc = drain(s);
+        if (rc) return rc;
+        cudaStream_t st = hp.stream[s];
+        const S* src = host_wave + static_cast<int64_t>(c0) * row_stride;
+        const size_t row_bytes = static_cast<size_t>(max_samples) * sizeof(S);
+        void* d_in = kPcm ? static_cast<void*>(hp.d_pcm[s]) : static_cast<void*>(hp.d_wave[s]);
+        if (in_pinned) {
+            CK(cudaMemcpy2DAsync(d_in, dev_stride * sizeof(S), src, row_stride * sizeof(S), row_bytes, nb, cudaMemcpyHostToDevice, st));
+        } else {
+            S* stage = reinterpret_cast<S*>(hp.h_stage[s]);
+            for (int i = 0; i < nb; ++i)
+                std::memcpy(stage + static_cast<size_t>(i) * dev_stride, src + static_cast<int64_t>(i) * row_stride, row_bytes);
+            CK(cudaMemcpyAsync(d_in, stage, static_cast<size_t>(nb) * dev_stride * sizeof(S), cudaMemcpyHostToDevice, st));
+        }
+        if (kPcm) {
+            const long long pairs = static_cast<long long>(nb) * dev_stride / 2;
+            const int grid = static_cast<int>(std::min<long long>((pairs + 255) / 256, 148ll * 16));
+            pcm16_to_f32_kernel<<<grid, 256, 0, st>>>(hp.d_pcm[s], hp.d_wave[s], pairs);
+            CK(cudaGetLastError());
+            ++launches_total;
+        }
+        const int32_t* dlen = nullptr;
+        if (host_lengths) {
+            CK(cudaMemcpyAsync(hp.d_len[s], host_lengths + c0, static_cast<size_t>(nb) * 4, cudaMemcpyHostToDevice, st));
+            dlen = hp.d_len[s];
+        }
+        rc = do_extract(device, sr, hp.d_wave[s], dev_stride, dlen, n_default, max_samples, nb, n_mfcc, hp.d_out[s], out_w,
+                        hp.d_ws[s], hp.ws_bytes, st, nullptr);
+        if (rc) return rc;
+        launches_total += g_last_launches;
+        if (out_pinned) {
+            CK(cudaMemcpy2DAsync(host_out + static_cast<int64_t>(c0) * out_stride, out_stride * 4, hp.d_out[s], out_w * 4,
+                                 static_cast<size_t>(out_w) * 4, nb, cudaMemcpyDeviceToHost, st));
+        } else {
+            CK(cudaMemcpyAsync(hp.h_out[s], hp.d_out[s], static_cast<size_t>(nb) * out_w * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaEventRecord(hp.ev_done[s], st));
+        pend_c0[s] = c0; pend_nb[s] = nb;
+    }
+    for (int s = 0; s < kHostStreams; ++s) {
+        int rc = drain(s);
+        if (rc) return rc;
+    }
+    g_last_launches = launches_total;
+    return SFX_OK;
+}
+
 
 extern "C" {
 
@@ -292,102 +418,15 @@ int sfx_extract_debug(int device, int32_t sr, const float* wave, int64_t row_str
 int sfx_extract_host(int device, int32_t sr, const float* host_wave, int64_t row_stride, const int32_t* host_lengths,
                      int64_t n_default, int32_t B, int32_t n_mfcc, float* host_out, int64_t out_stride,
                      int32_t chunk_clips) {
-    if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
-    if (B < 0 || n_mfcc < 1 || n_mfcc > sfx::kMels) return fail(SFX_ERR_ARG, "B < 0 or n_mfcc outside [1,128]");
-    if (B == 0) return SFX_OK;
-    if (!host_wave || !host_out) return fail(SFX_ERR_ARG, "null host pointer");
-    if (row_stride < 1 || out_stride < n_mfcc + 16) return fail(SFX_ERR_ARG, "bad row_stride/out_stride");
-    if (!host_lengths && (n_default < 1 || n_default > row_stride)) return fail(SFX_ERR_ARG, "n_default outside [1,row_stride]");
-    DevCtx& c = g_ctx[device];
-    if (!c.ready || !find_set(c, sr)) return fail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this (device, sample rate)");
-    CK(cudaSetDevice(device));
-    int64_t max_samples = n_default;
-    if (host_lengths) {
-        max_samples = 1;
-        for (int i = 0; i < B; ++i) {
-            if (host_lengths[i] <= 0 || host_lengths[i] > row_stride) return fail(SFX_ERR_BAD_CLIP, "clip length outside [1,row_stride]");
-            max_samples = std::max<int64_t>(max_samples, host_lengths[i]);
-        }
-    }
-    // rows are copied up to max_samples only (rounded to even for 8-byte alignment of every device row)
-    const int64_t dev_stride = (max_samples + 1) & ~int64_t(1);
-    int chunk = chunk_clips > 0 ? chunk_clips : static_cast<int>(std::max<int64_t>(64, (256ll << 20) / (dev_stride * 4)));
-    chunk = std::min(chunk, B);
-    const int out_w = n_mfcc + 16;
-    const size_t need_wave = static_cast<size_t>(chunk) * dev_stride;
-    const size_t need_ws = sfx_workspace_bytes(device, max_samples);
-    const size_t need_out = static_cast<size_t>(chunk) * out_w;
-    std::lock_guard<std::mutex> lk(g_mu);
-    HostPath& hp = c.hp;
-    const bool in_pinned = is_pinned(host_wave), out_pinned = is_pinned(host_out);
-    if (hp.wave_elems < need_wave || hp.ws_bytes < need_ws || hp.out_elems < need_out || hp.chunk < chunk ||
-        (!in_pinned && !hp.h_stage[0]) || (!out_pinned && !hp.h_out[0])) {
-        free_host_path(hp);
-        for (int s = 0; s < kHostStreams; ++s) {
-            CK(cudaStreamCreateWithFlags(&hp.stream[s], cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&hp.ev_done[s], cudaEventDisableTiming));
-            CK(cudaMalloc(&hp.d_wave[s], need_wave * 4));
-            CK(cudaMalloc(&hp.d_len[s], static_cast<size_t>(chunk) * 4));
-            CK(cudaMalloc(&hp.d_out[s], need_out * 4));
-            CK(cudaMalloc(&hp.d_ws[s], need_ws));
-            if (!in_pinned) CK(cudaMallocHost(&hp.h_stage[s], need_wave * 4));
-            if (!out_pinned) CK(cudaMallocHost(&hp.h_out[s], need_out * 4));
-        }
-        hp.wave_elems = need_wave; hp.ws_bytes = need_ws; hp.out_elems = need_out; hp.chunk = chunk;
-    }
-    int nchunks = (B + chunk - 1) / chunk;
-    int launches_total = 0;
-    std::vector<int> pend_c0(kHostStreams, -1), pend_nb(kHostStreams, 0);
-    auto drain = [&](int s) -> int {      // copy a finished chunk's rows out of pinned staging
-        if (pend_c0[s] < 0) return SFX_OK;
-        CK(cudaEventSynchronize(hp.ev_done[s]));
-        if (!out_pinned) {
-            for (int i = 0; i < pend_nb[s]; ++i)
-                std::memcpy(host_out + static_cast<int64_t>(pend_c0[s] + i) * out_stride, hp.h_out[s] + static_cast<size_t>(i) * out_w,
-                            sizeof(float) * out_w);
-        }
-        pend_c0[s] = -1;
-        return SFX_OK;
-    };
-    for (int ci = 0; ci < nchunks; ++ci) {
-        const int s = ci % kHostStreams;
-        const int c0 = ci * chunk, nb = std::min(chunk, B - c0);
-        int rc = drain(s);
-        if (rc) return rc;
-        cudaStream_t st = hp.stream[s];
-        const float* src = host_wave + static_cast<int64_t>(c0) * row_stride;
-        const size_t row_bytes = static_cast<size_t>(max_samples) * 4;
-        if (in_pinned) {
-            CK(cudaMemcpy2DAsync(hp.d_wave[s], dev_stride * 4, src, row_stride * 4, row_bytes, nb, cudaMemcpyHostToDevice, st));
-        } else {
-            for (int i = 0; i < nb; ++i)
-                std::memcpy(hp.h_stage[s] + static_cast<size_t>(i) * dev_stride, src + static_cast<int64_t>(i) * row_stride, row_bytes);
-            CK(cudaMemcpyAsync(hp.d_wave[s], hp.h_stage[s], static_cast<size_t>(nb) * dev_stride * 4, cudaMemcpyHostToDevice, st));
-        }
-        const int32_t* dlen = nullptr;
-        if (host_lengths) {
-            CK(cudaMemcpyAsync(hp.d_len[s], host_lengths + c0, static_cast<size_t>(nb) * 4, cudaMemcpyHostToDevice, st));
-            dlen = hp.d_len[s];
-        }
-        rc = do_extract(device, sr, hp.d_wave[s], dev_stride, dlen, n_default, max_samples, nb, n_mfcc, hp.d_out[s], out_w,
-                        hp.d_ws[s], hp.ws_bytes, st, nullptr);
-        if (rc) return rc;
-        launches_total += g_last_launches;
-        if (out_pinned) {
-            CK(cudaMemcpy2DAsync(host_out + static_cast<int64_t>(c0) * out_stride, out_stride * 4, hp.d_out[s], out_w * 4,
-                                 static_cast<size_t>(out_w) * 4, nb, cudaMemcpyDeviceToHost, st));
-        } else {
-            CK(cudaMemcpyAsync(hp.h_out[s], hp.d_out[s], static_cast<size_t>(nb) * out_w * 4, cudaMemcpyDeviceToHost, st));
-        }
-        CK(cudaEventRecord(hp.ev_done[s], st));
-        pend_c0[s] = c0; pend_nb[s] = nb;
-    }
-    for (int s = 0; s < kHostStreams; ++s) {
-        int rc = drain(s);
-        if (rc) return rc;
-    }
-    g_last_launches = launches_total;
-    return SFX_OK;
+    return extract_host_impl<float>(device, sr, host_wave, row_stride, host_lengths, n_default, B, n_mfcc, host_out, out_stride,
+                                    chunk_clips);
+}
+
+int sfx_extract_host_pcm16(int device, int32_t sr, const int16_t* host_pcm, int64_t row_stride, const int32_t* host_lengths,
+                           int64_t n_default, int32_t B, int32_t n_mfcc, float* host_out, int64_t out_stride,
+                           int32_t chunk_clips) {
+    return extract_host_impl<int16_t>(device, sr, host_pcm, row_stride, host_lengths, n_default, B, n_mfcc, host_out, out_stride,
+                                      chunk_clips);
 }
 
 }  // extern "C"

@@ -40,7 +40,8 @@ class DnnHost(C.Structure):
 
 EXPORTS = ["sfx_dnn_create", "sfx_dnn_destroy", "sfx_dnn_workspace_bytes", "sfx_dnn_launches_per_forward",
            "sfx_dnn_last_error", "sfx_dnn_forward", "sfx_abi_version", "sfx_last_error", "sfx_device_count", "sfx_init_tables", "sfx_workspace_bytes",
-           "sfx_launches_per_extract", "sfx_set_pipeline", "sfx_extract", "sfx_extract_debug", "sfx_extract_host", "sfx_release"]
+           "sfx_launches_per_extract", "sfx_set_pipeline", "sfx_extract", "sfx_extract_debug", "sfx_extract_host", "sfx_extract_host_pcm16",
+           "sfx_release"]
 
 
 def lib_path() -> str:
@@ -71,6 +72,9 @@ def load():
     lib.sfx_extract_debug.argtypes = common + [C.POINTER(DebugOut)]
     lib.sfx_extract_host.restype = C.c_int
     lib.sfx_extract_host.argtypes = [C.c_int, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_int64, C.c_int32]
+    lib.sfx_extract_host_pcm16.restype = C.c_int
+    lib.sfx_extract_host_pcm16.argtypes = [C.c_int, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_int64, C.c_int32]
     lib.sfx_release.restype = C.c_int
     lib.sfx_release.argtypes = [C.c_int]

@@ -111,11 +111,13 @@ class SpeechFeatureExtractor:
     def extract_host(self, waves: np.ndarray, lengths: np.ndarray | None = None, n_samples: int | None = None,
                      n_mfcc: int = 40, out: np.ndarray | None = None, chunk_clips: int = 0) -> np.ndarray:
         """waves: host float32 [B, L] (numpy, or anything exposing a C-contiguous-row buffer; pinned memory is
-        copied without staging); returns host float32 [B, n_mfcc+16].  H2D, kernel and D2H are chunk-pipelined
-        inside the C library; the call returns when the rows are in ``out``."""
+        copied without staging), or host int16 [B, L] = 16-bit PCM as stored in a WAV file at this extractor's sample
+        rate (converted on the device as soundfile does, x / 32768; half the bytes over PCIe); returns host float32
+        [B, n_mfcc+16].  H2D, kernel and D2H are chunk-pipelined inside the C library; the call returns when the rows
+        are in ``out``."""
         waves = np.asarray(waves)
-        if waves.dtype != np.float32 or waves.ndim != 2 or waves.strides[1] != 4:
-            raise ValueError("waves must be a 2-D float32 array with contiguous rows")
+        if waves.dtype not in (np.float32, np.int16) or waves.ndim != 2 or waves.strides[1] != waves.itemsize:
+            raise ValueError("waves must be a 2-D float32 (or int16 PCM) array with contiguous rows")
         B, L = waves.shape
         n_default = L if n_samples is None else int(n_samples)
         width = n_mfcc + N_CHROMA + N_SPECTRAL
@@ -131,9 +133,10 @@ class SpeechFeatureExtractor:
             lp = lengths.ctypes.data
         if B == 0:
             return out
+        fn = self.lib.sfx_extract_host if waves.dtype == np.float32 else self.lib.sfx_extract_host_pcm16
         with torch.cuda.device(self.index):
-            _lib.check(self.lib.sfx_extract_host(self.index, self.sr, waves.ctypes.data, waves.strides[0] // 4, lp, n_default,
-                                                 B, n_mfcc, out.ctypes.data, out.strides[0] // 4, int(chunk_clips)))
+            _lib.check(fn(self.index, self.sr, waves.ctypes.data, waves.strides[0] // waves.itemsize, lp, n_default,
+                          B, n_mfcc, out.ctypes.data, out.strides[0] // 4, int(chunk_clips)))
         self.launches += self.lib.sfx_launches_per_extract()      # summed over the call's chunks by the library
         return out
 

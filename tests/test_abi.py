@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def header_symbols():
     txt = open(os.path.join(ROOT, "include", "sfx.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(sfx_[a-z_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(sfx_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_library_builds_and_exports_header_symbols():

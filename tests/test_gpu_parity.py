@@ -162,6 +162,25 @@ def test_host_path_matches_device_path_and_chunks(ex):
     assert np.array_equal(ex.extract_host(wr, lens, chunk_clips=4), dr)
 
 
+def test_pcm16_host_path_is_the_float_path_on_dequantised_samples(ex):
+    """16-bit PCM rows (as in a WAV file at the extractor's rate) are dequantised on the device exactly as soundfile does
+    for librosa.load (x / 32768): the features equal, bit for bit, those of the float path fed the dequantised samples."""
+    w = synth.make_batch(21, N3S, seed=53)
+    pcm = np.clip(np.round(w * 32768.0), -32768, 32767).astype(np.int16)
+    deq = pcm.astype(np.float32) / np.float32(32768.0)
+    d = ex.extract(dev(deq)).cpu().numpy()
+    assert np.array_equal(ex.extract_host(pcm), d)
+    assert np.array_equal(ex.extract_host(pcm, chunk_clips=4), d)
+    pinned = torch.from_numpy(pcm).pin_memory()
+    assert np.array_equal(ex.extract_host(pinned.numpy(), chunk_clips=8), d)
+    wr, lens = synth.make_ragged(7, 11025, 90001, seed=54)          # odd maximum length: padded device rows
+    pr = np.clip(np.round(wr * 32768.0), -32768, 32767).astype(np.int16)
+    dr = ex.extract(dev(pr.astype(np.float32) / np.float32(32768.0)), dev(lens)).cpu().numpy()
+    assert np.array_equal(ex.extract_host(pr, lens, chunk_clips=3), dr)
+    ok, report = synth.compare(d, lp.features_batch(deq))
+    assert ok, "\n" + report
+
+
 def test_dropin_module_functions(ex):
     """The reference's tests/test_preprocessing.py:30-67 against the drop-in module, plus values vs the oracle."""
     from config import Config
