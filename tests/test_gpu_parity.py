@@ -325,6 +325,17 @@ def test_fast_peak_arithmetic_equals_reference_forms(ex):
     finally:
         ex.lib.sfx_set_pipeline(0)
     assert total > 500_000          # the check saw a meaningful number of peaks
+    # a 60 s noise clip: ~250 k peaks overflow the shared-memory key array and the queue of edge cases, so the global
+    # key / bin arrays and the inline reference-form path are exercised as well
+    rng = np.random.default_rng(5)
+    wl = np.zeros((3, 1_323_000), dtype=np.float32)
+    lens = np.array([1_323_000, 400_000, 66_150], dtype=np.int32)
+    for i, n in enumerate(lens):
+        wl[i, :n] = 0.1 * rng.standard_normal(n).astype(np.float32)
+    dbg = {}
+    ex.extract(dev(wl), dev(lens), debug=dbg)
+    ci = dbg["clip_info"].cpu().numpy()
+    assert ci[0, 2] > 100_000 and (ci[:, 6] == 0).all(), ci[:, [2, 6]]
 
 
 def test_fused_and_split_pipelines_agree(ex):
