@@ -37,11 +37,16 @@ def partition_by_samples(lengths, world: int):
     return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
 
 
-def gather_feature_cache(local_feats: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+def gather_feature_cache(local_feats: torch.Tensor, n_total: int, group=None, out: torch.Tensor | None = None,
+                         async_op: bool = False):
     """All-gather equal-size shards of feature rows into the full [n_total, F] cache on every rank.
 
     `local_feats` holds this rank's rows of shard_range(n_total, world, rank); shorter trailing shards are
-    padded to shard_size rows for the collective and the padding is dropped afterwards."""
+    padded to shard_size rows for the collective and the padding is dropped afterwards.
+
+    `out` ([shard_size * world, F]) reuses a cache buffer.  With ``async_op=True`` the call returns ``(cache, work)`` at
+    once: the collective runs on the communication stream underneath the next batch's extraction, and
+    ``work.wait()`` orders the current stream after it (call it before `local_feats` or `out` are overwritten)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     per = shard_size(n_total, world)
@@ -53,9 +58,11 @@ def gather_feature_cache(local_feats: torch.Tensor, n_total: int, group=None) ->
     if hi - lo < per:
         send = torch.zeros((per, width), dtype=local_feats.dtype, device=local_feats.device)
         send[:hi - lo] = local_feats
-    full = torch.empty((per * world, width), dtype=local_feats.dtype, device=local_feats.device)
-    dist.all_gather_into_tensor(full, send.contiguous(), group=group)
-    return full[:n_total]
+    full = out if out is not None else torch.empty((per * world, width), dtype=local_feats.dtype, device=local_feats.device)
+    if full.shape != (per * world, width):
+        raise ValueError(f"out must have shape {(per * world, width)}")
+    work = dist.all_gather_into_tensor(full, send.contiguous(), group=group, async_op=async_op)
+    return (full[:n_total], work) if async_op else full[:n_total]
 
 
 def gather_ragged_feature_cache(local_feats: torch.Tensor, ranges, group=None) -> torch.Tensor:

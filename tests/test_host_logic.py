@@ -103,6 +103,12 @@ def _worker(rank, world, port, n_total, ragged):
             full = shard.gather_ragged_feature_cache(fake_extract(table[lo:hi], None), ranges)
         else:
             full = shard.extract_sharded(fake_extract, table)
+            # the same through the asynchronous form with a caller-owned cache buffer
+            lo, hi = shard.shard_range(n_total, world, rank)
+            buf = torch.empty((shard.shard_size(n_total, world) * world, 6))
+            full2, work = shard.gather_feature_cache(fake_extract(table[lo:hi], None), n_total, out=buf, async_op=True)
+            work.wait()
+            assert torch.equal(full2, expect) and full2.data_ptr() == buf.data_ptr()
         assert full.shape == expect.shape and torch.equal(full, expect)
     finally:
         dist.destroy_process_group()
