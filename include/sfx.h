@@ -92,7 +92,8 @@ int         sfx_init_tables(int device, const sfx_tables_host *tables);
 size_t      sfx_workspace_bytes(int device, int64_t max_samples);
 
 /* Kernels launched by the most recent sfx_extract / sfx_extract_debug / sfx_extract_host call of this thread (1 before
- * any call; fused pipeline: 1 per call or host chunk; split pipeline: 3 per chunk of <= 1024 clips). */
+ * any call; fused pipeline: 1 per call or host chunk, +1 for a ragged batch (lengths != NULL, more clips than CTAs), whose
+ * clips are processed longest first; split pipeline: 3 per chunk of <= 1024 clips). */
 int         sfx_launches_per_extract(void);
 
 /* Pipeline selection: 0 = auto (default: the frame-parallel two-kernel pipeline for batches <= 256 clips, where it has

@@ -178,9 +178,15 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
     if (ws_bytes < sfx::kWsHeader + slice * static_cast<size_t>(grid))
         return fail(SFX_ERR_WORKSPACE, "workspace smaller than sfx_workspace_bytes(device, max_samples)");
     p.cta_scratch_bytes = static_cast<long long>(slice);
-    CK(cudaMemsetAsync(ws, 0, sfx::kWsHeader, st));
-    CK(sfx::launch_extract(p, grid, dbg != nullptr, st));
+    CK(cudaMemsetAsync(ws, 0, sfx::kWsQueueBytes, st));
     g_last_launches = 1;
+    if (lengths && B > grid && B <= sfx::kOrderMax) {        // ragged batch with more clips than CTAs: longest clips first
+        int* order = reinterpret_cast<int*>(static_cast<unsigned char*>(ws) + sfx::kWsQueueBytes);
+        CK(sfx::launch_order(lengths, B, order, st));
+        p.order = order;
+        g_last_launches = 2;
+    }
+    CK(sfx::launch_extract(p, grid, dbg != nullptr, st));
     return SFX_OK;
 }
 

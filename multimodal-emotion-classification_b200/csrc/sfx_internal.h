@@ -24,7 +24,9 @@ constexpr int kRedoCap = 256;            // peaks per clip queued for the refere
 constexpr int kPRow = 36;                // floats per 32 bins of the |X|^2 tile (4 pad: 128-bit conflict-free rows)
 constexpr int kPartOff = 1156;           // offset of the mel partial-sum slots inside a warp's tile
 constexpr int kKeyCap = 13312;           // peak keys (u32) + bins (u8) kept in shared memory during the median select
-constexpr size_t kWsHeader = 256;        // clip-queue counter lives in the first bytes of the workspace
+constexpr int kOrderMax = 65536;         // largest ragged batch that is processed longest-clip-first (order array in the header)
+constexpr size_t kWsQueueBytes = 256;    // clip-queue counter lives in the first bytes of the workspace
+constexpr size_t kWsHeader = kWsQueueBytes + 4 * static_cast<size_t>(kOrderMax);   // + the clip order of a ragged batch
 
 struct DevTables {
     const float2* hann;     // [1024]
@@ -55,6 +57,7 @@ struct Params {
     int Tmax;
     int aligned8;
     int max_pk;             // peak records per frame the scratch slice is sized for
+    const int* order;       // clip processed q-th by the queue (ragged batches: longest first), nullptr = q
     DevTables tb;
     sfx_debug_out dbg;
 };
@@ -95,5 +98,6 @@ cudaError_t configure_split(int* frames_per_sm, int* clips_per_sm);
 cudaError_t launch_split_chunk(const SplitParams& q, int grid_frames, int grid_clips, bool debug, cudaStream_t stream);
 cudaError_t configure_kernels(int* blocks_per_sm);
 cudaError_t launch_extract(const Params& p, int grid, bool debug, cudaStream_t stream);
+cudaError_t launch_order(const int32_t* lengths, int B, int* order, cudaStream_t stream);
 
 }  // namespace sfx

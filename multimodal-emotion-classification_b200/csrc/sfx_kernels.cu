@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         __syncthreads();
         if (tid == 0) { s_i[0] = atomicAdd(counter, 1); s_i[17] = 0; s_i[18] = 0; s_i[19] = -1; }
         __syncthreads();
-        const int clip = s_i[0];
-        if (clip >= p.B) break;
+        if (s_i[0] >= p.B) break;
+        const int clip = p.order ? p.order[s_i[0]] : s_i[0];
         const long long n = p.lengths ? static_cast<long long>(p.lengths[clip]) : p.n_default;
         float* out = p.out + static_cast<long long>(clip) * p.out_stride;
         if (n <= 0) {
@@ -128,6 +128,49 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
 }
 
 // ------------------------------------------------------------------------------------------------
+// Longest-processing-time-first order of a ragged batch: one CTA, counting sort of the clips by a 256-level logarithmic
+// key of their frame count (8 levels per octave), longest first.  With one persistent CTA per clip, a 60 s clip that is
+// pulled from the queue last would otherwise run alone at the end of the launch.
+__global__ void __launch_bounds__(1024) sfx_order_kernel(const int32_t* __restrict__ lengths, const int B,
+                                                         int* __restrict__ order) {
+    __shared__ int s_cnt[256], s_pos[256];
+    const int tid = threadIdx.x;
+    auto bucket = [](int n) {
+        const unsigned T = n > 0 ? 1u + static_cast<unsigned>(n) / kHop : 0u;
+        unsigned key = T;
+        if (T >= 8u) {
+            const int e = 31 - __clz(T);
+            key = (static_cast<unsigned>(e) << 3) | ((T >> (e - 3)) & 7u);
+        }
+        return 255 - static_cast<int>(min(key, 255u));
+    };
+    if (tid < 256) s_cnt[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < B; i += 1024) atomicAdd(&s_cnt[bucket(lengths[i])], 1);
+    __syncthreads();
+    if (tid < 32) {                                  // exclusive scan of the 256 counters by one warp
+        int loc[8], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { loc[q] = s_cnt[tid * 8 + q]; sum += loc[q]; }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= o) inc += v;
+        }
+        int run = inc - sum;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { s_pos[tid * 8 + q] = run; run += loc[q]; }
+    }
+    __syncthreads();
+    for (int i = tid; i < B; i += 1024) order[atomicAdd(&s_pos[bucket(lengths[i])], 1)] = i;
+}
+
+cudaError_t launch_order(const int32_t* lengths, int B, int* order, cudaStream_t stream) {
+    sfx_order_kernel<<<1, 1024, 0, stream>>>(lengths, B, order);
+    return cudaGetLastError();
+}
+
 size_t smem_bytes() {
     return sizeof(float2) * (2560 + 17 * 64) + sizeof(float) * kWarps * kExFloats +
            sizeof(double) * (256 + kWarps * 16 + 104 + 1) + sizeof(int) * (256 + 32) + sizeof(float) * 32;

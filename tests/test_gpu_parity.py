@@ -338,6 +338,25 @@ def test_fast_peak_arithmetic_equals_reference_forms(ex):
     assert ci[0, 2] > 100_000 and (ci[:, 6] == 0).all(), ci[:, [2, 6]]
 
 
+def test_ragged_batch_longest_first_order(ex):
+    """A ragged batch with more clips than resident CTAs is processed longest clip first (device-side counting sort of
+    the clip queue); every clip's row must be what the same clip gives in a small batch that is processed in order."""
+    wr, lens = synth.make_ragged(700, 600, 40000, seed=93)
+    lens[::97] = 0                                        # invalid clips keep their NaN rows, wherever they are queued
+    wd, ld = dev(wr), dev(lens)
+    try:
+        assert ex.lib.sfx_set_pipeline(1) == 0
+        full = ex.extract(wd, ld).cpu().numpy()
+        assert ex.lib.sfx_launches_per_extract() == 2     # order kernel + extractor
+        parts = [ex.extract(wd[i:i + 100], ld[i:i + 100]).cpu().numpy() for i in range(0, 700, 100)]
+        assert ex.lib.sfx_launches_per_extract() == 1
+    finally:
+        ex.lib.sfx_set_pipeline(0)
+    ref = np.concatenate(parts, axis=0)
+    assert np.isnan(full[::97]).all() and np.array_equal(np.isnan(full), np.isnan(ref))
+    assert np.array_equal(np.nan_to_num(full), np.nan_to_num(ref))
+
+
 def test_fused_and_split_pipelines_agree(ex):
     """The persistent fused kernel and the frame-parallel two-kernel pipeline run the same arithmetic; only the order of
     the per-clip float64 sums of the per-frame centroid / roll-off differs."""
