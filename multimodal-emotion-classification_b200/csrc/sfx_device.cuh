@@ -1,6 +1,6 @@
 // sfx_device.cuh -- device helpers shared by the fused kernel (sfx_kernels.cu) and the split kernels (sfx_split.cu):
-// compile-time unrolling, the register-resident 32-point FFT, warp reductions, the CTA radix select, MMA / TMA wrappers,
-// and the frame loader.
+// compile-time unrolling, the register-resident 32-point FFT (scalar and packed-FP32 forms), warp reductions, the CTA
+// radix select, MMA / TMA wrappers, small inline-PTX helpers and the frame loader.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -50,58 +50,6 @@ __host__ __device__ constexpr float cos32(int q) {
 // sin(2*pi*q/32) = cos(2*pi*(8-q)/32) for q <= 8, cos(2*pi*(q-8)/32) for q in (8,16)
 __host__ __device__ constexpr float sin32x(int q) { return q <= 8 ? cos32(8 - q) : cos32(q - 8); }
 
-// DIT butterfly on (a, b) with twiddle w = exp(-2*pi*i*Q/32) = (c, -s):  a' = a + w*b,  b' = a - w*b.
-// Non-trivial twiddles use the 6-FMA "tangent" form: w*b = c*(br + t*bi, bi - t*br) with t = s/c when |c| >= |s|,
-// and w*b = s*(t*br + bi, t*bi - br) with t = c/s otherwise (|t| <= 1 in both cases).
-template <int Q>
-__device__ __forceinline__ void dit_bfly(float& ar, float& ai, float& br, float& bi) {
-    if constexpr (Q == 0) {
-        const float xr = ar - br, xi = ai - bi;
-        ar += br; ai += bi; br = xr; bi = xi;
-    } else if constexpr (Q == 8) {          // w = -i: w*b = (bi, -br)
-        const float xr = ar - bi, xi = ai + br;
-        ar += bi; ai -= br; br = xr; bi = xi;
-    } else {
-        constexpr float c = cos32(Q), sn = sin32x(Q);
-        constexpr bool use_c = (c >= 0 ? c : -c) >= sn;        // sn >= 0 for Q in (0, 16)
-        if constexpr (use_c) {
-            constexpr float t = sn / c;
-            const float pr = fmaf(t, bi, br);
-            const float pi = fmaf(-t, br, bi);
-            br = fmaf(-c, pr, ar); bi = fmaf(-c, pi, ai);
-            ar = fmaf(c, pr, ar);  ai = fmaf(c, pi, ai);
-        } else {
-            constexpr float t = c / sn;
-            const float pr = fmaf(t, br, bi);
-            const float pi = fmaf(t, bi, -br);
-            br = fmaf(-sn, pr, ar); bi = fmaf(-sn, pi, ai);
-            ar = fmaf(sn, pr, ar);  ai = fmaf(sn, pi, ai);
-        }
-    }
-}
-
-// radix-2 DIT stage of half-size H on the bit-reversed view v[p] = reg[brev5(p)]
-template <int H>
-__device__ __forceinline__ void dit_stage(float (&re)[32], float (&im)[32]) {
-    sfor<16 / H>([&](auto B) {
-        sfor<H>([&](auto J) {
-            constexpr int p0 = decltype(B)::value * 2 * H + decltype(J)::value;
-            constexpr int i0 = brev5(p0), i1 = brev5(p0 + H);
-            constexpr int Q = decltype(J)::value * (16 / H);
-            dit_bfly<Q>(re[i0], im[i0], re[i1], im[i1]);
-        });
-    });
-}
-
-// 32-point complex FFT in registers: natural-order input x[n] in slot n, output X[k] in slot brev5(k)
-__device__ __forceinline__ void fft32(float (&re)[32], float (&im)[32]) {
-    dit_stage<1>(re, im);
-    dit_stage<2>(re, im);
-    dit_stage<4>(re, im);
-    dit_stage<8>(re, im);
-    dit_stage<16>(re, im);
-}
-
 // ------------------------------------------------------------------------------------------------
 // Packed FP32 (sm_100 FFMA2 / FADD2 / FMUL2): a complex value lives in one aligned 64-bit register pair (re, im) and
 // every butterfly acts on both halves at once.  ptxas folds the (re, im) swap and the per-half sign of a multiplication
@@ -128,7 +76,9 @@ __device__ __forceinline__ c64 conj2(c64 v) { float a, b; upk(v, a, b); return p
 // v * w for complex v and w = (wr, wi): wr * v + wi * (i v)
 __device__ __forceinline__ c64 cmul(c64 v, float wr, float wi) { return fma2(rot_pi(v), bc2(wi), mul2(v, bc2(wr))); }
 
-// radix-2 DIT butterfly (a, b) <- (a + w b, a - w b), w = exp(-2 pi i Q / 32), same tangent forms as dit_bfly
+// radix-2 DIT butterfly (a, b) <- (a + w b, a - w b), w = exp(-2 pi i Q / 32).  Non-trivial twiddles use the "tangent"
+// form: w*b = c*(br + t*bi, bi - t*br) with t = s/c when |c| >= |s|, and w*b = s*(t*br + bi, t*bi - br) with t = c/s
+// otherwise (|t| <= 1 in both cases), i.e. one packed FMA for the rotation and one each for a + w b and a - w b.
 template <int Q>
 __device__ __forceinline__ void dit_bfly_p(c64& a, c64& b) {
     if constexpr (Q == 0) {
@@ -154,6 +104,7 @@ __device__ __forceinline__ void dit_bfly_p(c64& a, c64& b) {
         }
     }
 }
+// radix-2 DIT stage of half-size H on the bit-reversed view v[p] = z[brev5(p)]
 template <int H>
 __device__ __forceinline__ void dit_stage_p(c64 (&z)[32]) {
     sfor<16 / H>([&](auto B) {

@@ -2,15 +2,18 @@
 //
 // One persistent CTA per clip (dynamic clip queue), 8 warps, 2 CTAs per SM.  Replaces, for a whole batch,
 // the per-clip librosa calls of the reference's preprocessing/audio_preprocessing.py:22-37:
-//   phase 1 (warp per STFT frame): framing + Hann + 2048-pt real FFT (1024-pt complex FFT as two
-//           register-resident radix-32 passes with one shared-memory transpose) -> |X|^2;
-//           rms / zero crossings from the raw samples; |X| centroid + 0.85 roll-off (warp scan);
-//           piptrack peaks (librosa.piptrack on the POWER spectrum) appended to the clip's peak list;
-//           sparse Slaney mel projection + 10*log10.  |X|^2 and log-mel rows go to the CTA's scratch slice.
-//   phase 2 (CTA): estimate_tuning = median of peak magnitudes (radix select) -> 100-bin histogram
-//           arg-max; global log-mel max for power_to_db(top_db=80).
-//   phase 3 (CTA): clamp + frame-mean of log-mel, DCT-II (float64) -> MFCC; chroma projection with the
-//           tuning's filter bank, per-frame inf-norm, frame mean; pooled spectral descriptors.
+//   phase 1 (warp per STFT frame): framing + Hann + 2048-pt real FFT (1024-pt complex FFT as two register-resident
+//           radix-32 passes on packed FP32 -- FFMA2 / FADD2, a complex value per register pair -- with one
+//           shared-memory transpose) -> |X|^2; rms / zero crossings from the raw samples; |X| centroid + 0.85
+//           roll-off (warp scan); piptrack peaks (librosa.piptrack on the POWER spectrum) ballot-compacted into the
+//           warp's own segment of the clip's record buffer; sparse Slaney mel projection + 10*log10.  FP16-scaled
+//           |X|^2 rows and log-mel rows go to the CTA's scratch slice.
+//   phase 2 (CTA): estimate_tuning = median of peak magnitudes (radix select over the differing key bits) ->
+//           100-bin histogram arg-max, per-peak arithmetic in guarded fast forms that reproduce librosa's float64 /
+//           float32 dtype trail exactly; global log-mel max for power_to_db(top_db=80).
+//   phase 3 (CTA): clamp + frame-mean of log-mel, DCT-II (float64) -> MFCC; chroma projection with the tuning's
+//           filter bank (TMA-staged, tensor-core MMA), per-frame inf-norm, frame mean; pooled spectral descriptors.
+// The phase code itself lives in sfx_phases.cuh (shared with the frame-parallel pipeline of sfx_split.cu).
 // Output row: [mfcc_0..n_mfcc-1 | chroma C..B | zcr, centroid, rolloff, rms]  (reference :45-46).
 #include "sfx_phases.cuh"
 

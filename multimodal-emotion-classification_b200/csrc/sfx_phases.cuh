@@ -3,8 +3,9 @@
 //   process_frame<kDebug, kSplit> : phase 1 for one STFT frame, executed by one warp
 //   clip_tail<kDebug>             : phases 2-3 + the pooled output row for one clip, executed by one CTA
 // kSplit selects where per-frame results are kept: the fused kernel accumulates centroid / roll-off / zero crossings /
-// log-mel max per warp in shared memory and counts peaks with a shared atomic; the split pipeline stores them per frame
-// in the clip's slice (summed later in a fixed order) and counts peaks with a global atomic.
+// log-mel max per warp in shared memory and appends peak records to the warp's own segment of the clip's record buffer
+// (fill level in a register); the split pipeline stores the per-frame values in the clip's slice (summed later in a
+// fixed order) and reserves record space with one global atomic per frame.
 #pragma once
 #include "sfx_device.cuh"
 
