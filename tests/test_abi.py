@@ -52,6 +52,9 @@ def test_no_cpu_fallback():
     out = np.zeros((1, 56), dtype=np.float32)
     rc = lib.sfx_extract_host(0, 22050, x.ctypes.data, 66150, None, 66150, 1, 40, out.ctypes.data, 56, 0)
     assert rc == -3                                   # SFX_ERR_NOT_INIT: nothing ran, nothing was computed
+    pcm = np.zeros((1, 66150), dtype=np.int16)
+    rc = lib.sfx_extract_host_pcm16(0, 22050, pcm.ctypes.data, 66150, None, 66150, 1, 40, out.ctypes.data, 56, 0)
+    assert rc == -3 and not out.any()
     from preprocessing.audio_preprocessing import extract_mfcc
     with pytest.raises(NoCudaDeviceError):
         extract_mfcc(np.zeros(66150, dtype=np.float32), 22050)
