@@ -714,7 +714,8 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
     // (hi and 2^11*lo halves, separate accumulators), B = the frame's scaled FP16 |X|^2 row.  One unit = 8 frames x
     // 512 bins = 16 steps of 1 LDG.128 + 4 LDS.128 + 4 MMA; lane (g = lane/4, t4 = lane%4) feeds frame g's bins
     // k0+8*t4..+7 and rows g, g+8 of the bank.  Units are dealt round-robin to the warps, the two K-halves of a tile
-    // are added in a fixed order, then each frame is normalised by its max (librosa norm=inf).
+    // are added in a fixed order, then each frame is normalised by its max (librosa norm=inf).  The clip's last,
+    // incomplete tile is split by steps instead (below).
     {
         float* part2 = cs.s_ex + (2 * kChroma * kP16Stride) / 2;        // [kChromaTiles][2][96] floats after the bank
         const int g = lane >> 2, t4 = lane & 3;
@@ -724,14 +725,15 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         float wny[kChroma];
 #pragma unroll
         for (int c = 0; c < kChroma; ++c) wny[c] = __ldg(tb.chroma_ny + tuning_idx * kChroma + c);
-        const int ntiles = (T + 7) >> 3;
-        for (int tile0 = 0; tile0 < ntiles; tile0 += kChromaTiles) {
-            const int nt = min(kChromaTiles, ntiles - tile0);
+        // full 8-frame tiles: unit = tile x K-half, dealt round-robin to the warps (16 tiles = 4 units per warp)
+        const int nfull = T >> 3, rem = T & 7;
+        for (int tile0 = 0; tile0 < nfull; tile0 += kChromaTiles) {
+            const int nt = min(kChromaTiles, nfull - tile0);
             for (int u = warp; u < 2 * nt; u += kWarps) {
                 const int tl = u >> 1, kh = u & 1;
                 const int f = (tile0 + tl) * 8 + g;
-                const bool valid = f < T;
-                const __half* prow = sl.gP16 + static_cast<size_t>(valid ? f : 0) * kP16Stride + kh * 512 + 8 * t4;
+                constexpr bool valid = true;
+                const __half* prow = sl.gP16 + static_cast<size_t>(f) * kP16Stride + kh * 512 + 8 * t4;
                 const int r1 = (g < 4) ? g + 8 : g;                  // bank rows 12..15 do not exist
                 const __half* whi0 = sW + g * kP16Stride + kh * 512 + 8 * t4;
                 const __half* whi1 = sW + r1 * kP16Stride + kh * 512 + 8 * t4;
@@ -789,6 +791,62 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
                     for (int c = 0; c < kChroma; ++c)
                         csum[c] += static_cast<double>(small ? raw[c] * inv_s : __fdiv_rn(raw[c], mx));
                 }
+            }
+            __syncthreads();
+        }
+        // remainder tile (T % 8 frames): its 32 steps are split evenly over the 8 warps (4 each), so that 130 frames cost
+        // every warp 4 units + 4 steps instead of 5 units for two of them; the 8 partial sums are added in warp order
+        if (rem) {
+            const int f = nfull * 8 + g;
+            const bool valid = f < T;
+            const int k0 = warp * 128 + 8 * t4;                      // steps 4*warp .. 4*warp+3
+            const __half* prow = sl.gP16 + static_cast<size_t>(valid ? f : 0) * kP16Stride + k0;
+            const int r1 = (g < 4) ? g + 8 : g;
+            const __half* whi0 = sW + g * kP16Stride + k0;
+            const __half* whi1 = sW + r1 * kP16Stride + k0;
+            const __half* wlo0 = whi0 + kChroma * kP16Stride;
+            const __half* wlo1 = whi1 + kChroma * kP16Stride;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f};
+            uint4 pv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pv[i] = valid ? *reinterpret_cast<const uint4*>(prow + i * 32) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int o = i * 32;
+                const uint4 h0 = *reinterpret_cast<const uint4*>(whi0 + o);
+                const uint4 h1 = *reinterpret_cast<const uint4*>(whi1 + o);
+                const uint4 l0 = *reinterpret_cast<const uint4*>(wlo0 + o);
+                const uint4 l1 = *reinterpret_cast<const uint4*>(wlo1 + o);
+                mma_f16(acc, h0.x, h1.x, h0.y, h1.y, pv[i].x, pv[i].y);
+                mma_f16(acc, h0.z, h1.z, h0.w, h1.w, pv[i].z, pv[i].w);
+                mma_f16(acl, l0.x, l1.x, l0.y, l1.y, pv[i].x, pv[i].y);
+                mma_f16(acl, l0.z, l1.z, l0.w, l1.w, pv[i].z, pv[i].w);
+            }
+            constexpr float kLo = 1.0f / 2048.0f;
+            float* dst = part2 + warp * 96;
+            *reinterpret_cast<float2*>(dst + g * 8 + 2 * t4) = make_float2(fmaf(acl[0], kLo, acc[0]), fmaf(acl[1], kLo, acc[1]));
+            if (g < 4)
+                *reinterpret_cast<float2*>(dst + (g + 8) * 8 + 2 * t4) = make_float2(fmaf(acl[2], kLo, acc[2]), fmaf(acl[3], kLo, acc[3]));
+            __syncthreads();
+            if (tid < rem) {
+                const int fr = nfull * 8 + tid;
+                const float* q = part2 + tid;
+                const float pn = sl.gNy[fr];
+                float raw[kChroma];
+                float mx = 0.0f;
+#pragma unroll
+                for (int c = 0; c < kChroma; ++c) {
+                    float v = q[c * 8];
+#pragma unroll
+                    for (int w = 1; w < kWarps; ++w) v += q[w * 96 + c * 8];
+                    raw[c] = fmaf(wny[c], pn, v);
+                    mx = fmaxf(mx, fabsf(raw[c]));
+                }
+                const float inv_s = sl.gInvS[fr];
+                const bool small = mx * inv_s < FLT_MIN;
+#pragma unroll
+                for (int c = 0; c < kChroma; ++c)
+                    csum[c] += static_cast<double>(small ? raw[c] * inv_s : __fdiv_rn(raw[c], mx));
             }
             __syncthreads();
         }

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_frames_kernel(const SplitPara
 
 // ---------------------------------------------------------------------------------------------- clips
 template <bool kDebug>
-__global__ void __launch_bounds__(kThreads, 3) sfx_clips_kernel(const SplitParams q) {
+__global__ void __launch_bounds__(kThreads, 2) sfx_clips_kernel(const SplitParams q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_ex = reinterpret_cast<float*>(smem_raw);                        // [kWarps][kExFloats]
     double* s_pool = reinterpret_cast<double*>(s_ex + kWarps * kExFloats);   // [256]
