@@ -362,6 +362,30 @@ def main():
                  "path": "sfx_extract_host_pcm16: pinned int16 PCM rows -> H2D || device x/32768 + kernel || D2H",
                  "finite": bool(torch.isfinite(h_out16).all())}
 
+    # file-shaped input: 3 s of 48 kHz mono 16-bit PCM per clip (what a RAVDESS WAV file holds), resampled to 22.05 kHz on
+    # the device by the load_audio front-end (scope row f3), then extracted
+    n48 = 48000 * 3
+    Bf = min(Be, 2048)
+    h_48 = torch.empty((Bf, n48), dtype=torch.int16).pin_memory()
+    h_48.copy_((torch.randn((Bf, n48), generator=torch.Generator().manual_seed(5)) * 3000.0).round().clamp(-32768, 32767).to(torch.int16))
+    h_out48 = torch.empty((Bf, 56), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        ex.preprocess_pcm16(h_48.numpy(), None, 48000, out=h_out48.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ex.preprocess_pcm16(h_48.numpy(), None, 48000, out=h_out48.numpy())
+    f_s = time.perf_counter() - t0
+    if world > 1:
+        tm = torch.tensor([f_s], device=device, dtype=torch.float64)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        f_s = tm.item()
+    e2e_48k = {"value": Bf * world * e2e_steps / f_s, "unit": "clips/s", "h2d_bytes_per_step": Bf * n48 * 2,
+               "d2h_bytes_per_step": Bf * 56 * 4, "clips_per_gpu_per_step": Bf, "steps": e2e_steps,
+               "path": "sfx_preprocess_host_pcm16: pinned 48 kHz int16 PCM rows -> H2D || x/32768 + polyphase resample to "
+                       "22.05 kHz (float64, scipy.resample_poly-identical) + extractor || D2H",
+               "finite": bool(torch.isfinite(h_out48).all())}
+
     # ---------------- small-batch behaviour (rank 0): single-clip latency through the host path (what one request of the
     # reference's Flask app costs), and device-resident throughput at the batch sizes of configs[0] / configs[1]
     small = None
@@ -423,6 +447,7 @@ def main():
                     "d2h_bytes_per_step": Be * 56 * 4, "clips_per_gpu_per_step": Be, "steps": e2e_steps,
                     "path": "sfx_extract_host: pinned host rows -> chunked H2D || kernel || D2H on 2 streams"},
             "e2e_pcm16": e2e_pcm16,
+            "e2e_pcm16_48k": e2e_48k,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic * B) if traffic else None,

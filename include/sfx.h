@@ -138,6 +138,32 @@ int         sfx_extract_host_pcm16(int device, int32_t sr, const int16_t *host_p
                                    const int32_t *host_lengths, int64_t n_default, int32_t B, int32_t n_mfcc,
                                    float *host_out, int64_t out_stride, int32_t chunk_clips);
 
+/* ---- scope row f3: load_audio (reference :12-19) on the device for 16-bit PCM ------------------------------------
+ * Polyphase resampler description = scipy.signal.resample_poly(x, up, down) as this package's load_audio uses it:
+ * taps = the zero-padded filter (n_pre_pad zeros, then firwin(2*half_len+1, 1/max(up,down), ('kaiser', 5.0)) * up with
+ * half_len = 10*max(up,down)), n_pre_remove = (half_len + n_pre_pad) / down.  sfx_b200/resample.py builds it. */
+typedef struct {
+    int32_t       up, down;       /* target_sr / g, native_sr / g, g = gcd */
+    int32_t       n_taps;
+    int32_t       n_pre_remove;
+    const double *taps;           /* [n_taps] host */
+} sfx_resampler_host;
+
+/* file -> features for B clips of raw 16-bit PCM frames (mono or interleaved stereo) at their native rate:
+ * x/32768 (soundfile), channel mean (float32), resample_poly in float64 (bit-identical to scipy's result; rs == NULL or
+ * up == down: native rate, no filter), float32, zero pad / trim to n_target = sr * duration samples, then the extractor.
+ *   host_frames  [B] frames (samples per channel) to take from each row, already limited to round(native_sr * duration)
+ *                as load_audio does (:13), or NULL = frames_default
+ *   row_stride   int16 elements between rows of host_pcm
+ * Same chunk-pipelined H2D || kernels || D2H structure as sfx_extract_host.  librosa's own resampler (soxr_hq) is not
+ * restated: see DESIGN.md, row f3. */
+int         sfx_preprocess_host_pcm16(int device, int32_t sr, const sfx_resampler_host *rs, const int16_t *host_pcm,
+                                      int64_t row_stride, int32_t channels, const int32_t *host_frames,
+                                      int64_t frames_default, int64_t n_target, int32_t B, int32_t n_mfcc,
+                                      float *host_out, int64_t out_stride, int32_t chunk_clips);
+const char *sfx_frontend_last_error(void);
+int         sfx_frontend_release(int device);
+
 /* Release cached device buffers/tables of `device` (tests; process exit does it implicitly). */
 int         sfx_release(int device);
 

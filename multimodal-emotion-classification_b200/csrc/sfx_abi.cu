@@ -328,6 +328,7 @@ int sfx_set_pipeline(int mode) {
 
 int sfx_release(int device) {
     if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
+    sfx_frontend_release(device);
     std::lock_guard<std::mutex> lk(g_mu);
     DevCtx& c = g_ctx[device];
     if (!c.ready && c.allocs.empty()) return SFX_OK;

@@ -62,8 +62,8 @@ def _features_1clip(audio, sr, n_mfcc):
     return _last["row"], np.result_type(audio.dtype, np.float32)
 
 
-def _read_wav(file_path):
-    """Minimal RIFF/WAVE reader (PCM 8/16/24/32-bit, IEEE float 32/64) -> (float32 [frames, channels], rate)."""
+def _wav_chunks(file_path):
+    """(fmt tuple, raw data bytes) of a RIFF/WAVE file."""
     with open(file_path, "rb") as fh:
         data = fh.read()
     if len(data) < 12 or data[:4] != b"RIFF" or data[8:12] != b"WAVE":
@@ -81,6 +81,22 @@ def _read_wav(file_path):
         pos += 8 + size + (size & 1)
     if fmt is None or raw is None:
         raise ValueError(f"{file_path}: missing fmt/data chunk")
+    return fmt, raw
+
+
+def _read_wav_pcm16(file_path):
+    """Raw frames of a 16-bit PCM mono/stereo WAV file: (int16 [frames * channels], channels, rate), else None."""
+    fmt, raw = _wav_chunks(file_path)
+    tag, channels, rate, _, _, bits = fmt
+    if tag != 1 or bits != 16 or channels not in (1, 2):
+        return None
+    x = np.frombuffer(raw, dtype="<i2")
+    return x[:len(x) // channels * channels], int(channels), int(rate)
+
+
+def _read_wav(file_path):
+    """Minimal RIFF/WAVE reader (PCM 8/16/24/32-bit, IEEE float 32/64) -> (float32 [frames, channels], rate)."""
+    fmt, raw = _wav_chunks(file_path)
     tag, channels, rate, _, _, bits = fmt
     if tag == 1:
         if bits == 8:
@@ -173,20 +189,53 @@ def extract_features_batch(waveforms, lengths=None, sr=Config.SAMPLE_RATE, n_mfc
 
 
 def preprocess_audio_batch(file_paths, on_error="raise"):
-    """Batched preprocess_audio: decode every file, one device pass, float32 [N, 56].
+    """Batched preprocess_audio: float32 [N, 56] for N files, one device pass per (sample rate, channel count) group.
+
+    16-bit PCM WAV files (mono / stereo, any rate) never touch the host's float path: their raw frames go to the device,
+    which does what load_audio does -- x/32768, channel mean, polyphase resampling to Config.SAMPLE_RATE, pad / trim --
+    and then extracts the features (sfx_preprocess_host_pcm16; bit-identical to load_audio + extract on the host path).
+    Other encodings are decoded by load_audio on the host and extracted in one batch.
     on_error='skip' mirrors the per-file try/except of train_speech_model.py:124,142-143 and returns
     (features, kept_indices)."""
-    clips, kept = [], []
+    file_paths = list(file_paths)
+    sr, duration = Config.SAMPLE_RATE, Config.AUDIO_DURATION
+    rows = {}                                    # index -> float32[56]
+    groups, host_clips, host_idx = {}, [], []
     for i, fp in enumerate(file_paths):
         try:
-            audio, _ = load_audio(fp)
-            _valid_audio(audio)
-            clips.append(audio)
-            kept.append(i)
+            raw = _read_wav_pcm16(fp)
+            if raw is not None:
+                x, channels, rate = raw
+                if len(x) == 0:
+                    raise ParameterError("Audio data must be a non-empty 1-D array (mono)")
+                groups.setdefault((rate, channels), []).append((i, x))
+            else:
+                audio, _ = load_audio(fp)
+                _valid_audio(audio)
+                host_clips.append(audio)
+                host_idx.append(i)
         except Exception:
             if on_error != "skip":
                 raise
-    n = Config.SAMPLE_RATE * Config.AUDIO_DURATION
-    waves = np.stack(clips) if clips else np.zeros((0, n), dtype=np.float32)
-    feats = extract_features_batch(waves) if len(clips) else np.zeros((0, 56), dtype=np.float32)
-    return (feats, kept) if on_error == "skip" else feats
+    if groups:
+        from sfx_b200 import get_extractor
+        ex = get_extractor(None, int(sr))
+        for (rate, channels), items in groups.items():
+            limit = int(round(rate * duration)) * channels
+            width = min(limit, max(len(x) for _, x in items))
+            pcm = np.zeros((len(items), width + (width & 1)), dtype=np.int16)
+            frames = np.zeros(len(items), dtype=np.int32)
+            for r, (_, x) in enumerate(items):
+                n = min(len(x), width)
+                pcm[r, :n] = x[:n]
+                frames[r] = n // channels
+            feats = ex.preprocess_pcm16(pcm, frames, rate, channels=channels, duration=duration)
+            for r, (i, _) in enumerate(items):
+                rows[i] = feats[r]
+    if host_clips:
+        feats = extract_features_batch(np.stack(host_clips))
+        for r, i in enumerate(host_idx):
+            rows[i] = feats[r]
+    kept = sorted(rows)
+    out = np.stack([rows[i] for i in kept]).astype(np.float32) if kept else np.zeros((0, 56), dtype=np.float32)
+    return (out, kept) if on_error == "skip" else out

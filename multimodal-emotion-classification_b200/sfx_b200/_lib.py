@@ -32,6 +32,11 @@ class DebugOut(C.Structure):
                 ("clip_info", C.c_void_p), ("T_dbg", C.c_int32)]
 
 
+class ResamplerHost(C.Structure):
+    _fields_ = [("up", C.c_int32), ("down", C.c_int32), ("n_taps", C.c_int32), ("n_pre_remove", C.c_int32),
+                ("taps", C.c_void_p)]
+
+
 class DnnHost(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("dims", C.c_void_p), ("kernel", C.c_void_p), ("bias", C.c_void_p),
                 ("bn_gamma", C.c_void_p), ("bn_beta", C.c_void_p), ("bn_mean", C.c_void_p), ("bn_var", C.c_void_p),
@@ -41,7 +46,7 @@ class DnnHost(C.Structure):
 EXPORTS = ["sfx_dnn_create", "sfx_dnn_destroy", "sfx_dnn_workspace_bytes", "sfx_dnn_launches_per_forward",
            "sfx_dnn_last_error", "sfx_dnn_forward", "sfx_abi_version", "sfx_last_error", "sfx_device_count", "sfx_init_tables", "sfx_workspace_bytes",
            "sfx_launches_per_extract", "sfx_set_pipeline", "sfx_extract", "sfx_extract_debug", "sfx_extract_host", "sfx_extract_host_pcm16",
-           "sfx_release"]
+           "sfx_preprocess_host_pcm16", "sfx_frontend_last_error", "sfx_frontend_release", "sfx_release"]
 
 
 def lib_path() -> str:
@@ -76,6 +81,13 @@ def load():
     lib.sfx_extract_host_pcm16.restype = C.c_int
     lib.sfx_extract_host_pcm16.argtypes = [C.c_int, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_int64, C.c_int32]
+    lib.sfx_preprocess_host_pcm16.restype = C.c_int
+    lib.sfx_preprocess_host_pcm16.argtypes = [C.c_int, C.c_int32, C.POINTER(ResamplerHost), C.c_void_p, C.c_int64, C.c_int32,
+                                              C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                              C.c_int32]
+    lib.sfx_frontend_last_error.restype = C.c_char_p
+    lib.sfx_frontend_release.restype = C.c_int
+    lib.sfx_frontend_release.argtypes = [C.c_int]
     lib.sfx_release.restype = C.c_int
     lib.sfx_release.argtypes = [C.c_int]
     lib.sfx_set_pipeline.restype = C.c_int

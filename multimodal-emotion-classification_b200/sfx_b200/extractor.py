@@ -141,6 +141,47 @@ class SpeechFeatureExtractor:
         return out
 
 
+    def preprocess_pcm16(self, pcm: np.ndarray, frames: np.ndarray | None, native_sr: int, channels: int = 1,
+                         duration: float = 3, n_mfcc: int = 40, out: np.ndarray | None = None,
+                         chunk_clips: int = 0) -> np.ndarray:
+        """load_audio + feature extraction for raw 16-bit PCM (scope row f3): ``pcm`` is host int16 [B, >= frames*channels]
+        (interleaved when stereo) at ``native_sr``; ``frames`` [B] are the frames each file holds (None: the row length).
+        Per clip: first round(native_sr*duration) frames, x/32768, channel mean, scipy-equivalent polyphase resampling
+        to this extractor's rate on the device (bit-identical to the host path of load_audio), zero pad / trim to
+        sr*duration, features.  Returns host float32 [B, n_mfcc+16]."""
+        from . import resample
+        pcm = np.asarray(pcm)
+        if pcm.dtype != np.int16 or pcm.ndim != 2 or pcm.strides[1] != 2:
+            raise ValueError("pcm must be a 2-D int16 array with contiguous rows")
+        B, L = pcm.shape
+        if channels not in (1, 2):
+            raise ValueError("channels must be 1 or 2")
+        limit = int(round(native_sr * duration))
+        if frames is None:
+            frames = np.full(B, L // channels, dtype=np.int64)
+        frames = np.minimum(np.asarray(frames, dtype=np.int64), limit).astype(np.int32)
+        if frames.shape != (B,) or (frames * channels > L).any():
+            raise ValueError("frames must have shape [B] and fit the rows")
+        width = n_mfcc + N_CHROMA + N_SPECTRAL
+        if out is None:
+            out = np.empty((B, width), dtype=np.float32)
+        if out.shape != (B, width) or out.dtype != np.float32 or out.strides[1] != 4:
+            raise ValueError("out must be float32 [B, n_mfcc+16]")
+        if B == 0:
+            return out
+        flt = resample.resample_filter(native_sr, self.sr)
+        rs = _lib.ResamplerHost(up=flt["up"], down=flt["down"], n_taps=len(flt["taps"]), n_pre_remove=flt["n_pre_remove"],
+                                taps=flt["taps"].ctypes.data)
+        n_target = int(self.sr * duration)
+        with torch.cuda.device(self.index):
+            rc = self.lib.sfx_preprocess_host_pcm16(self.index, self.sr, rs, pcm.ctypes.data, pcm.strides[0] // 2, channels,
+                                                    frames.ctypes.data, 0, n_target, B, n_mfcc, out.ctypes.data,
+                                                    out.strides[0] // 4, int(chunk_clips))
+        if rc:
+            raise _lib.SfxError(rc, self.lib.sfx_frontend_last_error().decode())
+        return out
+
+
 def get_extractor(device=None, sr: int = 22050) -> SpeechFeatureExtractor:
     """Process-wide cache: one extractor per (device index, sr)."""
     if not torch.cuda.is_available():
