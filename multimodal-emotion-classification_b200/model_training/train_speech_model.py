@@ -55,9 +55,11 @@ def _label_of(fp: str, label_from: str, name_map):
     raise ValueError('label_from must be "parent" or "name"')
 
 
-def _extract_many(waves: np.ndarray) -> np.ndarray:
-    """One device pass over the decoded clips of this rank; with torch.distributed initialised, also the all-gather."""
-    return _ap.extract_features_batch(waves) if len(waves) else np.zeros((0, 56), dtype=np.float32)
+def _extract_files(paths):
+    """Features of this rank's files in batched device passes: (float32 [n, 56] with NaN rows for failures, {j: error})."""
+    if not len(paths):
+        return np.zeros((0, 56), dtype=np.float32), {}
+    return _ap.preprocess_audio_batch(paths, on_error="collect")
 
 
 def load_dataset(data_root: str, pattern: str, label_from: str, name_map: Dict[str, str] = None,
@@ -80,25 +82,14 @@ def load_dataset(data_root: str, pattern: str, label_from: str, name_map: Dict[s
     from sfx_b200.shard import shard_range
     lo, hi = shard_range(len(files), world, rank)
 
-    # ---- decode this rank's files; failures are reported and skipped like the reference's per-file try/except
-    n_len = Config.SAMPLE_RATE * Config.AUDIO_DURATION
-    waves = np.zeros((hi - lo, n_len), dtype=np.float32)
+    # ---- this rank's files: 16-bit PCM goes to the device as raw frames (dequantise, mono, resample, pad/trim and the
+    #      features all happen there), other encodings are decoded on the host; failures are reported and skipped like
+    #      the reference's per-file try/except
     ok = np.zeros(len(files), dtype=bool)
-    errors = {}
-    for j, fp in enumerate(files[lo:hi]):
-        if (lo + j) % 100 == 0:
-            print(f"  Processing {lo + j}/{len(files)}...", end='\r')
-        try:
-            audio, _ = _ap.load_audio(fp)
-            _ap._valid_audio(audio)
-            waves[j] = audio
-            ok[lo + j] = True
-        except Exception as e:  # noqa: BLE001  (reference :142 catches everything)
-            errors[lo + j] = e
-    local_ok = ok[lo:hi]
-    feats_local = np.full((hi - lo, 56), np.nan, dtype=np.float32)
-    if local_ok.any():
-        feats_local[local_ok] = _extract_many(np.ascontiguousarray(waves[local_ok]))
+    print(f"  Processing {lo}..{hi} of {len(files)}...", end='\r')
+    feats_local, local_errors = _extract_files(files[lo:hi])
+    errors = {lo + j: e for j, e in local_errors.items()}
+    ok[lo:hi] = [j not in local_errors for j in range(hi - lo)]
 
     # ---- feature cache on every rank
     if dist:

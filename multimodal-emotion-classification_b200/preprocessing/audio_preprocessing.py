@@ -196,8 +196,9 @@ def preprocess_audio_batch(file_paths, on_error="raise"):
     and then extracts the features (sfx_preprocess_host_pcm16; bit-identical to load_audio + extract on the host path).
     Other encodings are decoded by load_audio on the host and extracted in one batch.
     on_error='skip' mirrors the per-file try/except of train_speech_model.py:124,142-143 and returns
-    (features, kept_indices)."""
+    (features, kept_indices); on_error='collect' returns (features [N, 56] with NaN rows for failed files, {index: error})."""
     file_paths = list(file_paths)
+    errors = {}
     sr, duration = Config.SAMPLE_RATE, Config.AUDIO_DURATION
     rows = {}                                    # index -> float32[56]
     groups, host_clips, host_idx = {}, [], []
@@ -214,9 +215,10 @@ def preprocess_audio_batch(file_paths, on_error="raise"):
                 _valid_audio(audio)
                 host_clips.append(audio)
                 host_idx.append(i)
-        except Exception:
-            if on_error != "skip":
+        except Exception as e:  # noqa: BLE001  (reference :142 catches everything)
+            if on_error not in ("skip", "collect"):
                 raise
+            errors[i] = e
     if groups:
         from sfx_b200 import get_extractor
         ex = get_extractor(None, int(sr))
@@ -237,5 +239,10 @@ def preprocess_audio_batch(file_paths, on_error="raise"):
         for r, i in enumerate(host_idx):
             rows[i] = feats[r]
     kept = sorted(rows)
+    if on_error == "collect":
+        full = np.full((len(file_paths), 56), np.nan, dtype=np.float32)
+        for i in kept:
+            full[i] = rows[i]
+        return full, errors
     out = np.stack([rows[i] for i in kept]).astype(np.float32) if kept else np.zeros((0, 56), dtype=np.float32)
     return (out, kept) if on_error == "skip" else out

@@ -67,7 +67,19 @@ def test_load_dataset_semantics_match_reference_loop(tmp_path, monkeypatch, caps
     from model_training import train_speech_model as tsm
     import preprocessing.audio_preprocessing as ap
     make_tree(str(tmp_path))
-    monkeypatch.setattr(tsm, "_extract_many", stub_features)
+
+    def stub_extract_files(paths):                      # stands in for the device passes of preprocess_audio_batch
+        feats = np.full((len(paths), 56), np.nan, dtype=np.float32)
+        errors = {}
+        for j, fp in enumerate(paths):
+            try:
+                audio, _ = ap.load_audio(fp)
+                feats[j] = stub_features(audio[None])[0]
+            except Exception as e:  # noqa: BLE001
+                errors[j] = e
+        return feats, errors
+
+    monkeypatch.setattr(tsm, "_extract_files", stub_extract_files)
     X, y = tsm.load_dataset(str(tmp_path), "**/*.wav", label_from, name_map, cache_path=os.path.join(tmp_path, "cache.npz"))
     files = glob.glob(os.path.join(str(tmp_path), "**/*.wav"), recursive=True)
 
