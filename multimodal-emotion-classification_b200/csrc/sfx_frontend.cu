@@ -20,7 +20,9 @@ constexpr int kStreams = 2;
 
 struct Filter {                 // device copy of one (up, down) filter
     int up = 0, down = 0, n_taps = 0, n_pre_remove = 0;
-    double* d_taps = nullptr;
+    bool rows = false;          // large up: taps regrouped by phase
+    int per_phase = 0;          // K = ceil(n_taps / up)
+    double* d_taps = nullptr;   // rows ? [up][K] (row p = taps p, p + up, p + 2 up, ..., zero padded) : [n_taps]
 };
 
 struct FrontPath {
@@ -77,27 +79,37 @@ bool pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
-// one thread per output sample of one clip
+// One thread per output sample; two tap layouts / block shapes, chosen by the size of `up`:
+//   kRows = false (up <= 1024, e.g. 48 kHz -> 22.05 kHz, up = 147): taps in scipy's flat order.  For a given tap number
+//       the 32 lanes of a warp (consecutive outputs) differ only in their phase, so they read inside one window of `up`
+//       doubles -- a few cache lines of an L1-resident table.  Block = 256 consecutive outputs of one clip.
+//   kRows = true (large up, e.g. TESS's 24 414 Hz -> 22 050 Hz, up = 3675, a 700 KB table): taps regrouped into one
+//       contiguous row per phase, so a thread streams 2-3 lines instead of one per tap; block = 32 consecutive outputs
+//       (threadIdx.x) of 8 clips (threadIdx.y): output m has the same phase in every clip, so seven of the eight warps
+//       find the rows in L1.
+// Exactness: a sample is k * 2^-15 (mono) or (k_l + k_r) * 2^-16 (stereo mean, exact in float32), so summing
+// round(k * h) and scaling the total by the power of two reproduces, rounding for rounding, scipy's sum of round(x * h)
+// over ascending i; the integer k converts to float64 in one instruction.
+constexpr int kRsClips = 8;
+template <bool kRows>
 __global__ void __launch_bounds__(256) sfx_resample_pcm16_kernel(
     const int16_t* __restrict__ pcm, const long long row_stride, const int channels, const int32_t* __restrict__ frames,
-    const int frames_default, const int up, const int down, const double* __restrict__ taps, const int n_taps,
-    const int n_pre_remove, float* __restrict__ wave, const long long wave_stride, const int n_target) {
-    const int b = blockIdx.y;
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= n_target) return;
+    const int frames_default, const int B, const int up, const int down, const double* __restrict__ taps,
+    const int per_phase, const int n_taps, const int n_pre_remove, float* __restrict__ wave, const long long wave_stride,
+    const int n_target) {
+    const int b = kRows ? blockIdx.y * kRsClips + threadIdx.y : blockIdx.y;
+    const int m = kRows ? blockIdx.x * 32 + threadIdx.x : blockIdx.x * 256 + threadIdx.y * 32 + threadIdx.x;
+    if (b >= B || m >= n_target) return;
     const int n_in = frames ? frames[b] : frames_default;
     const int16_t* x = pcm + static_cast<long long>(b) * row_stride;
     float* y = wave + static_cast<long long>(b) * wave_stride;
-    // soundfile's float32 sample and numpy's float32 channel mean (2 channels: (a + b) / 2), then float64 like load_audio
-    auto sample = [&](int i) -> double {
-        constexpr float k = 1.0f / 32768.0f;
-        if (channels == 1) return static_cast<double>(static_cast<float>(x[i]) * k);
-        const float a = static_cast<float>(x[2 * i]) * k, c = static_cast<float>(x[2 * i + 1]) * k;
-        return static_cast<double>(__fmul_rn(__fadd_rn(a, c), 0.5f));
+    auto ksum = [&](long long i) -> int {                     // integer numerator of the (mono-mixed) sample
+        return channels == 1 ? static_cast<int>(x[i]) : static_cast<int>(x[2 * i]) + static_cast<int>(x[2 * i + 1]);
     };
+    const double scale = channels == 1 ? 1.0 / 32768.0 : 1.0 / 65536.0;
     if (n_in <= 0) { y[m] = 0.0f; return; }
     if (up == down) {                                   // native rate: no filter (resample_poly returns a copy)
-        y[m] = m < n_in ? static_cast<float>(sample(m)) : 0.0f;
+        y[m] = m < n_in ? static_cast<float>(static_cast<double>(ksum(m)) * scale) : 0.0f;
         return;
     }
     const long long n_out = (static_cast<long long>(n_in) * up + down - 1) / down;
@@ -105,12 +117,14 @@ __global__ void __launch_bounds__(256) sfx_resample_pcm16_kernel(
     const long long t0 = (static_cast<long long>(m) + n_pre_remove) * down;
     long long lo = t0 - (n_taps - 1);
     lo = lo > 0 ? (lo + up - 1) / up : 0;
-    long long hi = t0 / up;
-    if (hi > n_in - 1) hi = n_in - 1;
+    const long long q = t0 / up;
+    const long long hi = q > n_in - 1 ? n_in - 1 : q;
+    // tap of sample i is h[t0 - i*up] = rows[t0 % up][q - i]; either way the sum runs over ascending i like scipy's
+    const double* h = kRows ? taps + static_cast<long long>(t0 - q * up) * per_phase + (q - lo) : taps + (t0 - lo * up);
+    const long long step = kRows ? 1 : up;
     double acc = 0.0;
-    const double* h = taps + (t0 - lo * up);
-    for (long long i = lo; i <= hi; ++i, h -= up) acc = __dadd_rn(acc, __dmul_rn(sample(static_cast<int>(i)), *h));
-    y[m] = static_cast<float>(acc);
+    for (long long i = lo; i <= hi; ++i, h -= step) acc = __dadd_rn(acc, __dmul_rn(static_cast<double>(ksum(i)), __ldg(h)));
+    y[m] = static_cast<float>(acc * scale);
 }
 
 }  // namespace
@@ -191,8 +205,13 @@ int sfx_preprocess_host_pcm16(int device, int32_t sr, const sfx_resampler_host* 
         if (!flt) {
             Filter f;
             f.up = up; f.down = down; f.n_taps = rs->n_taps; f.n_pre_remove = rs->n_pre_remove;
-            FCK(cudaMalloc(&f.d_taps, sizeof(double) * f.n_taps));
-            FCK(cudaMemcpy(f.d_taps, rs->taps, sizeof(double) * f.n_taps, cudaMemcpyHostToDevice));
+            f.per_phase = (f.n_taps + up - 1) / up;
+            f.rows = up > 1024;
+            std::vector<double> poly(f.rows ? static_cast<size_t>(up) * f.per_phase : static_cast<size_t>(f.n_taps), 0.0);
+            for (int t = 0; t < f.n_taps; ++t)
+                poly[f.rows ? static_cast<size_t>(t % up) * f.per_phase + t / up : static_cast<size_t>(t)] = rs->taps[t];
+            FCK(cudaMalloc(&f.d_taps, sizeof(double) * poly.size()));
+            FCK(cudaMemcpy(f.d_taps, poly.data(), sizeof(double) * poly.size(), cudaMemcpyHostToDevice));
             fp.filters.push_back(f);
             flt = &fp.filters.back();
         }
@@ -228,11 +247,19 @@ int sfx_preprocess_host_pcm16(int device, int32_t sr, const sfx_resampler_host* 
             FCK(cudaMemcpyAsync(fp.d_frames[s], host_frames + c0, static_cast<size_t>(nb) * 4, cudaMemcpyHostToDevice, st));
             dfr = fp.d_frames[s];
         }
-        const dim3 grid(static_cast<unsigned>((n_target + 255) / 256), static_cast<unsigned>(nb));
-        sfx_resample_pcm16_kernel<<<grid, 256, 0, st>>>(fp.d_pcm[s], pcm_stride, channels, dfr, static_cast<int>(frames_default), up, down,
-                                                        flt ? flt->d_taps : nullptr, flt ? flt->n_taps : 0,
-                                                        flt ? flt->n_pre_remove : 0, fp.d_wave[s], wave_stride,
-                                                        static_cast<int>(n_target));
+        const double* d_taps = flt ? flt->d_taps : nullptr;
+        const int per_phase = flt ? flt->per_phase : 0, n_taps = flt ? flt->n_taps : 0, npr = flt ? flt->n_pre_remove : 0;
+        if (flt && flt->rows) {
+            const dim3 grid(static_cast<unsigned>((n_target + 31) / 32), static_cast<unsigned>((nb + kRsClips - 1) / kRsClips));
+            sfx_resample_pcm16_kernel<true><<<grid, dim3(32, kRsClips), 0, st>>>(
+                fp.d_pcm[s], pcm_stride, channels, dfr, static_cast<int>(frames_default), nb, up, down, d_taps, per_phase, n_taps,
+                npr, fp.d_wave[s], wave_stride, static_cast<int>(n_target));
+        } else {
+            const dim3 grid(static_cast<unsigned>((n_target + 255) / 256), static_cast<unsigned>(nb));
+            sfx_resample_pcm16_kernel<false><<<grid, dim3(32, 8), 0, st>>>(
+                fp.d_pcm[s], pcm_stride, channels, dfr, static_cast<int>(frames_default), nb, up, down, d_taps, per_phase, n_taps,
+                npr, fp.d_wave[s], wave_stride, static_cast<int>(n_target));
+        }
         FCK(cudaGetLastError());
         rc = sfx_extract(device, sr, fp.d_wave[s], wave_stride, nullptr, n_target, n_target, nb, n_mfcc, fp.d_out[s], out_w, fp.d_ws[s],
                          fp.ws_bytes, st);

@@ -166,7 +166,16 @@ def extract_spectral_features(audio, sr):
 
 
 def preprocess_audio(file_path):
-    """reference :40-46 -- file -> np.float32[56] = [40 mfcc | 12 chroma | zcr, centroid, rolloff, rms]."""
+    """reference :40-46 -- file -> np.float32[56] = [40 mfcc | 12 chroma | zcr, centroid, rolloff, rms].
+
+    A 16-bit PCM WAV file is handed to the device as raw frames (what load_audio does happens there, bit-identically,
+    see preprocess_audio_batch), so a 48 kHz file costs one device pass instead of a host resample_poly."""
+    try:
+        raw = _read_wav_pcm16(file_path)
+    except ValueError:
+        raw = None                      # not a RIFF file: let load_audio raise its own error below
+    if raw is not None:
+        return preprocess_audio_batch([file_path])[0]
     audio, sr = load_audio(file_path)
     mfcc = extract_mfcc(audio, sr)
     chroma = extract_chroma(audio, sr)

@@ -101,6 +101,13 @@ def test_preprocess_audio_batch_uses_the_device_front_end(ex, tmp_path):
             wf.setnchannels(ch); wf.setsampwidth(2); wf.setframerate(rate)
             wf.writeframes(np.clip(np.round(y * 32767.0), -32768, 32767).astype("<i2").tobytes())
         paths.append(p)
+    from preprocessing.audio_preprocessing import extract_chroma, extract_mfcc, extract_spectral_features, load_audio
     batch = preprocess_audio_batch(paths)
-    single = np.stack([preprocess_audio(p) for p in paths])
-    assert batch.shape == (5, 56) and np.array_equal(batch, single)
+
+    def host_path(p):                 # the reference's own composition (:40-46) on the host-decoded, host-resampled audio
+        audio, sr = load_audio(p)
+        return np.concatenate([extract_mfcc(audio, sr), extract_chroma(audio, sr), extract_spectral_features(audio, sr)])
+
+    host = np.stack([host_path(p) for p in paths]).astype(np.float32)
+    assert batch.shape == (5, 56) and np.array_equal(batch, host)
+    assert np.array_equal(np.stack([preprocess_audio(p) for p in paths]), host)
