@@ -121,9 +121,23 @@ __global__ void __launch_bounds__(256) sfx_resample_pcm16_kernel(
     const long long hi = q > n_in - 1 ? n_in - 1 : q;
     // tap of sample i is h[t0 - i*up] = rows[t0 % up][q - i]; either way the sum runs over ascending i like scipy's
     const double* h = kRows ? taps + static_cast<long long>(t0 - q * up) * per_phase + (q - lo) : taps + (t0 - lo * up);
-    const long long step = kRows ? 1 : up;
+    const int hstep = kRows ? 1 : up;
+    const int cnt = static_cast<int>(hi - lo + 1);
     double acc = 0.0;
-    for (long long i = lo; i <= hi; ++i, h -= step) acc = __dadd_rn(acc, __dmul_rn(static_cast<double>(ksum(i)), __ldg(h)));
+    if (channels == 1) {
+        const int16_t* xs = x + lo;
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k)
+            acc = __dadd_rn(acc, __dmul_rn(static_cast<double>(static_cast<int>(xs[k])), __ldg(h - k * hstep)));
+    } else {
+        const int* xs = reinterpret_cast<const int*>(x) + lo;             // one 32-bit load per stereo frame
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+            const int v = xs[k];
+            const int ks = static_cast<int>(static_cast<short>(v & 0xffff)) + (v >> 16);
+            acc = __dadd_rn(acc, __dmul_rn(static_cast<double>(ks), __ldg(h - k * hstep)));
+        }
+    }
     y[m] = static_cast<float>(acc * scale);
 }
 
