@@ -2,9 +2,8 @@
 Audio preprocessing utilities -- B200-native drop-in for the reference module of the same name
 (/root/reference/preprocessing/audio_preprocessing.py:12-46).
 
-Same five entry points, argument names, defaults and return shapes:
-- Load audio (pad/trim to fixed duration)
-- Extract MFCC, Chroma, and spectral features
+Same five entry points, argument names, defaults and return shapes: fixed-duration loading (zero pad / trim) and the
+frame-mean MFCC, chroma and [zcr, centroid, rolloff, rms] descriptors.
 
 The arithmetic that the reference delegates to librosa (STFT, mel/log/DCT, tuning estimate + chroma,
 zcr/centroid/rolloff/rms, frame-mean pooling) runs in hand-written sm_100a CUDA kernels behind the C ABI of
@@ -137,13 +136,10 @@ def load_audio(file_path, sr=Config.SAMPLE_RATE, duration=Config.AUDIO_DURATION)
         from scipy.signal import resample_poly
         g = gcd(int(sr), int(native))
         audio = resample_poly(audio.astype(np.float64), int(sr) // g, int(native) // g).astype(np.float32)
-    audio = np.ascontiguousarray(audio, dtype=np.float32)
-    target_len = sr * duration
-    if len(audio) < target_len:
-        audio = np.pad(audio, (0, target_len - len(audio)), mode='constant')
-    else:
-        audio = audio[:target_len]
-    return audio, sr
+    fixed = np.zeros(sr * duration, dtype=np.float32)          # zero tail for short files, cut for long ones
+    keep = min(len(audio), len(fixed))
+    fixed[:keep] = audio[:keep]
+    return fixed, sr
 
 
 def extract_mfcc(audio, sr, n_mfcc=Config.N_MFCC):
@@ -161,8 +157,7 @@ def extract_chroma(audio, sr):
 def extract_spectral_features(audio, sr):
     """reference :32-37 -- np.float32[4] = [zcr, spectral_centroid, spectral_rolloff, rms] frame means."""
     row, _ = _features_1clip(audio, sr, Config.N_MFCC)
-    zcr, spectral_centroid, spectral_rolloff, rms = (float(v) for v in row[Config.N_MFCC + 12:Config.N_MFCC + 16])
-    return np.array([zcr, spectral_centroid, spectral_rolloff, rms], dtype=np.float32)
+    return np.array(row[Config.N_MFCC + 12:Config.N_MFCC + 16], dtype=np.float32)     # zcr, centroid, rolloff, rms
 
 
 def preprocess_audio(file_path):
@@ -176,12 +171,9 @@ def preprocess_audio(file_path):
         raw = None                      # not a RIFF file: let load_audio raise its own error below
     if raw is not None:
         return preprocess_audio_batch([file_path])[0]
-    audio, sr = load_audio(file_path)
-    mfcc = extract_mfcc(audio, sr)
-    chroma = extract_chroma(audio, sr)
-    spectral = extract_spectral_features(audio, sr)
-    features = np.concatenate([mfcc, chroma, spectral])
-    return features.astype(np.float32)
+    wave_, rate = load_audio(file_path)
+    parts = (extract_mfcc(wave_, rate), extract_chroma(wave_, rate), extract_spectral_features(wave_, rate))
+    return np.concatenate(parts).astype(np.float32)
 
 
 # --------------------------------------------------------------------------- additive batched entry points
