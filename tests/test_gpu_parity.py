@@ -139,13 +139,21 @@ def test_other_n_mfcc(ex, n_mfcc):
     assert_parity(got, ref, n_mfcc=n_mfcc)
 
 
-def test_other_sample_rate(ex):
+@pytest.mark.parametrize("sr", [8000, 16000, 44100, 48000])
+def test_other_sample_rate(ex, sr):
+    """Other table sets: 8 kHz has the widest piptrack range (bins 39..1023, 31 rows of 32) and the fewest mel slots per lane,
+    48 kHz the narrowest range and the most slots (mel_ps = 25)."""
     from sfx_b200 import get_extractor
-    ex16 = get_extractor(torch.device("cuda", 0), sr=16000)
-    w = synth.make_batch(4, 48000, seed=41)
-    got = ex16.extract(dev(w)).cpu().numpy()
-    ref = np.stack([lp.features_from_audio(x, sr=16000) for x in w])
-    assert_parity(got, ref)
+    exs = get_extractor(torch.device("cuda", 0), sr=sr)
+    w = synth.make_batch(4, 3 * sr, seed=41)
+    try:
+        for mode in (1, 2):                                   # fused and split pipelines
+            assert exs.lib.sfx_set_pipeline(mode) == 0
+            got = exs.extract(dev(w)).cpu().numpy()
+            ref = np.stack([lp.features_from_audio(x, sr=sr) for x in w]) if mode == 1 else ref
+            assert_parity(got, ref)
+    finally:
+        exs.lib.sfx_set_pipeline(0)
 
 
 def test_host_path_matches_device_path_and_chunks(ex):
