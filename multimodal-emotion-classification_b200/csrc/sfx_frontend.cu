@@ -8,6 +8,7 @@
 // _upfirdn_apply -- and rounded once to float32.  The output is bit-identical to the host path.
 #include <algorithm>
 #include <mutex>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -91,7 +92,8 @@ bool pinned(const void* p) {
 // round(k * h) and scaling the total by the power of two reproduces, rounding for rounding, scipy's sum of round(x * h)
 // over ascending i; the integer k converts to float64 in one instruction.
 constexpr int kRsClips = 8;
-template <bool kRows>
+// kWide = false: every index product fits 31 bits (checked on the host), so the three divisions per output are 32-bit
+template <bool kRows, bool kWide>
 __global__ void __launch_bounds__(256) sfx_resample_pcm16_kernel(
     const int16_t* __restrict__ pcm, const long long row_stride, const int channels, const int32_t* __restrict__ frames,
     const int frames_default, const int B, const int up, const int down, const double* __restrict__ taps,
@@ -112,13 +114,14 @@ __global__ void __launch_bounds__(256) sfx_resample_pcm16_kernel(
         y[m] = m < n_in ? static_cast<float>(static_cast<double>(ksum(m)) * scale) : 0.0f;
         return;
     }
-    const long long n_out = (static_cast<long long>(n_in) * up + down - 1) / down;
+    using idx_t = std::conditional_t<kWide, long long, int>;
+    const idx_t n_out = (static_cast<idx_t>(n_in) * up + down - 1) / down;
     if (m >= n_out) { y[m] = 0.0f; return; }
-    const long long t0 = (static_cast<long long>(m) + n_pre_remove) * down;
-    long long lo = t0 - (n_taps - 1);
+    const idx_t t0 = (static_cast<idx_t>(m) + n_pre_remove) * down;
+    idx_t lo = t0 - (n_taps - 1);
     lo = lo > 0 ? (lo + up - 1) / up : 0;
-    const long long q = t0 / up;
-    const long long hi = q > n_in - 1 ? n_in - 1 : q;
+    const idx_t q = t0 / up;
+    const idx_t hi = q > n_in - 1 ? n_in - 1 : q;
     // tap of sample i is h[t0 - i*up] = rows[t0 % up][q - i]; either way the sum runs over ascending i like scipy's
     const double* h = kRows ? taps + static_cast<long long>(t0 - q * up) * per_phase + (q - lo) : taps + (t0 - lo * up);
     const int hstep = kRows ? 1 : up;
@@ -263,17 +266,20 @@ int sfx_preprocess_host_pcm16(int device, int32_t sr, const sfx_resampler_host* 
         }
         const double* d_taps = flt ? flt->d_taps : nullptr;
         const int per_phase = flt ? flt->per_phase : 0, n_taps = flt ? flt->n_taps : 0, npr = flt ? flt->n_pre_remove : 0;
-        if (flt && flt->rows) {
-            const dim3 grid(static_cast<unsigned>((n_target + 31) / 32), static_cast<unsigned>((nb + kRsClips - 1) / kRsClips));
-            sfx_resample_pcm16_kernel<true><<<grid, dim3(32, kRsClips), 0, st>>>(
-                fp.d_pcm[s], pcm_stride, channels, dfr, static_cast<int>(frames_default), nb, up, down, d_taps, per_phase, n_taps,
-                npr, fp.d_wave[s], wave_stride, static_cast<int>(n_target));
-        } else {
-            const dim3 grid(static_cast<unsigned>((n_target + 255) / 256), static_cast<unsigned>(nb));
-            sfx_resample_pcm16_kernel<false><<<grid, dim3(32, 8), 0, st>>>(
-                fp.d_pcm[s], pcm_stride, channels, dfr, static_cast<int>(frames_default), nb, up, down, d_taps, per_phase, n_taps,
-                npr, fp.d_wave[s], wave_stride, static_cast<int>(n_target));
-        }
+        // 32-bit index arithmetic when (frames + taps) * up and (n_target + n_pre_remove) * down stay below 2^31
+        const bool wide = flt && ((max_frames + 2) * up + n_taps >= (1ll << 31) || (n_target + npr + 2) * static_cast<long long>(down) >= (1ll << 31));
+        const dim3 grid_rows(static_cast<unsigned>((n_target + 31) / 32), static_cast<unsigned>((nb + kRsClips - 1) / kRsClips));
+        const dim3 grid_flat(static_cast<unsigned>((n_target + 255) / 256), static_cast<unsigned>(nb));
+        const bool rows = flt && flt->rows;
+#define SFX_RS_LAUNCH(R, W)                                                                                                  \
+    sfx_resample_pcm16_kernel<R, W><<<(R) ? grid_rows : grid_flat, dim3(32, 8), 0, st>>>(                                      \
+        fp.d_pcm[s], pcm_stride, channels, dfr, static_cast<int>(frames_default), nb, up, down, d_taps, per_phase, n_taps, npr, \
+        fp.d_wave[s], wave_stride, static_cast<int>(n_target))
+        if (rows && wide) SFX_RS_LAUNCH(true, true);
+        else if (rows) SFX_RS_LAUNCH(true, false);
+        else if (wide) SFX_RS_LAUNCH(false, true);
+        else SFX_RS_LAUNCH(false, false);
+#undef SFX_RS_LAUNCH
         FCK(cudaGetLastError());
         rc = sfx_extract(device, sr, fp.d_wave[s], wave_stride, nullptr, n_target, n_target, nb, n_mfcc, fp.d_out[s], out_w, fp.d_ws[s],
                          fp.ws_bytes, st);

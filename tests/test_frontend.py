@@ -40,7 +40,7 @@ def test_native_rate_filter_is_identity():
     assert np.array_equal(resample.resample_poly_direct(x, flt), x)
 
 
-def host_load_audio(pcm_row, frames, native, channels):
+def host_load_audio(pcm_row, frames, native, channels, DUR=DUR):
     """What preprocessing.audio_preprocessing.load_audio does to a decoded PCM16 file (reference :12-19 + resample_poly)."""
     from scipy.signal import resample_poly
     x = pcm_row[:frames * channels].astype(np.float32) / np.float32(32768.0)
@@ -84,6 +84,21 @@ def test_device_front_end_equals_host_load_audio(ex, native, channels):
     assert np.array_equal(ex.preprocess_pcm16(pcm, frames, native, channels=channels, duration=DUR, chunk_clips=4), ref)
     pinned = torch.from_numpy(pcm).pin_memory()
     assert np.array_equal(ex.preprocess_pcm16(pinned.numpy(), frames, native, channels=channels, duration=DUR), ref)
+
+
+@pytest.mark.gpu
+def test_device_front_end_long_clip_uses_64_bit_indices(ex):
+    """30 s at 24 414 Hz: frames * up exceeds 2^31, so the kernel switches to 64-bit index arithmetic; same bits as the host."""
+    native, dur = 24414, 30
+    rng = np.random.default_rng(9)
+    frames = np.array([native * dur + 500, native * 11], dtype=np.int32)
+    pcm = np.zeros((2, int(frames.max())), dtype=np.int16)
+    for i in range(2):
+        y = synth.make_clip(synth.KINDS[i], int(frames[i]), rng)
+        pcm[i, :frames[i]] = np.clip(np.round(y * 32767.0), -32768, 32767).astype(np.int16)
+    got = ex.preprocess_pcm16(pcm, frames, native, duration=dur)
+    waves = np.stack([host_load_audio(pcm[i], int(frames[i]), native, 1, DUR=dur) for i in range(2)])
+    assert np.array_equal(got, ex.extract_host(waves))
 
 
 @pytest.mark.gpu
