@@ -21,9 +21,8 @@ constexpr int kStreams = 2;
 
 struct Filter {                 // device copy of one (up, down) filter
     int up = 0, down = 0, n_taps = 0, n_pre_remove = 0;
-    bool rows = false;          // large up: taps regrouped by phase
     int per_phase = 0;          // K = ceil(n_taps / up)
-    double* d_taps = nullptr;   // rows ? [up][K] (row p = taps p, p + up, p + 2 up, ..., zero padded) : [n_taps]
+    double* d_taps = nullptr;   // [K][up], output-major: [k][r] = tap r' + k * up of the phase r' of outputs m = r (mod up)
 };
 
 struct FrontPath {
@@ -80,35 +79,34 @@ bool pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
-// One thread per output sample; two tap layouts / block shapes, chosen by the size of `up`:
-//   kRows = false (up <= 1024, e.g. 48 kHz -> 22.05 kHz, up = 147): taps in scipy's flat order.  For a given tap number
-//       the 32 lanes of a warp (consecutive outputs) differ only in their phase, so they read inside one window of `up`
-//       doubles -- a few cache lines of an L1-resident table.  Block = 256 consecutive outputs of one clip.
-//   kRows = true (large up, e.g. TESS's 24 414 Hz -> 22 050 Hz, up = 3675, a 700 KB table): taps regrouped into one
-//       contiguous row per phase, so a thread streams 2-3 lines instead of one per tap; block = 32 consecutive outputs
-//       (threadIdx.x) of 8 clips (threadIdx.y): output m has the same phase in every clip, so seven of the eight warps
-//       find the rows in L1.
+// One thread per output sample, a block = 256 consecutive outputs of one clip.  Output m uses the taps of phase
+// ((m + n_pre_remove) * down) % up, which depends on m % up only, so the filter is stored "output-major":
+// tab[k][r] = tap number k of the phase that outputs m = r (mod up) use.  For a given k the 32 lanes of a warp then read 32
+// consecutive doubles (and nearly consecutive samples), whatever `up` is -- 147 for 48 kHz -> 22.05 kHz or 3675 for
+// TESS's 24 414 Hz.  Sample i = q - k pairs with tab[k][r] (q = (m + n_pre_remove) * down / up); k runs downwards so that
+// the sum runs over ascending i like scipy's.  Taps past the end of the filter are stored as zeros: adding x * 0 does
+// not change the float64 sum, so every thread runs the same K steps.
 // Exactness: a sample is k * 2^-15 (mono) or (k_l + k_r) * 2^-16 (stereo mean, exact in float32), so summing
-// round(k * h) and scaling the total by the power of two reproduces, rounding for rounding, scipy's sum of round(x * h)
-// over ascending i; the integer k converts to float64 in one instruction.
-constexpr int kRsClips = 8;
-// kWide = false: every index product fits 31 bits (checked on the host), so the three divisions per output are 32-bit
-template <bool kRows, bool kWide>
+// round(k * h) and scaling the total by the power of two reproduces, rounding for rounding, scipy's sum of round(x * h);
+// the integer converts to float64 in one instruction.
+// kWide = false: every index product fits 31 bits (checked on the host), so the divisions are 32-bit.
+template <bool kWide>
 __global__ void __launch_bounds__(256) sfx_resample_pcm16_kernel(
     const int16_t* __restrict__ pcm, const long long row_stride, const int channels, const int32_t* __restrict__ frames,
-    const int frames_default, const int B, const int up, const int down, const double* __restrict__ taps,
-    const int per_phase, const int n_taps, const int n_pre_remove, float* __restrict__ wave, const long long wave_stride,
-    const int n_target) {
-    const int b = kRows ? blockIdx.y * kRsClips + threadIdx.y : blockIdx.y;
-    const int m = kRows ? blockIdx.x * 32 + threadIdx.x : blockIdx.x * 256 + threadIdx.y * 32 + threadIdx.x;
-    if (b >= B || m >= n_target) return;
+    const int frames_default, const int up, const int down, const double* __restrict__ tab, const int per_phase,
+    const int n_pre_remove, float* __restrict__ wave, const long long wave_stride, const int n_target) {
+    const int b = blockIdx.y;
+    const int m = blockIdx.x * 256 + threadIdx.x;
+    if (m >= n_target) return;
     const int n_in = frames ? frames[b] : frames_default;
     const int16_t* x = pcm + static_cast<long long>(b) * row_stride;
     float* y = wave + static_cast<long long>(b) * wave_stride;
-    auto ksum = [&](long long i) -> int {                     // integer numerator of the (mono-mixed) sample
-        return channels == 1 ? static_cast<int>(x[i]) : static_cast<int>(x[2 * i]) + static_cast<int>(x[2 * i + 1]);
-    };
     const double scale = channels == 1 ? 1.0 / 32768.0 : 1.0 / 65536.0;
+    auto ksum = [&](int i) -> int {                           // integer numerator of the (mono-mixed) sample
+        if (channels == 1) return static_cast<int>(x[i]);
+        const int v = reinterpret_cast<const int*>(x)[i];     // one 32-bit load per stereo frame (rows are 4-byte aligned)
+        return static_cast<int>(static_cast<short>(v & 0xffff)) + (v >> 16);
+    };
     if (n_in <= 0) { y[m] = 0.0f; return; }
     if (up == down) {                                   // native rate: no filter (resample_poly returns a copy)
         y[m] = m < n_in ? static_cast<float>(static_cast<double>(ksum(m)) * scale) : 0.0f;
@@ -117,28 +115,29 @@ __global__ void __launch_bounds__(256) sfx_resample_pcm16_kernel(
     using idx_t = std::conditional_t<kWide, long long, int>;
     const idx_t n_out = (static_cast<idx_t>(n_in) * up + down - 1) / down;
     if (m >= n_out) { y[m] = 0.0f; return; }
-    const idx_t t0 = (static_cast<idx_t>(m) + n_pre_remove) * down;
-    idx_t lo = t0 - (n_taps - 1);
-    lo = lo > 0 ? (lo + up - 1) / up : 0;
-    const idx_t q = t0 / up;
-    const idx_t hi = q > n_in - 1 ? n_in - 1 : q;
-    // tap of sample i is h[t0 - i*up] = rows[t0 % up][q - i]; either way the sum runs over ascending i like scipy's
-    const double* h = kRows ? taps + static_cast<long long>(t0 - q * up) * per_phase + (q - lo) : taps + (t0 - lo * up);
-    const int hstep = kRows ? 1 : up;
-    const int cnt = static_cast<int>(hi - lo + 1);
+    const int q = static_cast<int>((static_cast<idx_t>(m) + n_pre_remove) * down / up);
+    const double* t = tab + static_cast<size_t>(per_phase - 1) * up + m % up;
     double acc = 0.0;
-    if (channels == 1) {
-        const int16_t* xs = x + lo;
+    const int i0 = q - (per_phase - 1);                 // sample of the first step
+    if (i0 >= 0 && q < n_in) {                          // interior output: all K samples exist, no per-step checks
+        if (channels == 1) {
+            const int16_t* xs = x + i0;
 #pragma unroll 4
-        for (int k = 0; k < cnt; ++k)
-            acc = __dadd_rn(acc, __dmul_rn(static_cast<double>(static_cast<int>(xs[k])), __ldg(h - k * hstep)));
+            for (int j = 0; j < per_phase; ++j)
+                acc = __dadd_rn(acc, __dmul_rn(static_cast<double>(static_cast<int>(xs[j])), __ldg(t - static_cast<size_t>(j) * up)));
+        } else {
+            const int* xs = reinterpret_cast<const int*>(x) + i0;
+#pragma unroll 4
+            for (int j = 0; j < per_phase; ++j) {
+                const int v = xs[j];
+                const int ks = static_cast<int>(static_cast<short>(v & 0xffff)) + (v >> 16);
+                acc = __dadd_rn(acc, __dmul_rn(static_cast<double>(ks), __ldg(t - static_cast<size_t>(j) * up)));
+            }
+        }
     } else {
-        const int* xs = reinterpret_cast<const int*>(x) + lo;             // one 32-bit load per stereo frame
-#pragma unroll 4
-        for (int k = 0; k < cnt; ++k) {
-            const int v = xs[k];
-            const int ks = static_cast<int>(static_cast<short>(v & 0xffff)) + (v >> 16);
-            acc = __dadd_rn(acc, __dmul_rn(static_cast<double>(ks), __ldg(h - k * hstep)));
+        for (int j = 0; j < per_phase; ++j, t -= up) {
+            const int i = i0 + j;
+            if (i >= 0 && i < n_in) acc = __dadd_rn(acc, __dmul_rn(static_cast<double>(ksum(i)), __ldg(t)));
         }
     }
     y[m] = static_cast<float>(acc * scale);
@@ -223,10 +222,14 @@ int sfx_preprocess_host_pcm16(int device, int32_t sr, const sfx_resampler_host* 
             Filter f;
             f.up = up; f.down = down; f.n_taps = rs->n_taps; f.n_pre_remove = rs->n_pre_remove;
             f.per_phase = (f.n_taps + up - 1) / up;
-            f.rows = up > 1024;
-            std::vector<double> poly(f.rows ? static_cast<size_t>(up) * f.per_phase : static_cast<size_t>(f.n_taps), 0.0);
-            for (int t = 0; t < f.n_taps; ++t)
-                poly[f.rows ? static_cast<size_t>(t % up) * f.per_phase + t / up : static_cast<size_t>(t)] = rs->taps[t];
+            std::vector<double> poly(static_cast<size_t>(up) * f.per_phase, 0.0);
+            for (int r = 0; r < up; ++r) {
+                const long long phase = (static_cast<long long>(r) + f.n_pre_remove) * down % up;
+                for (int k = 0; k < f.per_phase; ++k) {
+                    const long long tap = phase + static_cast<long long>(k) * up;
+                    if (tap < f.n_taps) poly[static_cast<size_t>(k) * up + r] = rs->taps[tap];
+                }
+            }
             FCK(cudaMalloc(&f.d_taps, sizeof(double) * poly.size()));
             FCK(cudaMemcpy(f.d_taps, poly.data(), sizeof(double) * poly.size(), cudaMemcpyHostToDevice));
             fp.filters.push_back(f);
@@ -265,21 +268,18 @@ int sfx_preprocess_host_pcm16(int device, int32_t sr, const sfx_resampler_host* 
             dfr = fp.d_frames[s];
         }
         const double* d_taps = flt ? flt->d_taps : nullptr;
-        const int per_phase = flt ? flt->per_phase : 0, n_taps = flt ? flt->n_taps : 0, npr = flt ? flt->n_pre_remove : 0;
-        // 32-bit index arithmetic when (frames + taps) * up and (n_target + n_pre_remove) * down stay below 2^31
-        const bool wide = flt && ((max_frames + 2) * up + n_taps >= (1ll << 31) || (n_target + npr + 2) * static_cast<long long>(down) >= (1ll << 31));
-        const dim3 grid_rows(static_cast<unsigned>((n_target + 31) / 32), static_cast<unsigned>((nb + kRsClips - 1) / kRsClips));
-        const dim3 grid_flat(static_cast<unsigned>((n_target + 255) / 256), static_cast<unsigned>(nb));
-        const bool rows = flt && flt->rows;
-#define SFX_RS_LAUNCH(R, W)                                                                                                  \
-    sfx_resample_pcm16_kernel<R, W><<<(R) ? grid_rows : grid_flat, dim3(32, 8), 0, st>>>(                                      \
-        fp.d_pcm[s], pcm_stride, channels, dfr, static_cast<int>(frames_default), nb, up, down, d_taps, per_phase, n_taps, npr, \
-        fp.d_wave[s], wave_stride, static_cast<int>(n_target))
-        if (rows && wide) SFX_RS_LAUNCH(true, true);
-        else if (rows) SFX_RS_LAUNCH(true, false);
-        else if (wide) SFX_RS_LAUNCH(false, true);
-        else SFX_RS_LAUNCH(false, false);
-#undef SFX_RS_LAUNCH
+        const int per_phase = flt ? flt->per_phase : 0, npr = flt ? flt->n_pre_remove : 0;
+        // 32-bit index arithmetic when frames * up and (n_target + n_pre_remove) * down stay below 2^31
+        const bool wide = flt && ((max_frames + 2) * up + down >= (1ll << 31) || (n_target + npr + 2) * static_cast<long long>(down) >= (1ll << 31));
+        const dim3 grid(static_cast<unsigned>((n_target + 255) / 256), static_cast<unsigned>(nb));
+        if (wide)
+            sfx_resample_pcm16_kernel<true><<<grid, 256, 0, st>>>(fp.d_pcm[s], pcm_stride, channels, dfr, static_cast<int>(frames_default),
+                                                                  up, down, d_taps, per_phase, npr, fp.d_wave[s], wave_stride,
+                                                                  static_cast<int>(n_target));
+        else
+            sfx_resample_pcm16_kernel<false><<<grid, 256, 0, st>>>(fp.d_pcm[s], pcm_stride, channels, dfr, static_cast<int>(frames_default),
+                                                                   up, down, d_taps, per_phase, npr, fp.d_wave[s], wave_stride,
+                                                                   static_cast<int>(n_target));
         FCK(cudaGetLastError());
         rc = sfx_extract(device, sr, fp.d_wave[s], wave_stride, nullptr, n_target, n_target, nb, n_mfcc, fp.d_out[s], out_w, fp.d_ws[s],
                          fp.ws_bytes, st);
