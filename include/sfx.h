@@ -96,10 +96,10 @@ size_t      sfx_workspace_bytes(int device, int64_t max_samples);
  * clips are processed longest first; split pipeline: 3 per chunk of <= 1024 clips). */
 int         sfx_launches_per_extract(void);
 
-/* Pipeline selection: 0 = auto (default: the frame-parallel two-kernel pipeline for batches <= 256 clips, where it has
- * about half the latency, the fused persistent kernel above that, where it has the higher throughput), 1 = fused,
- * 2 = split.  Also settable through the environment variable SFX_PIPELINE=auto|fused|split before the first call.
- * Call sfx_workspace_bytes again after changing the mode. */
+/* Pipeline selection: 0 = auto (default: the frame-parallel two-kernel pipeline for batches that fit one chunk of at most
+ * 1024 clips -- 256 for ragged batches --, where it has the lower latency and, up to ~1000 clips, the higher throughput; the
+ * fused persistent kernel above that), 1 = fused, 2 = split.  Also settable through the environment variable
+ * SFX_PIPELINE=auto|fused|split before the first call.  Call sfx_workspace_bytes again after changing the mode. */
 int         sfx_set_pipeline(int mode);
 
 /* Batched extraction, device buffers.

@@ -58,14 +58,21 @@ thread_local int g_last_launches = 1;
 
 // Pipeline choice: 0 = auto (split for small batches, fused otherwise), 1 = fused, 2 = split.
 // Initial value from the environment variable SFX_PIPELINE (auto | fused | split); sfx_set_pipeline() overrides it.
-constexpr int kAutoSplitMaxB = 256;      // at or below this batch the frame-parallel split pipeline has lower latency
+// Auto mode uses the frame-parallel split pipeline when the whole batch fits one chunk and has at most this many clips:
+// measured on 3 s clips (tools/batch_sweep.py) it is 4-15 % faster than the fused kernel up to 1 024 clips (0.65 vs 0.69 ms)
+// and slower from 1 440 on.  Ragged batches switch at 256: a few very long clips serialise its per-chunk kernels.
+constexpr int kAutoSplitMaxB = 1024;
+constexpr int kAutoSplitMaxBRagged = 256;
 int g_pipeline = [] {
     const char* e = std::getenv("SFX_PIPELINE");
     if (e && std::strcmp(e, "split") == 0) return 2;
     if (e && std::strcmp(e, "fused") == 0) return 1;
     return 0;
 }();
-bool use_split(int B) { return g_pipeline == 2 || (g_pipeline == 0 && B <= kAutoSplitMaxB); }
+bool use_split(int B, bool ragged, size_t chunk_cap) {
+    if (g_pipeline != 0) return g_pipeline == 2;
+    return B <= (ragged ? kAutoSplitMaxBRagged : kAutoSplitMaxB) && static_cast<size_t>(B) <= chunk_cap;
+}
 
 // clips per chunk of the split pipeline: at most kSplitChunkMax, at most ~1 GiB of slices
 int split_chunk_for(size_t slice) {
@@ -151,11 +158,14 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
     p.max_pk = c.max_pk;
     if (dbg) p.dbg = *dbg;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (use_split(B)) {
-        const size_t slice = sfx::split_slice_bytes(Tmax, c.max_pk);
+    const size_t split_slice = sfx::split_slice_bytes(Tmax, c.max_pk);
+    const size_t split_cap = ws_bytes > sfx::kSplitHeader
+                                 ? std::min<size_t>(split_chunk_for(split_slice), (ws_bytes - sfx::kSplitHeader) / split_slice) : 0;
+    if (use_split(B, lengths != nullptr, split_cap)) {
+        const size_t slice = split_slice;
         if (ws_bytes < sfx::kSplitHeader + slice)
             return fail(SFX_ERR_WORKSPACE, "workspace smaller than sfx_workspace_bytes(device, max_samples)");
-        const int chunk = static_cast<int>(std::min<size_t>(split_chunk_for(slice), (ws_bytes - sfx::kSplitHeader) / slice));
+        const int chunk = static_cast<int>(split_cap);
         p.cta_scratch_bytes = static_cast<long long>(slice);
         int launches = 0;
         for (int c0 = 0; c0 < B; c0 += chunk) {
