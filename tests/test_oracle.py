@@ -99,6 +99,27 @@ def test_filterbanks_against_independent_ports():
     assert np.allclose(lp.power_to_db(x), au.power_to_db(x, reference=1.0, min_value=1e-10, db_range=80.0), atol=1e-5)
 
 
+def test_stft_and_centroid_against_torch():
+    """Independent implementations of the framing / FFT and of the centroid formula: torch.stft with the same centring and
+    zero padding, and torchaudio's spectral_centroid (reflect-padded, so only interior frames are comparable)."""
+    torch = pytest.importorskip("torch")
+    torchaudio = pytest.importorskip("torchaudio")
+    y = synth.make_batch(2, 40000, seed=9)
+    win = torch.hann_window(2048, periodic=True, dtype=torch.float64)
+    for clip in y:
+        X = lp.stft(clip)
+        Xt = torch.stft(torch.from_numpy(clip).double(), n_fft=2048, hop_length=512, win_length=2048, window=win, center=True,
+                        pad_mode="constant", return_complex=True).numpy()
+        assert X.shape == Xt.shape
+        assert np.abs(X - Xt).max() < 2e-6 * np.abs(Xt).max()
+        c = lp.spectral_centroid(clip)[0]
+        ct = torchaudio.functional.spectral_centroid(torch.from_numpy(clip), SR, pad=0, window=win.float(), n_fft=2048,
+                                                     hop_length=512, win_length=2048).numpy()
+        assert c.shape == ct.shape
+        inner = slice(3, len(c) - 3)
+        assert np.abs(c[inner] - ct[inner]).max() < 1e-3 * np.abs(c[inner]).max()
+
+
 def test_frame_count_and_dtype_trail():
     for n in (11025, 66150, 81585):
         X = lp.stft(np.zeros(n, dtype=np.float32))
