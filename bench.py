@@ -219,6 +219,9 @@ def main():
     ap.add_argument("--clips", type=int, default=65536, help="resident clips per GPU per step")
     ap.add_argument("--e2e-clips", type=int, default=4096, help="clips per GPU per end-to-end (host buffer) step")
     ap.add_argument("--no-allgather", action="store_true")
+    ap.add_argument("--allgather", choices=["overlap", "serial"], default="serial",
+                    help="serial (default): the all-gather is waited for inside its step; overlap: step i's all-gather runs under "
+                         "step i+1's extraction (its polling NCCL CTAs can delay the persistent extraction kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -272,6 +275,8 @@ def main():
         ex.extract(pool, out=outs[b])
         if do_gather:
             _, works[b] = gather_feature_cache(outs[b], n_total, out=caches[b], async_op=True)
+            if args.allgather == "serial":
+                works[b].wait()
 
     def drain():
         for b in range(2):
@@ -303,6 +308,8 @@ def main():
         k1[i].record()
         if do_gather:
             _, works[b] = gather_feature_cache(outs[b], n_total, out=caches[b], async_op=True)
+            if args.allgather == "serial":
+                works[b].wait()
     drain()                                   # the timed region ends when every step's cache is complete
     e1.record()
     barrier()
@@ -440,7 +447,8 @@ def main():
             "config": {"workload": "configs[3]: 1M x 3 s clips @22.05 kHz, clip-sharded; resident pool per GPU per step",
                        "clips_per_gpu_per_step": B, "n_samples": N_SAMPLES, "frames_per_clip": 1 + N_SAMPLES // 512,
                        "signal_mix": list(KINDS), "allgather_feature_cache": do_gather,
-                       "allgather_overlap": "step i's all-gather runs under step i+1's extraction" if do_gather else None,
+                       "allgather_overlap": (("step i's all-gather runs under step i+1's extraction" if args.allgather == "overlap"
+                                             else "serial: waited for inside its step") if do_gather else None),
                        "l2": f"inputs larger than L2 ({B * N_SAMPLES * 4 / 1e9:.1f} GB per GPU per step)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": Be * N_SAMPLES * 4,
