@@ -69,6 +69,32 @@ def test_load_audio_pad_trim_and_mono(tmp_path):
         ap.load_audio(os.path.join(tmp_path, "bad.wav"))
 
 
+def test_raw_pcm16_reader_selects_only_16_bit_mono_or_stereo(tmp_path):
+    """preprocess_audio_batch hands raw frames to the device only for 16-bit PCM mono/stereo files; anything else goes
+    through load_audio's host decoder."""
+    import wave
+    from preprocessing import audio_preprocessing as ap
+    rng = np.random.default_rng(2)
+    x = rng.integers(-30000, 30000, size=(500, 2)).astype("<i2")
+    cases = {"m16": (1, 2, x[:, 0].tobytes()), "s16": (2, 2, x.tobytes()), "m8": (1, 1, (x[:, 0] // 256 + 128).astype("u1").tobytes())}
+    for name, (ch, width, payload) in cases.items():
+        with wave.open(str(tmp_path / f"{name}.wav"), "wb") as wf:
+            wf.setnchannels(ch); wf.setsampwidth(width); wf.setframerate(24414)
+            wf.writeframes(payload)
+    raw, ch, rate = ap._read_wav_pcm16(str(tmp_path / "m16.wav"))
+    assert ch == 1 and rate == 24414 and np.array_equal(raw, x[:, 0])
+    raw, ch, rate = ap._read_wav_pcm16(str(tmp_path / "s16.wav"))
+    assert ch == 2 and np.array_equal(raw.reshape(-1, 2), x)
+    assert ap._read_wav_pcm16(str(tmp_path / "m8.wav")) is None
+    (tmp_path / "junk.wav").write_bytes(b"not a wav")
+    with pytest.raises(ValueError):
+        ap._read_wav_pcm16(str(tmp_path / "junk.wav"))
+    # the host decoder agrees with the raw reader on the 16-bit files (x / 32768, channel mean)
+    a, sr = ap.load_audio(str(tmp_path / "s16.wav"), sr=24414, duration=1)
+    ref = (x.astype(np.float32) / np.float32(32768.0)).mean(axis=1, dtype=np.float32)
+    assert sr == 24414 and np.array_equal(a[:500], ref) and not a[500:].any()
+
+
 def test_shard_ranges_cover_exactly():
     for n, w in ((1_000_000, 8), (1440, 4), (7, 8), (0, 2), (64, 1)):
         ranges = [shard.shard_range(n, w, r) for r in range(w)]
