@@ -110,7 +110,8 @@ int         sfx_set_pipeline(int mode);
  *               [mfcc_0..n_mfcc-1 | chroma C..B | zcr, centroid_Hz, rolloff_Hz, rms]
  *   workspace   >= sfx_workspace_bytes(device, max length in the batch)
  *   stream      cudaStream_t (NULL = legacy default stream)
- * A clip with length <= 0 yields a row of NaN (the host wrapper raises, as librosa would).
+ * A clip with length <= 0 or > max_samples yields a row of NaN (the host wrapper raises, as librosa would); lengths are
+ * read on the device, so they are not validated by the call itself.
  */
 int         sfx_extract(int device, int32_t sr, const float *wave, int64_t row_stride, const int32_t *lengths,
                         int64_t n_default, int64_t max_samples, int32_t B, int32_t n_mfcc,

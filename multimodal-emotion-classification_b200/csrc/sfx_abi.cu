@@ -152,7 +152,7 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
     sfx::Params p{};
     p.wave = wave; p.row_stride = row_stride; p.lengths = lengths; p.n_default = n_default;
     p.B = B; p.n_mfcc = n_mfcc; p.out = out; p.out_stride = out_stride;
-    p.ws = static_cast<unsigned char*>(ws); p.Tmax = Tmax;
+    p.ws = static_cast<unsigned char*>(ws); p.Tmax = Tmax; p.max_samples = max_samples;
     p.aligned8 = ((reinterpret_cast<uintptr_t>(wave) & 7u) == 0 && (row_stride & 1) == 0) ? 1 : 0;
     p.tb = ts->tb;
     p.max_pk = c.max_pk;
@@ -253,6 +253,7 @@ int extract_host_impl(int device, int32_t sr, const S* host_wave, int64_t row_st
     }
     int nchunks = (B + chunk - 1) / chunk;
     int launches_total = 0;
+    sfx::QuiesceOnError<kHostStreams> quiesce{hp.stream};
     std::vector<int> pend_c0(kHostStreams, -1), pend_nb(kHostStreams, 0);
     auto drain = [&](int s) -> int {      // copy a finished chunk's rows out of pinned staging
         if (pend_c0[s] < 0) return SFX_OK;
@@ -311,6 +312,7 @@ int extract_host_impl(int device, int32_t sr, const S* host_wave, int64_t row_st
         int rc = drain(s);
         if (rc) return rc;
     }
+    quiesce.armed = false;
     g_last_launches = launches_total;
     return SFX_OK;
 }

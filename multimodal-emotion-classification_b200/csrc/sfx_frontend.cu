@@ -248,6 +248,7 @@ int sfx_preprocess_host_pcm16(int device, int32_t sr, const sfx_resampler_host* 
         return SFX_OK;
     };
     const size_t row_bytes = static_cast<size_t>(max_frames) * channels * 2;
+    sfx::QuiesceOnError<kStreams> quiesce{fp.stream};
     for (int ci = 0; ci < nchunks; ++ci) {
         const int s = ci % kStreams;
         const int c0 = ci * chunk, nb = std::min(chunk, B - c0);
@@ -297,6 +298,7 @@ int sfx_preprocess_host_pcm16(int device, int32_t sr, const sfx_resampler_host* 
         int rc = drain(s);
         if (rc) return rc;
     }
+    quiesce.armed = false;
     return SFX_OK;
 }
 

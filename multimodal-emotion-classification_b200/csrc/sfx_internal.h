@@ -56,12 +56,21 @@ struct Params {
     unsigned char* ws;
     long long cta_scratch_bytes;
     int Tmax;
+    long long max_samples;  // the scratch slices hold 1 + max_samples / hop frames per clip
     int aligned8;
     int max_pk;             // peak records per frame the scratch slice is sized for
     const int* order;       // clip processed q-th by the queue (ragged batches: longest first), nullptr = q
     DevTables tb;
     sfx_debug_out dbg;
 };
+
+// Samples of a clip.  A device-side length outside [1, max_samples] gives 0 and the clip gets a NaN row: its frames would
+// not fit the scratch slice and its samples would be read past the row.
+__device__ __forceinline__ long long clip_samples(const Params& p, int clip) {
+    if (!p.lengths) return p.n_default;
+    const long long n = p.lengths[clip];
+    return n > p.max_samples ? 0 : n;
+}
 
 __host__ __device__ inline int rec_frames(int Tmax) { return (Tmax + kWarps - 1) / kWarps * kWarps; }
 
@@ -100,5 +109,19 @@ cudaError_t launch_split_chunk(const SplitParams& q, int grid_frames, int grid_c
 cudaError_t configure_kernels(int* blocks_per_sm);
 cudaError_t launch_extract(const Params& p, int grid, bool debug, cudaStream_t stream);
 cudaError_t launch_order(const int32_t* lengths, int B, int* order, cudaStream_t stream);
+
+// Host pipelines (sfx_extract_host*, sfx_preprocess_host_pcm16): on an early error return the pipeline's streams are drained,
+// so that no copy is left in flight that still targets the caller's host buffers.
+template <int N>
+struct QuiesceOnError {
+    cudaStream_t* streams;
+    bool armed = true;
+    ~QuiesceOnError() {
+        if (!armed) return;
+        for (int s = 0; s < N; ++s)
+            if (streams[s]) cudaStreamSynchronize(streams[s]);
+        cudaGetLastError();
+    }
+};
 
 }  // namespace sfx

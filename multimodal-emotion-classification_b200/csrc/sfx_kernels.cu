@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         __syncthreads();
         if (s_i[0] >= p.B) break;
         const int clip = p.order ? p.order[s_i[0]] : s_i[0];
-        const long long n = p.lengths ? static_cast<long long>(p.lengths[clip]) : p.n_default;
+        const long long n = clip_samples(p, clip);
         float* out = p.out + static_cast<long long>(clip) * p.out_stride;
         if (n <= 0) {
             for (int i = tid; i < p.n_mfcc + 16; i += kThreads) out[i] = __int_as_float(0x7fc00000);

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(1024) sfx_prep_kernel(const SplitParams q) {
     if (c < q.nclips) npk[c] = 0;
     int T = 0;
     if (c < q.nclips) {
-        const long long n = q.p.lengths ? static_cast<long long>(q.p.lengths[q.chunk0 + c]) : q.p.n_default;
+        const long long n = clip_samples(q.p, q.chunk0 + c);
         T = n > 0 ? 1 + static_cast<int>(n / kHop) : 0;
     }
     int inc = T;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_frames_kernel(const SplitPara
         }
         const int t = item - (q.T_uniform > 0 ? c * q.T_uniform : off[c]);
         const int clip = q.chunk0 + c;
-        const long long n = p.lengths ? static_cast<long long>(p.lengths[clip]) : p.n_default;
+        const long long n = clip_samples(p, clip);
         const int T = 1 + static_cast<int>(n / kHop);
         const float* x = p.wave + static_cast<long long>(clip) * p.row_stride;
         const Slice sl = slice_of(p.ws + kSplitHeader + static_cast<size_t>(c) * p.cta_scratch_bytes, p.Tmax, p.max_pk);
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_clips_kernel(const SplitParam
         const int c = s_i[0];
         if (c >= q.nclips) break;
         const int clip = q.chunk0 + c;
-        const long long n = p.lengths ? static_cast<long long>(p.lengths[clip]) : p.n_default;
+        const long long n = clip_samples(p, clip);
         float* out = p.out + static_cast<long long>(clip) * p.out_stride;
         if (n <= 0) {
             for (int i = tid; i < p.n_mfcc + 16; i += kThreads) out[i] = __int_as_float(0x7fc00000);

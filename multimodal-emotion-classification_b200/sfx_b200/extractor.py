@@ -140,7 +140,6 @@ class SpeechFeatureExtractor:
         self.launches += self.lib.sfx_launches_per_extract()      # summed over the call's chunks by the library
         return out
 
-
     def preprocess_pcm16(self, pcm: np.ndarray, frames: np.ndarray | None, native_sr: int, channels: int = 1,
                          duration: float = 3, n_mfcc: int = 40, out: np.ndarray | None = None,
                          chunk_clips: int = 0) -> np.ndarray:
@@ -186,7 +185,9 @@ def get_extractor(device=None, sr: int = 22050) -> SpeechFeatureExtractor:
     """Process-wide cache: one extractor per (device index, sr)."""
     if not torch.cuda.is_available():
         raise NoCudaDeviceError("sfx_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
-    idx = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    idx = None if device is None else torch.device(device).index      # "cuda" without an index = the current device
+    if idx is None:
+        idx = torch.cuda.current_device()
     key = (idx, int(sr))
     with _LOCK:
         ex = _EXTRACTORS.get(key)

@@ -117,6 +117,19 @@ def test_single_sample_and_bad_lengths(ex):
     assert np.isfinite(got[0]).all()                                # T = 1 frame
     assert_parity(got[:1], lp.features_batch(w[:1], lens[:1]))
     assert np.isnan(got[1:]).all()                                  # length <= 0 -> NaN row (host wrapper raises)
+    # a device-side length beyond the row (more frames than the scratch slice holds) is a NaN row as well, in either
+    # pipeline, and does not disturb its neighbours
+    w = synth.make_batch(6, 4096, seed=5)
+    lens = np.array([4096, 4097, 3000, 2**31 - 1, 4096, 100000], dtype=np.int32)
+    good = [0, 2, 4]
+    try:
+        for mode in (1, 2):
+            assert ex.lib.sfx_set_pipeline(mode) == 0
+            got = ex.extract(dev(w), dev(lens)).cpu().numpy()
+            assert np.isnan(got[[1, 3, 5]]).all()
+            assert_parity(got[good], lp.features_batch(w[good], lens[good]))
+    finally:
+        ex.lib.sfx_set_pipeline(0)
 
 
 def test_unaligned_rows_and_strided_batch(ex):
