@@ -25,7 +25,39 @@ for _p in (os.path.join(ROOT, "multimodal-emotion-classification_b200"), ROOT, o
 N_SAMPLES = 66150
 BYTES_PER_CLIP = 4 * N_SAMPLES + 56 * 4          # algorithmic bytes: waveform in + 56 floats out
 METRIC = "clips/sec (3 s @22.05 kHz -> 56-dim)"
+# algorithmic flops per STFT frame (SURVEY 8d's itemisation, DESIGN.md "Roofline"); FMA = 2 flops
+FLOPS_PER_FRAME = {
+    "hann window": 2048,
+    "1024-point complex FFT (5 N log2 N)": 51200,
+    "real-FFT unpack (512 conjugate pairs x 14)": 7168,
+    "|X|^2 and |X| (1025 bins x 4)": 4100,
+    "mel projection (2018 non-zeros x 2)": 4036,
+    "10 log10 (128 bands x 2)": 256,
+    "piptrack (358 bins x 8)": 2864,
+    "centroid and roll-off (1025 bins x 3)": 3075,
+    "rms and zero crossings (512 samples x 3)": 1536,
+    "chroma projection (12 x 1025 FMA)": 24600,       # runs on the tensor cores (FP16 hi/lo MMA), not on the FP32 pipes
+}
+FRAMES_PER_CLIP = 1 + N_SAMPLES // 512
+FLOPS_PER_CLIP = FRAMES_PER_CLIP * sum(FLOPS_PER_FRAME.values())
+FLOPS_PER_CLIP_FP32 = FLOPS_PER_CLIP - FRAMES_PER_CLIP * FLOPS_PER_FRAME["chroma projection (12 x 1025 FMA)"]
 KINDS = ("noise", "harmonic", "noise_tail", "harmonic_tail")
+
+
+def fp32_roofline(ex, clips_per_s_per_gpu):
+    """Second, compute-side roofline: the algorithmic FP32-pipe flop rate of the extraction kernel against the
+    FP32 FMA peak measured on this GPU by the library's register-only FFMA kernel (sfx_measure_fp32_peak)."""
+    import ctypes
+    tf = ctypes.c_double(0.0)
+    rc = ex.lib.sfx_measure_fp32_peak(ex.index, ctypes.byref(tf))
+    if rc != 0 or tf.value <= 0.0:
+        return None
+    achieved = clips_per_s_per_gpu * FLOPS_PER_CLIP_FP32 / 1e12
+    return {"bound": "fp32", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value,
+            "flops_per_clip_fp32": FLOPS_PER_CLIP_FP32, "flops_per_clip_total": FLOPS_PER_CLIP,
+            "note": "peak = FFMA micro-benchmark measured in this run (CUDA events, best of 3); achieved = algorithmic flops "
+                    "on the FP32 pipes (everything but the chroma contraction, which runs as FP16 hi/lo MMA) x clips/s of "
+                    "the timed kernel; supplementary to the HBM roofline BASELINE.json names"}
 
 
 # --------------------------------------------------------------------------------------------- CPU reference arm
@@ -461,6 +493,7 @@ def main():
                          "traffic": (traffic * B) if traffic else None,
                          "note": f"{peak_src}; algorithmic bytes/launch = {B} clips x {BYTES_PER_CLIP} B; kernel avg "
                                  f"{kern_ms:.3f} ms (CUDA events); path is FP32-issue/SMEM bound (DESIGN.md), not HBM bound"},
+            "roofline_fp32": fp32_roofline(ex, per_gpu),
             "cpu_baseline": cpu_baseline,
             "small_batch": small,
             "parity": parity,

@@ -168,6 +168,11 @@ int         sfx_frontend_release(int device);
 /* Release cached device buffers/tables of `device` (tests; process exit does it implicitly). */
 int         sfx_release(int device);
 
+/* Measurement helper: FP32 FMA throughput of `device` in TFLOP/s, from a register-only FFMA kernel timed
+ * with CUDA events on a private stream (best of three launches).  bench.py uses it as the compute denominator next to the
+ * HBM roofline; nothing on the extraction path calls it. */
+int         sfx_measure_fp32_peak(int device, double *tflops);
+
 /* ---- scope row f1: device-resident StandardScaler + speech DNN forward ------------------------------------------
  * Consumer of the feature rows in the reference's inference/speech_inference.py:66-76 (scaler.transform + model.predict)
  * and :85-105 (layers[-3] tap); architecture of model_training/train_speech_model.py:55-90.  FP32 kernels. */

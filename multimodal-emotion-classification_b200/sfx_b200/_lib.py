@@ -46,7 +46,8 @@ class DnnHost(C.Structure):
 EXPORTS = ["sfx_dnn_create", "sfx_dnn_destroy", "sfx_dnn_workspace_bytes", "sfx_dnn_launches_per_forward",
            "sfx_dnn_last_error", "sfx_dnn_forward", "sfx_abi_version", "sfx_last_error", "sfx_device_count", "sfx_init_tables", "sfx_workspace_bytes",
            "sfx_launches_per_extract", "sfx_set_pipeline", "sfx_extract", "sfx_extract_debug", "sfx_extract_host", "sfx_extract_host_pcm16",
-           "sfx_preprocess_host_pcm16", "sfx_frontend_last_error", "sfx_frontend_release", "sfx_release"]
+           "sfx_preprocess_host_pcm16", "sfx_frontend_last_error", "sfx_frontend_release", "sfx_release",
+           "sfx_measure_fp32_peak"]
 
 
 def lib_path() -> str:
@@ -90,6 +91,8 @@ def load():
     lib.sfx_frontend_release.argtypes = [C.c_int]
     lib.sfx_release.restype = C.c_int
     lib.sfx_release.argtypes = [C.c_int]
+    lib.sfx_measure_fp32_peak.restype = C.c_int
+    lib.sfx_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.sfx_set_pipeline.restype = C.c_int
     lib.sfx_set_pipeline.argtypes = [C.c_int]
     lib.sfx_dnn_create.restype = C.c_int

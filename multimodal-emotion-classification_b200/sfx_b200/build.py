@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB_PATH = os.path.join(HERE, "libsfx_b200.so")
-SOURCES = ["sfx_kernels.cu", "sfx_split.cu", "sfx_abi.cu", "sfx_dnn.cu", "sfx_frontend.cu"]
+SOURCES = ["sfx_kernels.cu", "sfx_split.cu", "sfx_abi.cu", "sfx_dnn.cu", "sfx_frontend.cu", "sfx_peak.cu"]
 HEADERS = ["sfx_internal.h", "sfx_device.cuh", "sfx_phases.cuh", os.path.join("..", "..", "include", "sfx.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "550"]

@@ -55,6 +55,8 @@ def test_no_cpu_fallback():
     pcm = np.zeros((1, 66150), dtype=np.int16)
     rc = lib.sfx_extract_host_pcm16(0, 22050, pcm.ctypes.data, 66150, None, 66150, 1, 40, out.ctypes.data, 56, 0)
     assert rc == -3 and not out.any()
+    tf = ctypes.c_double(-1.0)
+    assert lib.sfx_measure_fp32_peak(0, ctypes.byref(tf)) == -2 and tf.value == 0.0      # SFX_ERR_CUDA, nothing measured
     from preprocessing.audio_preprocessing import extract_mfcc
     with pytest.raises(NoCudaDeviceError):
         extract_mfcc(np.zeros(66150, dtype=np.float32), 22050)

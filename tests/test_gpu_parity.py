@@ -37,6 +37,14 @@ def test_native_library_is_loaded(ex):
     assert ex.lib.sfx_device_count() >= 1 and ex.lib.sfx_launches_per_extract() >= 1
 
 
+def test_fp32_peak_helper_measures_a_plausible_rate(ex):
+    """bench.py's compute denominator: a B200 has 148 SMs x 128 FP32 lanes x 2 flop at <= 2.1 GHz = 79.6 TFLOP/s."""
+    import ctypes
+    tf = ctypes.c_double(0.0)
+    assert ex.lib.sfx_measure_fp32_peak(ex.index, ctypes.byref(tf)) == 0
+    assert 40.0 < tf.value < 80.0
+
+
 def test_config1_golden_64_clips(ex):
     """BASELINE configs[0]: 64 synthetic 3 s clips, seed 0, against the committed oracle fixture."""
     g = np.load(os.path.join(GOLD, "config1_seed0.npz"))
