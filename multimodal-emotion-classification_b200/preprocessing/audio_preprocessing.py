@@ -44,7 +44,7 @@ def _valid_audio(audio):
         raise ParameterError("Audio buffer is not finite everywhere")
 
 
-_last = {"key": None, "row": None}
+_last = (None, None)       # (key, row) of the most recent clip; replaced in one assignment, so threads never see a mixed pair
 
 
 def _features_1clip(audio, sr, n_mfcc):
@@ -53,12 +53,14 @@ def _features_1clip(audio, sr, n_mfcc):
     _valid_audio(audio)
     a32 = np.ascontiguousarray(audio, dtype=np.float32)
     key = (a32.shape[0], int(sr), int(n_mfcc), zlib.crc32(a32.view(np.uint8)))
-    if _last["key"] != key:
+    global _last
+    last_key, row = _last
+    if last_key != key:
         from sfx_b200 import get_extractor
         ex = get_extractor(None, int(sr))
         row = ex.extract_host(a32.reshape(1, -1), n_mfcc=int(n_mfcc))[0]
-        _last["key"], _last["row"] = key, row
-    return _last["row"], np.result_type(audio.dtype, np.float32)
+        _last = (key, row)
+    return row, np.result_type(audio.dtype, np.float32)
 
 
 def _wav_chunks(file_path):
