@@ -42,6 +42,7 @@ FRAMES_PER_CLIP = 1 + N_SAMPLES // 512
 FLOPS_PER_CLIP = FRAMES_PER_CLIP * sum(FLOPS_PER_FRAME.values())
 FLOPS_PER_CLIP_FP32 = FLOPS_PER_CLIP - FRAMES_PER_CLIP * FLOPS_PER_FRAME["chroma projection (12 x 1025 FMA)"]
 KINDS = ("noise", "harmonic", "noise_tail", "harmonic_tail")
+WORKLOAD = "configs[3]: 1M x 3 s clips @22.05 kHz, clip-sharded; resident pool per GPU per step"
 
 
 def fp32_roofline(ex, clips_per_s_per_gpu):
@@ -121,8 +122,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": len(rates), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * per_step / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic",
-        "config": {"workload": "config4 sample: 3 s clips @22.05 kHz, same synthetic distributions",
-                   "clips_per_step": per_step, "n_samples": N_SAMPLES},
+        "config": {"workload": WORKLOAD, "n_samples": N_SAMPLES, "frames_per_clip": 1 + N_SAMPLES // 512,
+                   "signal_mix": list(KINDS), "clips_per_step": per_step,
+                   "sample": f"bounded sample of that workload: {per_step} clips per step, same synthetic distributions "
+                             "(tests/synth.py), all host cores"},
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port",
                          "sample": f"{tot} clips in {len(rates)} steps; oracle/librosa_port.py (librosa 0.10.0 "
                                    f"restatement, 4 STFTs per clip; real librosa is not installable here); {cpu_model()}"},
@@ -476,7 +479,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[3]: 1M x 3 s clips @22.05 kHz, clip-sharded; resident pool per GPU per step",
+            "config": {"workload": WORKLOAD,
                        "clips_per_gpu_per_step": B, "n_samples": N_SAMPLES, "frames_per_clip": 1 + N_SAMPLES // 512,
                        "signal_mix": list(KINDS), "allgather_feature_cache": do_gather,
                        "allgather_overlap": (("step i's all-gather runs under step i+1's extraction" if args.allgather == "overlap"
