@@ -50,7 +50,8 @@ def fp32_roofline(ex, clips_per_s_per_gpu):
     FP32 FMA peak measured on this GPU by the library's register-only FFMA kernel (sfx_measure_fp32_peak)."""
     import ctypes
     tf = ctypes.c_double(0.0)
-    rc = ex.lib.sfx_measure_fp32_peak(ex.index, ctypes.byref(tf))
+    from sfx_b200 import _lib
+    rc = _lib.load_bench().sfx_measure_fp32_peak(ex.index, ctypes.byref(tf))
     if rc != 0 or tf.value <= 0.0:
         return None
     achieved = clips_per_s_per_gpu * FLOPS_PER_CLIP_FP32 / 1e12

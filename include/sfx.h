@@ -16,8 +16,9 @@
  * Conventions: plain pointers and sizes, no C++/torch types.  Every function returns 0 on success
  * or a negative sfx_status; sfx_last_error() gives the text.  Nothing here falls back to the CPU:
  * without a CUDA device every compute entry point fails with SFX_ERR_CUDA.
- * Device entry points are stream-ordered (no host sync inside) and re-entrant across streams given
- * distinct workspaces.  The caller owns every buffer.
+ * Device entry points are stream-ordered (no host sync inside) and re-entrant across streams and host
+ * threads given distinct workspaces (table sets and the pipeline mode are read under a lock / atomically
+ * once per call).  The caller owns every buffer.
  */
 #ifndef SFX_B200_H
 #define SFX_B200_H
@@ -45,7 +46,9 @@ typedef enum {
     SFX_ERR_CUDA        = -2,  /* CUDA runtime error (including "no device") */
     SFX_ERR_NOT_INIT    = -3,  /* sfx_init_tables has not been called for this device */
     SFX_ERR_WORKSPACE   = -4,  /* workspace too small */
-    SFX_ERR_BAD_CLIP    = -5   /* a clip has length <= 0 or a non-finite sample (sfx_extract_host only) */
+    SFX_ERR_BAD_CLIP    = -5   /* host entry points only: a clip has length <= 0 (rejected before any work) or a
+                                * non-finite sample (found on the device: the clip's feature row is NaN; every row of
+                                * the batch has been delivered when the call returns this code) */
 } sfx_status;
 
 /* Host-side constant tables (generated in float64 by sfx_b200/tables.py; see that file for layouts). */
@@ -87,19 +90,28 @@ int         sfx_device_count(void);
  * of several sample rates coexist and are selected by the `sr` argument of the extract calls. */
 int         sfx_init_tables(int device, const sfx_tables_host *tables);
 
-/* Bytes of device workspace sfx_extract needs for clips of at most max_samples samples.
- * Independent of the batch size (persistent CTAs each own a fixed scratch slice).  0 on error. */
+/* Bytes of device workspace sfx_extract needs for clips of at most max_samples samples, whatever the batch size
+ * (persistent CTAs each own a fixed number of scratch slices).  0 on error. */
 size_t      sfx_workspace_bytes(int device, int64_t max_samples);
 
+/* The same for batches of at most B clips: a single-clip request needs one slice, not one per resident CTA
+ * (B <= 0: any batch size, i.e. sfx_workspace_bytes).  The host entry points size their cached workspaces with it. */
+size_t      sfx_workspace_bytes_batch(int device, int64_t max_samples, int64_t B);
+
 /* Kernels launched by the most recent sfx_extract / sfx_extract_debug / sfx_extract_host call of this thread (1 before
- * any call; fused pipeline: 1 per call or host chunk, +1 for a ragged batch (lengths != NULL, more clips than CTAs), whose
- * clips are processed longest first; split pipeline: 3 per chunk of <= 1024 clips). */
+ * any call; stream and fused pipelines: 1 per call or host chunk, +1 for a ragged batch (lengths != NULL, more clips than
+ * CTAs), whose clips are processed longest first; split pipeline: 3 per chunk of <= 1024 clips). */
 int         sfx_launches_per_extract(void);
 
-/* Pipeline selection: 0 = auto (default: the frame-parallel two-kernel pipeline for batches that fit one chunk of at most
- * 1024 clips -- 256 for ragged batches --, where it has the lower latency and, up to ~1000 clips, the higher throughput; the
- * fused persistent kernel above that), 1 = fused, 2 = split.  Also settable through the environment variable
- * SFX_PIPELINE=auto|fused|split before the first call.  Call sfx_workspace_bytes again after changing the mode. */
+/* Pipeline selection: 0 = auto (default), 1 = fused, 2 = split, 3 = stream.  One arithmetic, three schedules:
+ *   stream  one persistent 16-warp CTA per SM; every warp pulls STFT frames or whole per-clip tails (tuning estimate,
+ *           MFCC, chroma, pooled row) from a CTA-local scheduler, so a tail occupies one warp while 15 keep transforming
+ *           frames.  Highest throughput on large batches.
+ *   fused   persistent 8-warp CTAs, two per SM, one clip per CTA at a time (frames, barrier, tail by all 8 warps).
+ *   split   frame-parallel two-kernel pipeline per chunk of <= 1024 clips: lowest latency for small batches.
+ * auto = split for batches that fit one chunk of at most 1024 clips (256 when ragged), stream above that.  Also settable
+ * through the environment variable SFX_PIPELINE=auto|fused|split|stream before the first call.  The mode is read once per
+ * call (atomically); call sfx_workspace_bytes again after changing it. */
 int         sfx_set_pipeline(int mode);
 
 /* Batched extraction, device buffers.
@@ -126,8 +138,11 @@ int         sfx_extract_debug(int device, int32_t sr, const float *wave, int64_t
 
 /* Batched extraction, HOST buffers (the reference-facing plugin path): pinned staging, chunked
  * H2D copy overlapped with the kernel on two streams, D2H of the feature rows, then a stream sync.
- * host_wave rows must hold finite float32 samples; host_lengths may be NULL.  Allocates and caches
- * its own device buffers per device.  chunk_clips <= 0 selects the default chunk. */
+ * host_lengths may be NULL; a length outside [1, row_stride] is rejected with SFX_ERR_BAD_CLIP before any work.
+ * Samples are not scanned on the host (that would cost more than the PCIe copy): a clip with a NaN / Inf sample gets a
+ * NaN feature row, and the call returns SFX_ERR_BAD_CLIP naming the first such clip after delivering every row (the
+ * reference raises librosa.ParameterError per clip; the Python wrapper raises for the NaN rows).  Allocates and caches its
+ * own device buffers per device; calls on one device are serialised.  chunk_clips <= 0 selects the default chunk. */
 int         sfx_extract_host(int device, int32_t sr, const float *host_wave, int64_t row_stride,
                              const int32_t *host_lengths, int64_t n_default, int32_t B, int32_t n_mfcc,
                              float *host_out, int64_t out_stride, int32_t chunk_clips);
@@ -167,11 +182,6 @@ int         sfx_frontend_release(int device);
 
 /* Release cached device buffers/tables of `device` (tests; process exit does it implicitly). */
 int         sfx_release(int device);
-
-/* Measurement helper: FP32 FMA throughput of `device` in TFLOP/s, from a register-only FFMA kernel timed
- * with CUDA events on a private stream (best of three launches).  bench.py uses it as the compute denominator next to the
- * HBM roofline; nothing on the extraction path calls it. */
-int         sfx_measure_fp32_peak(int device, double *tflops);
 
 /* ---- scope row f1: device-resident StandardScaler + speech DNN forward ------------------------------------------
  * Consumer of the feature rows in the reference's inference/speech_inference.py:66-76 (scaler.transform + model.predict)

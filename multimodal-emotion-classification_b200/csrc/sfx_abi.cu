@@ -2,6 +2,8 @@
 // Host-only logic: per-device table upload, workspace sizing, launch, and the host-buffer pipeline.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -39,6 +41,7 @@ struct DevCtx {
     bool ready = false;
     int sm_count = 0, blocks_per_sm = 0, grid_max = 0;
     int frames_per_sm = 0, clips_per_sm = 0;      // split pipeline occupancies
+    int stream_per_sm = 0;                        // stream pipeline: CTAs per SM (1: a 16-warp CTA owns the register file)
     int max_pk = 0;             // max over table sets of local maxima that fit the piptrack bin range (multiple of 4)
     std::vector<TableSet> sets;
     std::vector<void*> allocs;
@@ -52,26 +55,52 @@ const TableSet* find_set(const DevCtx& c, int sr) {
 }
 
 DevCtx g_ctx[kMaxDev];
-std::mutex g_mu;
+std::mutex g_tab_mu;            // guards DevCtx::{ready, sets, occupancies, max_pk, allocs}: short critical sections only
+std::mutex g_host_mu;           // guards DevCtx::hp (the cached buffers of the host-buffer pipeline) for a whole call
 thread_local std::string g_err;
 thread_local int g_last_launches = 1;
 
-// Pipeline choice: 0 = auto (split for small batches, fused otherwise), 1 = fused, 2 = split.
-// Initial value from the environment variable SFX_PIPELINE (auto | fused | split); sfx_set_pipeline() overrides it.
-// Auto mode uses the frame-parallel split pipeline when the whole batch fits one chunk and has at most this many clips:
-// measured on 3 s clips (tools/batch_sweep.py) it is 4-15 % faster than the fused kernel up to 1 024 clips (0.65 vs 0.69 ms)
-// and slower from 1 440 on.  Ragged batches switch at 256: a few very long clips serialise its per-chunk kernels.
+// What a launch needs from the device context, copied under g_tab_mu (a concurrent sfx_init_tables for another sample
+// rate may reallocate DevCtx::sets, so no pointer into it is kept).
+struct LaunchCtx {
+    sfx::DevTables tb{};
+    int sm_count = 0, grid_max = 0, frames_per_sm = 0, clips_per_sm = 0, stream_per_sm = 0, max_pk = 0;
+};
+bool snapshot(int device, int sr, LaunchCtx* out) {
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    const DevCtx& c = g_ctx[device];
+    const TableSet* ts = c.ready ? find_set(c, sr) : nullptr;
+    if (!ts) return false;
+    out->tb = ts->tb;
+    out->sm_count = c.sm_count; out->grid_max = c.grid_max; out->frames_per_sm = c.frames_per_sm;
+    out->clips_per_sm = c.clips_per_sm; out->stream_per_sm = c.stream_per_sm; out->max_pk = c.max_pk;
+    return true;
+}
+
+// Pipeline choice: 0 = auto, 1 = fused, 2 = split, 3 = stream.
+// Initial value from the environment variable SFX_PIPELINE (auto | fused | split | stream); sfx_set_pipeline() overrides it.
+// Auto mode uses the frame-parallel split pipeline when the whole batch fits one chunk and has at most kAutoSplitMaxB clips:
+// measured on 3 s clips (tools/batch_sweep.py) it is 4-15 % faster than the persistent kernels up to 1 024 clips and slower
+// from 1 440 on.  Ragged batches switch at 256: a few very long clips serialise its per-chunk kernels.  Larger batches take
+// kAutoLarge.
 constexpr int kAutoSplitMaxB = 1024;
 constexpr int kAutoSplitMaxBRagged = 256;
-int g_pipeline = [] {
+constexpr int kPipeFused = 1, kPipeSplit = 2, kPipeStream = 3;
+#ifndef SFX_AUTO_LARGE
+#define SFX_AUTO_LARGE 3
+#endif
+constexpr int kAutoLarge = SFX_AUTO_LARGE;
+std::atomic<int> g_pipeline{[] {
     const char* e = std::getenv("SFX_PIPELINE");
-    if (e && std::strcmp(e, "split") == 0) return 2;
-    if (e && std::strcmp(e, "fused") == 0) return 1;
+    if (e && std::strcmp(e, "split") == 0) return kPipeSplit;
+    if (e && std::strcmp(e, "fused") == 0) return kPipeFused;
+    if (e && std::strcmp(e, "stream") == 0) return kPipeStream;
     return 0;
-}();
-bool use_split(int B, bool ragged, size_t chunk_cap) {
-    if (g_pipeline != 0) return g_pipeline == 2;
-    return B <= (ragged ? kAutoSplitMaxBRagged : kAutoSplitMaxB) && static_cast<size_t>(B) <= chunk_cap;
+}()};
+int choose_pipeline(int mode, int B, bool ragged, size_t split_cap) {
+    if (mode != 0) return mode;
+    if (B <= (ragged ? kAutoSplitMaxBRagged : kAutoSplitMaxB) && static_cast<size_t>(B) <= split_cap) return kPipeSplit;
+    return kAutoLarge;
 }
 
 // clips per chunk of the split pipeline: at most kSplitChunkMax, at most ~1 GiB of slices
@@ -134,6 +163,37 @@ __global__ void pcm16_to_f32_kernel(const int16_t* __restrict__ src, float* __re
     }
 }
 
+// bytes of workspace `pipe` needs for B clips of at most max_samples samples (B <= 0: any batch size)
+size_t pipeline_ws_bytes(const LaunchCtx& c, int pipe, int64_t max_samples, int64_t B) {
+    const int Tmax = 1 + static_cast<int>(max_samples / sfx::kHop);
+    if (pipe == kPipeSplit) {
+        const size_t slice = sfx::split_slice_bytes(Tmax, c.max_pk);
+        size_t n = static_cast<size_t>(split_chunk_for(slice));
+        if (B > 0) n = std::min<size_t>(n, static_cast<size_t>(B));
+        return sfx::kSplitHeader + slice * n;
+    }
+    if (pipe == kPipeStream) {
+        size_t grid = static_cast<size_t>(c.sm_count) * c.stream_per_sm;
+        if (B > 0) grid = std::min<size_t>(grid, static_cast<size_t>(B));
+        return sfx::kWsHeader + sfx::stream_slot_bytes(Tmax, c.max_pk) * sfx::stream_slots() * grid;
+    }
+    size_t grid = static_cast<size_t>(c.grid_max);
+    if (B > 0) grid = std::min<size_t>(grid, static_cast<size_t>(B));
+    return sfx::kWsHeader + sfx::cta_scratch_bytes(Tmax, c.max_pk) * grid;
+}
+
+// workspace that covers every pipeline the current mode may select for a batch of B clips (B <= 0: any batch size)
+size_t mode_ws_bytes(const LaunchCtx& c, int64_t max_samples, int64_t B) {
+    const int mode = g_pipeline.load();
+    if (mode != 0) return pipeline_ws_bytes(c, mode, max_samples, B);
+    // auto: a batch small enough for the split pipeline takes it if the workspace holds its slices, else the large-batch
+    // pipeline.  Size for the split pipeline's auto range and for the large-batch pipeline.
+    const int64_t bs = B > 0 ? std::min<int64_t>(B, kAutoSplitMaxB) : kAutoSplitMaxB;
+    const size_t split = pipeline_ws_bytes(c, kPipeSplit, max_samples, bs);
+    if (B > 0 && B <= kAutoSplitMaxBRagged) return split;      // split whatever the lengths look like
+    return std::max(split, pipeline_ws_bytes(c, kAutoLarge, max_samples, B));
+}
+
 int do_extract(int device, int sr, const float* wave, int64_t row_stride, const int32_t* lengths, int64_t n_default,
                int64_t max_samples, int32_t B, int32_t n_mfcc, float* out, int64_t out_stride, void* ws,
                size_t ws_bytes, void* stream, const sfx_debug_out* dbg) {
@@ -144,9 +204,8 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
     if (row_stride < 0 || out_stride < n_mfcc + 16) return fail(SFX_ERR_ARG, "bad row_stride/out_stride");
     if (max_samples < 1) return fail(SFX_ERR_ARG, "max_samples < 1");
     if (!lengths && (n_default < 1 || n_default > max_samples)) return fail(SFX_ERR_ARG, "n_default outside [1,max_samples]");
-    DevCtx& c = g_ctx[device];
-    const TableSet* ts = c.ready ? find_set(c, sr) : nullptr;
-    if (!ts) return fail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this (device, sample rate)");
+    LaunchCtx c;
+    if (!snapshot(device, sr, &c)) return fail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this (device, sample rate)");
     CK(cudaSetDevice(device));
     const int Tmax = 1 + static_cast<int>(max_samples / sfx::kHop);
     sfx::Params p{};
@@ -154,14 +213,15 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
     p.B = B; p.n_mfcc = n_mfcc; p.out = out; p.out_stride = out_stride;
     p.ws = static_cast<unsigned char*>(ws); p.Tmax = Tmax; p.max_samples = max_samples;
     p.aligned8 = ((reinterpret_cast<uintptr_t>(wave) & 7u) == 0 && (row_stride & 1) == 0) ? 1 : 0;
-    p.tb = ts->tb;
+    p.tb = c.tb;
     p.max_pk = c.max_pk;
     if (dbg) p.dbg = *dbg;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t split_slice = sfx::split_slice_bytes(Tmax, c.max_pk);
     const size_t split_cap = ws_bytes > sfx::kSplitHeader
                                  ? std::min<size_t>(split_chunk_for(split_slice), (ws_bytes - sfx::kSplitHeader) / split_slice) : 0;
-    if (use_split(B, lengths != nullptr, split_cap)) {
+    const int pipe = choose_pipeline(g_pipeline.load(), B, lengths != nullptr, split_cap);
+    if (pipe == kPipeSplit) {
         const size_t slice = split_slice;
         if (ws_bytes < sfx::kSplitHeader + slice)
             return fail(SFX_ERR_WORKSPACE, "workspace smaller than sfx_workspace_bytes(device, max_samples)");
@@ -183,11 +243,13 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
         g_last_launches = launches;
         return SFX_OK;
     }
-    const size_t slice = sfx::cta_scratch_bytes(Tmax, c.max_pk);
-    const int grid = std::min<int64_t>(B, c.grid_max);
+    const bool stream_pipe = pipe == kPipeStream;
+    const size_t slice = stream_pipe ? sfx::stream_slot_bytes(Tmax, c.max_pk) * sfx::stream_slots()
+                                     : sfx::cta_scratch_bytes(Tmax, c.max_pk);
+    const int grid = static_cast<int>(std::min<int64_t>(B, stream_pipe ? c.sm_count * c.stream_per_sm : c.grid_max));
     if (ws_bytes < sfx::kWsHeader + slice * static_cast<size_t>(grid))
         return fail(SFX_ERR_WORKSPACE, "workspace smaller than sfx_workspace_bytes(device, max_samples)");
-    p.cta_scratch_bytes = static_cast<long long>(slice);
+    p.cta_scratch_bytes = static_cast<long long>(stream_pipe ? sfx::stream_slot_bytes(Tmax, c.max_pk) : slice);
     CK(cudaMemsetAsync(ws, 0, sfx::kWsQueueBytes, st));
     g_last_launches = 1;
     if (lengths && B > grid && B <= sfx::kOrderMax) {        // ragged batch with more clips than CTAs: longest clips first
@@ -196,7 +258,8 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
         p.order = order;
         g_last_launches = 2;
     }
-    CK(sfx::launch_extract(p, grid, dbg != nullptr, st));
+    if (stream_pipe) CK(sfx::launch_stream(p, grid, dbg != nullptr, st));
+    else             CK(sfx::launch_extract(p, grid, dbg != nullptr, st));
     return SFX_OK;
 }
 
@@ -213,8 +276,9 @@ int extract_host_impl(int device, int32_t sr, const S* host_wave, int64_t row_st
     if (!host_wave || !host_out) return fail(SFX_ERR_ARG, "null host pointer");
     if (row_stride < 1 || out_stride < n_mfcc + 16) return fail(SFX_ERR_ARG, "bad row_stride/out_stride");
     if (!host_lengths && (n_default < 1 || n_default > row_stride)) return fail(SFX_ERR_ARG, "n_default outside [1,row_stride]");
+    LaunchCtx lc;
+    if (!snapshot(device, sr, &lc)) return fail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this (device, sample rate)");
     DevCtx& c = g_ctx[device];
-    if (!c.ready || !find_set(c, sr)) return fail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this (device, sample rate)");
     CK(cudaSetDevice(device));
     int64_t max_samples = n_default;
     if (host_lengths) {
@@ -230,9 +294,9 @@ int extract_host_impl(int device, int32_t sr, const S* host_wave, int64_t row_st
     chunk = std::min(chunk, B);
     const int out_w = n_mfcc + 16;
     const size_t need_wave = static_cast<size_t>(chunk) * dev_stride;
-    const size_t need_ws = sfx_workspace_bytes(device, max_samples);
+    const size_t need_ws = mode_ws_bytes(lc, max_samples, chunk);      // sized for the chunk, not for any batch
     const size_t need_out = static_cast<size_t>(chunk) * out_w;
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lk(g_host_mu);
     HostPath& hp = c.hp;
     const bool in_pinned = is_pinned(host_wave), out_pinned = is_pinned(host_out);
     if (hp.wave_elems < need_wave || hp.ws_bytes < need_ws || hp.out_elems < need_out || hp.chunk < chunk ||
@@ -255,13 +319,17 @@ int extract_host_impl(int device, int32_t sr, const S* host_wave, int64_t row_st
     int launches_total = 0;
     sfx::QuiesceOnError<kHostStreams> quiesce{hp.stream};
     std::vector<int> pend_c0(kHostStreams, -1), pend_nb(kHostStreams, 0);
-    auto drain = [&](int s) -> int {      // copy a finished chunk's rows out of pinned staging
+    int64_t first_bad = -1;               // first clip whose feature row is not finite (bad length or non-finite sample)
+    auto drain = [&](int s) -> int {      // copy a finished chunk's rows out of pinned staging, look for non-finite rows
         if (pend_c0[s] < 0) return SFX_OK;
         CK(cudaEventSynchronize(hp.ev_done[s]));
-        if (!out_pinned) {
-            for (int i = 0; i < pend_nb[s]; ++i)
-                std::memcpy(host_out + static_cast<int64_t>(pend_c0[s] + i) * out_stride, hp.h_out[s] + static_cast<size_t>(i) * out_w,
-                            sizeof(float) * out_w);
+        for (int i = 0; i < pend_nb[s]; ++i) {
+            float* dst = host_out + static_cast<int64_t>(pend_c0[s] + i) * out_stride;
+            if (!out_pinned) std::memcpy(dst, hp.h_out[s] + static_cast<size_t>(i) * out_w, sizeof(float) * out_w);
+            // a NaN / Inf sample reaches every frame-mean it touches (rms and centroid at least): one look at the row's
+            // four descriptors finds it without a pass over the waveform on the host
+            const float chk = dst[n_mfcc + 12] + dst[n_mfcc + 13] + dst[n_mfcc + 14] + dst[n_mfcc + 15] + dst[0];
+            if (!std::isfinite(chk) && (first_bad < 0 || pend_c0[s] + i < first_bad)) first_bad = pend_c0[s] + i;
         }
         pend_c0[s] = -1;
         return SFX_OK;
@@ -314,6 +382,9 @@ int extract_host_impl(int device, int32_t sr, const S* host_wave, int64_t row_st
     }
     quiesce.armed = false;
     g_last_launches = launches_total;
+    if (first_bad >= 0)
+        return fail(SFX_ERR_BAD_CLIP, "clip " + std::to_string(first_bad) + ": non-finite sample (its feature row, like that of every "
+                                      "other such clip, is NaN; all rows were delivered)");
     return SFX_OK;
 }
 
@@ -333,15 +404,16 @@ int sfx_device_count(void) {
 int sfx_launches_per_extract(void) { return g_last_launches; }
 
 int sfx_set_pipeline(int mode) {
-    if (mode < 0 || mode > 2) return fail(SFX_ERR_ARG, "pipeline mode must be 0 (auto), 1 (fused) or 2 (split)");
-    g_pipeline = mode;
+    if (mode < 0 || mode > 3) return fail(SFX_ERR_ARG, "pipeline mode must be 0 (auto), 1 (fused), 2 (split) or 3 (stream)");
+    g_pipeline.store(mode);
     return SFX_OK;
 }
 
 int sfx_release(int device) {
     if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
     sfx_frontend_release(device);
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lh(g_host_mu);
+    std::lock_guard<std::mutex> lk(g_tab_mu);
     DevCtx& c = g_ctx[device];
     if (!c.ready && c.allocs.empty()) return SFX_OK;
     cudaSetDevice(device);
@@ -363,7 +435,7 @@ int sfx_init_tables(int device, const sfx_tables_host* t) {
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (device >= ndev) return fail(SFX_ERR_CUDA, "no such CUDA device");
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lk(g_tab_mu);
     DevCtx& c = g_ctx[device];
     if (c.ready && find_set(c, t->sr)) return SFX_OK;        // idempotent per (device, sr)
     CK(cudaSetDevice(device));
@@ -399,25 +471,31 @@ int sfx_init_tables(int device, const sfx_tables_host* t) {
     c.grid_max = c.sm_count * c.blocks_per_sm;
     CK(sfx::configure_split(&c.frames_per_sm, &c.clips_per_sm));
     if (c.frames_per_sm < 1 || c.clips_per_sm < 1) return fail(SFX_ERR_CUDA, "split kernels do not fit on an SM");
+    CK(sfx::configure_stream(&c.stream_per_sm));
+    if (c.stream_per_sm < 1) return fail(SFX_ERR_CUDA, "stream kernel does not fit on an SM");
     c.max_pk = std::max(c.max_pk, (((t->pip_kmax - t->pip_kmin + 2) / 2) + 3) & ~3);
     c.sets.push_back(set);
     c.ready = true;
     return SFX_OK;
 }
 
-size_t sfx_workspace_bytes(int device, int64_t max_samples) {
-    if (device < 0 || device >= kMaxDev || max_samples < 1 || !g_ctx[device].ready) {
+size_t sfx_workspace_bytes_batch(int device, int64_t max_samples, int64_t B) {
+    LaunchCtx c;
+    bool ok = device >= 0 && device < kMaxDev && max_samples >= 1;
+    if (ok) {
+        std::lock_guard<std::mutex> lk(g_tab_mu);
+        const DevCtx& d = g_ctx[device];
+        ok = d.ready;
+        c.sm_count = d.sm_count; c.grid_max = d.grid_max; c.stream_per_sm = d.stream_per_sm; c.max_pk = d.max_pk;
+    }
+    if (!ok) {
         g_err = "sfx_workspace_bytes: bad device/max_samples or tables not initialised";
         return 0;
     }
-    const int Tmax = 1 + static_cast<int>(max_samples / sfx::kHop);
-    const size_t fused = sfx::kWsHeader + sfx::cta_scratch_bytes(Tmax, g_ctx[device].max_pk) * static_cast<size_t>(g_ctx[device].grid_max);
-    // covers either pipeline: the split one needs one slice per clip of a chunk (auto mode: at most kAutoSplitMaxB clips)
-    const size_t slice = sfx::split_slice_bytes(Tmax, g_ctx[device].max_pk);
-    const size_t nsplit = g_pipeline == 2 ? static_cast<size_t>(split_chunk_for(slice))
-                                          : std::min<size_t>(kAutoSplitMaxB, split_chunk_for(slice));
-    return std::max(fused, sfx::kSplitHeader + slice * nsplit);
+    return mode_ws_bytes(c, max_samples, B);
 }
+
+size_t sfx_workspace_bytes(int device, int64_t max_samples) { return sfx_workspace_bytes_batch(device, max_samples, 0); }
 
 int sfx_extract(int device, int32_t sr, const float* wave, int64_t row_stride, const int32_t* lengths, int64_t n_default,
                 int64_t max_samples, int32_t B, int32_t n_mfcc, float* out, int64_t out_stride, void* workspace,

@@ -183,9 +183,6 @@ int sfx_preprocess_host_pcm16(int device, int32_t sr, const sfx_resampler_host* 
     FCK(cudaGetDeviceCount(&ndev));
     if (device >= ndev) return ffail(SFX_ERR_CUDA, "no such CUDA device");
     FCK(cudaSetDevice(device));
-    const size_t need_ws = sfx_workspace_bytes(device, n_target);
-    if (need_ws == 0) return ffail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this (device, sample rate)");
-
     const int64_t pcm_stride = (max_frames * channels + 1) & ~int64_t(1);         // int16 elements per device row
     const int64_t wave_stride = (n_target + 1) & ~int64_t(1);
     int chunk = chunk_clips > 0 ? chunk_clips
@@ -194,6 +191,8 @@ int sfx_preprocess_host_pcm16(int device, int32_t sr, const sfx_resampler_host* 
     const int out_w = n_mfcc + 16;
     const size_t need_pcm = static_cast<size_t>(chunk) * pcm_stride, need_wave = static_cast<size_t>(chunk) * wave_stride;
     const size_t need_out = static_cast<size_t>(chunk) * out_w;
+    const size_t need_ws = sfx_workspace_bytes_batch(device, n_target, chunk);       // sized for the chunk, not for any batch
+    if (need_ws == 0) return ffail(SFX_ERR_NOT_INIT, "sfx_init_tables not called for this (device, sample rate)");
 
     std::lock_guard<std::mutex> lk(g_front_mu);
     FrontPath& fp = g_front[device];

@@ -16,6 +16,7 @@ constexpr int kChroma = SFX_N_CHROMA;
 constexpr int kPStride = SFX_P_STRIDE;
 constexpr int kTunings = SFX_N_TUNINGS;
 constexpr int kWarps = 8;
+constexpr int kStreamWarps = 16;         // warps per CTA of the stream kernel (sfx_stream.cu)
 constexpr int kThreads = kWarps * 32;
 constexpr int kExFloats = 32 * 33 * 2;   // per-warp float2[32][33] exchange tile, reused as the padded |X|^2 tile
 constexpr int kP16Stride = 1056;         // halves per FP16 |X|^2 row (2112 B = 64 mod 128: conflict-free LDS.128 of the bank rows)
@@ -102,6 +103,23 @@ inline size_t split_slice_bytes(int Tmax, int max_pk) {
     size_t b = static_cast<size_t>(Tmax) * (kP16Stride * 2 + kMels * 4 + 12 + 16 + static_cast<size_t>(max_pk) * (16 + 4 + 1));
     return (b + 255) & ~static_cast<size_t>(255);
 }
+
+// ---- stream pipeline (sfx_stream.cu): workspace = header (queue counter + clip order) | per CTA: stream_slots() slices
+// peak records of a slot are kept in one segment per warp of the 16-warp CTA; a segment holds the peaks of
+// ceil(Tmax / 12) frames, and a warp is only handed a frame of a clip while its segment has room for a full frame
+// (at least 13 of the 16 warps transform frames at any time, so a clip's frames always find room)
+__host__ __device__ inline int stream_seg_frames(int Tmax) { return (Tmax + 11) / 12; }
+inline size_t stream_slot_bytes(int Tmax, int max_pk) {
+    // FP16 |X|^2 rows, log-mel rows, hop energy / Nyquist / 1/scale / centroid / roll-off / row max / zero crossings per
+    // frame, peak keys (u32) + bins (u8) of the overflow path, record segments (float4)
+    size_t b = static_cast<size_t>(Tmax) * (kP16Stride * 2 + kMels * 4 + 8 * 4 + static_cast<size_t>(max_pk) * (4 + 1)) +
+               static_cast<size_t>(kStreamWarps) * stream_seg_frames(Tmax) * max_pk * 16;
+    return (b + 255) & ~static_cast<size_t>(255);
+}
+size_t smem_stream();
+int stream_slots();
+cudaError_t configure_stream(int* blocks_per_sm);
+cudaError_t launch_stream(const Params& p, int grid, bool debug, cudaStream_t stream);
 
 size_t smem_bytes();
 cudaError_t configure_split(int* frames_per_sm, int* clips_per_sm);

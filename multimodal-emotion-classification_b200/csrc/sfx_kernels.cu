@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     FrameOut fo;
     fo.gP16 = gP16; fo.gL = gL; fo.gRec = gRec; fo.gE = gE; fo.gNy = gNy; fo.gInvS = gInvS;
     fo.npk = nullptr; fo.gSeg = gRec + static_cast<size_t>(warp) * seg_cap; fo.s_wacc = s_wacc; fo.s_f = s_f;
-    fo.gCent = nullptr; fo.gRoll = nullptr; fo.gLmax = nullptr; fo.gZc = nullptr;
+    fo.gCent = nullptr; fo.gRoll = nullptr; fo.gLmax = nullptr; fo.gZc = nullptr; fo.gFv = nullptr;
     const ClipSmem cs{s_ex, s_pool, s_wacc, s_edges, s_mbar, s_hist, s_i, s_f};
     const ClipSlice sl{gP16, gL, gRec, gKey, gE, gNy, gInvS, gBin, seg_cap};
 
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         __syncwarp();
 
         for (int t = warp; t < T; t += kWarps)
-            process_frame<kDebug, false>(p, tb, fs, fo, x, n, T, t, clip, lane, warp, acc_zc, wcount);
+            process_frame<kDebug, kModeFused>(p, tb, fs, fo, x, n, T, t, clip, lane, warp, acc_zc, wcount);
 
         // per-warp partials
         {

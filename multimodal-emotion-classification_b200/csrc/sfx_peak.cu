@@ -1,10 +1,12 @@
 // sfx_peak.cu -- measurement helper ("measure an FP32 FMA micro-benchmark peak on the box as the compute
 // denominator").  The extractor is bound by FP32 issue slots and shared memory, not by HBM, so bench.py reports the
-// algorithmic flop rate against this number next to the HBM roofline BASELINE.json asks for.  Not on the product path.
+// algorithmic flop rate against this number next to the HBM roofline BASELINE.json asks for.  Built into its own library
+// (libsfx_bench.so, include/sfx_bench.h): not part of libsfx_b200.so.
 #include <cuda_runtime.h>
 #include <string>
 
 #include "../../include/sfx.h"
+#include "../../include/sfx_bench.h"
 
 namespace {
 

@@ -28,7 +28,11 @@ struct FrameOut {
     float4* gSeg;                                                                      // fused: this warp's record segment
     double* s_wacc; float* s_f;                                                        // fused: per-warp accumulators
     float* gCent; float* gRoll; float* gLmax; int* gZc;                                // split: per-frame values
+    float* gFv;           // stream: per-frame values as one record of kFvStride floats per frame (one live pointer
+                          // instead of seven): [0] hop energy, [1] scaled Nyquist |X|^2, [2] 1/scale, [3] centroid,
+                          // [4] roll-off, [5] row max of log-mel, [6] weighted zero crossings (int), [7] unused
 };
+constexpr int kFvStride = 8;
 
 // shared memory of phases 2-3
 struct ClipSmem {
@@ -41,10 +45,20 @@ struct ClipSlice {
 };
 
 // ------------------------------------------------------------------------------------------------ phase 1
-template <bool kDebug, bool kSplit>
+// kMode: where per-frame results are kept.
+//   kModeFused : per-warp accumulators in shared memory, peaks appended to the warp's own record segment
+//   kModeSplit : per-frame values in the clip's slice, record space reserved with one global atomic per frame
+//   kModeStream: per-frame values in the clip's slice (summed in frame order by the tail warp: deterministic whatever
+//                warp ran the frame), peaks appended to the calling warp's own record segment of the clip's slot
+constexpr int kModeFused = 0, kModeSplit = 1, kModeStream = 2;
+
+template <bool kDebug, int kMode>
 __device__ __forceinline__ void process_frame(const Params& p, const DevTables& tb, const FrameSmem& fs, const FrameOut& fo,
                                               const float* __restrict__ x, const long long n, const int T, const int t,
                                               const int clip, const int lane, const int warp, int& acc_zc, int& wcount) {
+    constexpr bool kSplit = kMode == kModeSplit;          // records through a global atomic per frame
+    constexpr bool kFrameVals = kMode != kModeFused;       // per-frame centroid / roll-off / zero crossings / row max stored
+    constexpr bool kStream = kMode == kModeStream;         // ... as one record per frame (fo.gFv)
     float re[32], im[32];
     load_frame(x, n, t, lane, fs.aligned8, re, im);
     // ---- all-zero frame (the zero tail load_audio pads short clips with, reference :15-16): every result is
@@ -63,11 +77,13 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             uint4* dst = reinterpret_cast<uint4*>(fo.gP16 + static_cast<size_t>(t) * kP16Stride + 32 * lane);
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(0u, 0u, 0u, 0u);
-            if (lane == 0) {
+            if constexpr (kStream) {
+                if (lane < kFvStride) fo.gFv[static_cast<size_t>(t) * kFvStride + lane] = lane == 5 ? lm0 : 0.0f;
+            } else if (lane == 0) {
                 fo.gE[t] = 0.0f;
                 fo.gNy[t] = 0.0f;
                 fo.gInvS[t] = 0.0f;
-                if constexpr (kSplit) { fo.gCent[t] = 0.0f; fo.gRoll[t] = 0.0f; fo.gLmax[t] = lm0; fo.gZc[t] = 0; }
+                if constexpr (kFrameVals) { fo.gCent[t] = 0.0f; fo.gRoll[t] = 0.0f; fo.gLmax[t] = lm0; fo.gZc[t] = 0; }
                 else fo.s_f[warp] = fmaxf(fo.s_f[warp], lm0);
             }
             if (kDebug) {
@@ -96,7 +112,10 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
 #pragma unroll
         for (int m1 = 16; m1 < 24; ++m1) { he = fmaf(re[m1], re[m1], he); he = fmaf(im[m1], im[m1], he); }
         he = warp_sum(he);
-        if (lane == 0) fo.gE[t] = he;
+        if (lane == 0) {
+            if constexpr (kStream) fo.gFv[static_cast<size_t>(t) * kFvStride] = he;
+            else fo.gE[t] = he;
+        }
     }
 
     // ---- zero crossings of hop t (samples [512t, 512t+512)), weighted by how many frames see them
@@ -214,7 +233,8 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
     // ---- warm L2 with the newest hop of this warp's next frame (its other three hops are shared with
     //      frames the neighbouring warps are reading now)
     {
-        const long long nh = static_cast<long long>(kHop) * (t + kWarps) + kHop + lane * 32;
+        constexpr int ahead = kMode == kModeStream ? kStreamWarps : kWarps;
+        const long long nh = static_cast<long long>(kHop) * (t + ahead) + kHop + lane * 32;
         if (!kSplit && lane < 16 && nh < n) prefetch_l2(x + nh);
     }
     if (kDebug) {
@@ -289,8 +309,13 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             uint4* dst = reinterpret_cast<uint4*>(fo.gP16 + static_cast<size_t>(t) * kP16Stride + 32 * lane);
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
-            if (lane == 31) fo.gNy[t] = fs.Pb[pidx(1024)] * scale;
-            if (lane == 0) fo.gInvS[t] = __uint_as_float((254u << 23) - sbits);      // 1/scale, exact
+            if constexpr (kStream) {
+                if (lane == 31) fo.gFv[static_cast<size_t>(t) * kFvStride + 1] = fs.Pb[pidx(1024)] * scale;
+                if (lane == 0) fo.gFv[static_cast<size_t>(t) * kFvStride + 2] = __uint_as_float((254u << 23) - sbits);
+            } else {
+                if (lane == 31) fo.gNy[t] = fs.Pb[pidx(1024)] * scale;
+                if (lane == 0) fo.gInvS[t] = __uint_as_float((254u << 23) - sbits);      // 1/scale, exact
+            }
         }
         float inc = run;
 #pragma unroll
@@ -315,7 +340,13 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
         cent_t = (total < FLT_MIN) ? 0.0f : (num / total) * fs.bin_hz;
         roll_t = static_cast<float>(first) * fs.bin_hz;
     }
-    if constexpr (kSplit) {
+    if constexpr (kStream) {
+        const int zsum = warp_sum_i(zc_w);
+        if (lane == 0) {
+            float* fv = fo.gFv + static_cast<size_t>(t) * kFvStride;
+            fv[3] = cent_t; fv[4] = roll_t; fv[6] = __int_as_float(zsum);
+        }
+    } else if constexpr (kFrameVals) {
         const int zsum = warp_sum_i(zc_w);
         if (lane == 0) { fo.gCent[t] = cent_t; fo.gRoll[t] = roll_t; fo.gZc[t] = zsum; }
     } else {
@@ -345,7 +376,8 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
         }
         gmax = warp_max(gmax);
         if (lane == 0) {
-            if constexpr (kSplit) fo.gLmax[t] = gmax;
+            if constexpr (kStream) fo.gFv[static_cast<size_t>(t) * kFvStride + 5] = gmax;
+            else if constexpr (kFrameVals) fo.gLmax[t] = gmax;
             else fo.s_f[warp] = fmaxf(fo.s_f[warp], gmax);
         }
     }

@@ -144,9 +144,9 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_frames_kernel(const SplitPara
         FrameOut fo;
         fo.gP16 = sl.gP16; fo.gL = sl.gL; fo.gRec = sl.gRec; fo.gE = sl.gE; fo.gNy = sl.gNy; fo.gInvS = sl.gInvS;
         fo.npk = npk_all + c; fo.gSeg = nullptr; fo.s_wacc = nullptr; fo.s_f = nullptr;
-        fo.gCent = sl.gCent; fo.gRoll = sl.gRoll; fo.gLmax = sl.gLmax; fo.gZc = sl.gZc;
+        fo.gCent = sl.gCent; fo.gRoll = sl.gRoll; fo.gLmax = sl.gLmax; fo.gZc = sl.gZc; fo.gFv = nullptr;
         int unused_zc = 0, unused_cnt = 0;
-        process_frame<kDebug, true>(p, tb, fs, fo, x, n, T, t, clip, lane, warp, unused_zc, unused_cnt);
+        process_frame<kDebug, kModeSplit>(p, tb, fs, fo, x, n, T, t, clip, lane, warp, unused_zc, unused_cnt);
     }
 }
 

@@ -47,7 +47,10 @@ EXPORTS = ["sfx_dnn_create", "sfx_dnn_destroy", "sfx_dnn_workspace_bytes", "sfx_
            "sfx_dnn_last_error", "sfx_dnn_forward", "sfx_abi_version", "sfx_last_error", "sfx_device_count", "sfx_init_tables", "sfx_workspace_bytes",
            "sfx_launches_per_extract", "sfx_set_pipeline", "sfx_extract", "sfx_extract_debug", "sfx_extract_host", "sfx_extract_host_pcm16",
            "sfx_preprocess_host_pcm16", "sfx_frontend_last_error", "sfx_frontend_release", "sfx_release",
-           "sfx_measure_fp32_peak"]
+           "sfx_workspace_bytes_batch"]
+BENCH_EXPORTS = ["sfx_measure_fp32_peak"]          # include/sfx_bench.h -> libsfx_bench.so (bench.py / tests only)
+PIPELINES = {"auto": 0, "fused": 1, "split": 2, "stream": 3}
+ERR_BAD_CLIP = -5
 
 
 def lib_path() -> str:
@@ -91,8 +94,8 @@ def load():
     lib.sfx_frontend_release.argtypes = [C.c_int]
     lib.sfx_release.restype = C.c_int
     lib.sfx_release.argtypes = [C.c_int]
-    lib.sfx_measure_fp32_peak.restype = C.c_int
-    lib.sfx_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.sfx_workspace_bytes_batch.restype = C.c_size_t
+    lib.sfx_workspace_bytes_batch.argtypes = [C.c_int, C.c_int64, C.c_int64]
     lib.sfx_set_pipeline.restype = C.c_int
     lib.sfx_set_pipeline.argtypes = [C.c_int]
     lib.sfx_dnn_create.restype = C.c_int
@@ -111,6 +114,22 @@ def load():
         raise RuntimeError("libsfx_b200.so ABI version mismatch; rebuild with sfx_b200.build.build(force=True)")
     _LIB = lib
     return lib
+
+
+_BENCH_LIB = None
+
+
+def load_bench():
+    """libsfx_bench.so: measurement helpers of include/sfx_bench.h.  Only bench.py and the tests load it."""
+    global _BENCH_LIB
+    if _BENCH_LIB is None:
+        if not os.path.exists(_build.BENCH_LIB_PATH):
+            _build.build()
+        lib = C.CDLL(_build.BENCH_LIB_PATH)
+        lib.sfx_measure_fp32_peak.restype = C.c_int
+        lib.sfx_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        _BENCH_LIB = lib
+    return _BENCH_LIB
 
 
 def check(rc: int):

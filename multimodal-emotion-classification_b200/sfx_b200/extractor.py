@@ -29,7 +29,9 @@ class NoCudaDeviceError(RuntimeError):
 
 
 class SpeechFeatureExtractor:
-    """One instance per (device, sample rate): owns the uploaded tables and a growable workspace."""
+    """One instance per (device, sample rate): owns the uploaded tables and one growable workspace per CUDA stream it has
+    been called on (the C ABI is re-entrant across streams and threads given distinct workspaces; a workspace holds the
+    clip queue and all scratch of a launch, so two launches in flight must never share one)."""
 
     def __init__(self, device=None, sr: int = 22050):
         self.lib = _lib.load()
@@ -43,20 +45,29 @@ class SpeechFeatureExtractor:
         self._tables = _lib.make_tables_struct(tables.build_tables(self.sr))
         with torch.cuda.device(self.index):
             _lib.check(self.lib.sfx_init_tables(self.index, C.byref(self._tables)))
-        self._ws = None
-        self._ws_samples = 0
+        self._ws = {}                  # cuda_stream handle -> uint8 workspace tensor
+        self._ws_lock = threading.Lock()
         self.launches = 0
 
     # ------------------------------------------------------------------ workspace
-    def _workspace(self, max_samples: int) -> torch.Tensor:
-        # re-queried every call: the requirement also grows when another sample rate's tables are uploaded
-        nbytes = self.lib.sfx_workspace_bytes(self.index, int(max(max_samples, self._ws_samples)))
+    def _workspace(self, max_samples: int, batch: int, stream: torch.cuda.Stream) -> torch.Tensor:
+        """The workspace of `stream`, grown to what a batch of `batch` clips of `max_samples` samples needs (re-queried
+        every call: the requirement depends on the pipeline mode and on the table sets uploaded so far).  Kernels on one
+        stream run in order, so reusing the stream's workspace for its next launch is safe; a buffer that is replaced is
+        handed back to the caching allocator only after `record_stream`, i.e. once the stream's queued work is done."""
+        nbytes = self.lib.sfx_workspace_bytes_batch(self.index, int(max_samples), int(batch))
         if nbytes == 0:
             raise _lib.SfxError(-1, self.lib.sfx_last_error().decode())
-        if self._ws is None or nbytes > self._ws.numel():
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        self._ws_samples = int(max(max_samples, self._ws_samples))
-        return self._ws
+        key = stream.cuda_stream
+        with self._ws_lock:
+            ws = self._ws.get(key)
+            if ws is None or nbytes > ws.numel():
+                if ws is not None:
+                    ws.record_stream(stream)
+                with torch.cuda.stream(stream):
+                    ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                self._ws[key] = ws
+        return ws
 
     # ------------------------------------------------------------------ device path
     def extract(self, waves: torch.Tensor, lengths: torch.Tensor | None = None, n_samples: int | None = None,
@@ -86,8 +97,9 @@ class SpeechFeatureExtractor:
             raise ValueError("out must be float32 [B, n_mfcc+16] on the extractor's device")
         if B == 0:
             return out
-        ws = self._workspace(max_samples)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        cur = torch.cuda.current_stream(self.device)
+        ws = self._workspace(max_samples, B, cur)
+        stream = cur.cuda_stream
         args = (self.index, self.sr, waves.data_ptr(), waves.stride(0), lengths.data_ptr() if lengths is not None else None,
                 n_default, max_samples, B, n_mfcc, out.data_ptr(), out.stride(0), ws.data_ptr(), ws.numel(),
                 C.c_void_p(stream))
@@ -135,10 +147,19 @@ class SpeechFeatureExtractor:
             return out
         fn = self.lib.sfx_extract_host if waves.dtype == np.float32 else self.lib.sfx_extract_host_pcm16
         with torch.cuda.device(self.index):
-            _lib.check(fn(self.index, self.sr, waves.ctypes.data, waves.strides[0] // waves.itemsize, lp, n_default,
-                          B, n_mfcc, out.ctypes.data, out.strides[0] // 4, int(chunk_clips)))
+            rc = fn(self.index, self.sr, waves.ctypes.data, waves.strides[0] // waves.itemsize, lp, n_default,
+                    B, n_mfcc, out.ctypes.data, out.strides[0] // 4, int(chunk_clips))
+        # SFX_ERR_BAD_CLIP after the rows were delivered = some clip held a non-finite sample: its row is NaN, which is
+        # what the callers look at (preprocessing.audio_preprocessing raises ParameterError for it, like librosa)
+        # (a bad *length* is rejected before any work with the same code and does raise)
+        if not (rc == _lib.ERR_BAD_CLIP and b"non-finite" in self.lib.sfx_last_error()):
+            _lib.check(rc)
         self.launches += self.lib.sfx_launches_per_extract()      # summed over the call's chunks by the library
         return out
+
+    def set_pipeline(self, mode) -> None:
+        """Process-wide pipeline choice: 'auto' | 'fused' | 'split' | 'stream' (or 0..3), see include/sfx.h."""
+        _lib.check(self.lib.sfx_set_pipeline(_lib.PIPELINES.get(mode, mode)))
 
     def preprocess_pcm16(self, pcm: np.ndarray, frames: np.ndarray | None, native_sr: int, channels: int = 1,
                          duration: float = 3, n_mfcc: int = 40, out: np.ndarray | None = None,

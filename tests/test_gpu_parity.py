@@ -41,7 +41,8 @@ def test_fp32_peak_helper_measures_a_plausible_rate(ex):
     """bench.py's compute denominator: a B200 has 148 SMs x 128 FP32 lanes x 2 flop at <= 2.1 GHz = 79.6 TFLOP/s."""
     import ctypes
     tf = ctypes.c_double(0.0)
-    assert ex.lib.sfx_measure_fp32_peak(ex.index, ctypes.byref(tf)) == 0
+    from sfx_b200 import _lib
+    assert _lib.load_bench().sfx_measure_fp32_peak(ex.index, ctypes.byref(tf)) == 0
     assert 40.0 < tf.value < 80.0
 
 
