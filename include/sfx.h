@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SFX_ABI_VERSION 1
+#define SFX_ABI_VERSION 2
 #define SFX_N_CHROMA    12
 #define SFX_N_SPECTRAL  4      /* [zcr, spectral_centroid, spectral_rolloff, rms] (reference :33-37) */
 #define SFX_N_FFT       2048
@@ -68,6 +68,8 @@ typedef struct {
     const float  *chroma_ny;     /* [100][12] float32 weights of the Nyquist bin */
     const double *dct;           /* [128][128] */
     const double *edges;         /* [101] */
+    const uint32_t*chroma_frag;  /* [100][32][2][2][32][4] the bank as mma.m16n8k16 A fragments: (tuning, 32-bin step,
+                                  * half step, hi/lo, lane) -> one 16-byte quad (stream pipeline; see tables.py) */
 } sfx_tables_host;
 
 /* Optional per-clip / per-frame intermediates for parity triage (device pointers, any may be NULL). */

@@ -43,6 +43,8 @@ struct DevCtx {
     int frames_per_sm = 0, clips_per_sm = 0;      // split pipeline occupancies
     int stream_per_sm = 0;                        // stream pipeline: CTAs per SM (1: a 16-warp CTA owns the register file)
     int max_pk = 0;             // max over table sets of local maxima that fit the piptrack bin range (multiple of 4)
+    size_t l2_persist = 0;      // bytes of L2 set aside for persisting accesses (0: none), l2_window = largest policy window
+    size_t l2_window = 0;
     std::vector<TableSet> sets;
     std::vector<void*> allocs;
     HostPath hp;
@@ -65,6 +67,7 @@ thread_local int g_last_launches = 1;
 struct LaunchCtx {
     sfx::DevTables tb{};
     int sm_count = 0, grid_max = 0, frames_per_sm = 0, clips_per_sm = 0, stream_per_sm = 0, max_pk = 0;
+    size_t l2_persist = 0, l2_window = 0;
 };
 bool snapshot(int device, int sr, LaunchCtx* out) {
     std::lock_guard<std::mutex> lk(g_tab_mu);
@@ -74,6 +77,7 @@ bool snapshot(int device, int sr, LaunchCtx* out) {
     out->tb = ts->tb;
     out->sm_count = c.sm_count; out->grid_max = c.grid_max; out->frames_per_sm = c.frames_per_sm;
     out->clips_per_sm = c.clips_per_sm; out->stream_per_sm = c.stream_per_sm; out->max_pk = c.max_pk;
+    out->l2_persist = c.l2_persist; out->l2_window = c.l2_window;
     return true;
 }
 
@@ -87,7 +91,7 @@ constexpr int kAutoSplitMaxB = 1024;
 constexpr int kAutoSplitMaxBRagged = 256;
 constexpr int kPipeFused = 1, kPipeSplit = 2, kPipeStream = 3;
 #ifndef SFX_AUTO_LARGE
-#define SFX_AUTO_LARGE 3
+#define SFX_AUTO_LARGE 1        // measured (tools/ab_modes.py, bench mix): fused 1.78 M clips/s, stream 1.42 M
 #endif
 constexpr int kAutoLarge = SFX_AUTO_LARGE;
 std::atomic<int> g_pipeline{[] {
@@ -97,6 +101,11 @@ std::atomic<int> g_pipeline{[] {
     if (e && std::strcmp(e, "stream") == 0) return kPipeStream;
     return 0;
 }()};
+// L2 pinning of the fused kernel's read-back rows: SFX_L2_PIN = 0 (off) | 1 (FP16 |X|^2 rows, default) | 2 (+ log-mel rows)
+const int g_l2_mode = [] {
+    const char* e = std::getenv("SFX_L2_PIN");
+    return e ? std::atoi(e) : 1;
+}();
 int choose_pipeline(int mode, int B, bool ragged, size_t split_cap) {
     if (mode != 0) return mode;
     if (B <= (ragged ? kAutoSplitMaxBRagged : kAutoSplitMaxB) && static_cast<size_t>(B) <= split_cap) return kPipeSplit;
@@ -249,7 +258,9 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
     const int grid = static_cast<int>(std::min<int64_t>(B, stream_pipe ? c.sm_count * c.stream_per_sm : c.grid_max));
     if (ws_bytes < sfx::kWsHeader + slice * static_cast<size_t>(grid))
         return fail(SFX_ERR_WORKSPACE, "workspace smaller than sfx_workspace_bytes(device, max_samples)");
-    p.cta_scratch_bytes = static_cast<long long>(stream_pipe ? sfx::stream_slot_bytes(Tmax, c.max_pk) : slice);
+    p.cta_scratch_bytes = static_cast<long long>(stream_pipe ? sfx::stream_slot_bytes(Tmax, c.max_pk) : sfx::cta_rest_bytes(Tmax, c.max_pk));
+    p.cta_p16_bytes = static_cast<long long>(sfx::cta_p16_bytes(Tmax));
+    p.cta_lm_bytes = static_cast<long long>(sfx::cta_lm_bytes(Tmax));
     CK(cudaMemsetAsync(ws, 0, sfx::kWsQueueBytes, st));
     g_last_launches = 1;
     if (lengths && B > grid && B <= sfx::kOrderMax) {        // ragged batch with more clips than CTAs: longest clips first
@@ -258,8 +269,28 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
         p.order = order;
         g_last_launches = 2;
     }
+    // Fused kernel: pin the rows phase 3 reads back (FP16 |X|^2, then log-mel, of every CTA: one block of the workspace)
+    // in the persisting part of L2 for the duration of the launch.  hitRatio = the fraction of the window's lines the
+    // set-aside can hold, so that persisting lines never evict each other.
+    const bool l2_pin = !stream_pipe && c.l2_persist > 0 && g_l2_mode != 0;
+    if (l2_pin) {
+        size_t win = static_cast<size_t>(grid) * (sfx::cta_p16_bytes(Tmax) + (g_l2_mode == 2 ? sfx::cta_lm_bytes(Tmax) : 0));
+        win = std::min(win, c.l2_window);
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.base_ptr = static_cast<unsigned char*>(ws) + sfx::kWsHeader;
+        av.accessPolicyWindow.num_bytes = win;
+        av.accessPolicyWindow.hitRatio = static_cast<float>(std::min(1.0, static_cast<double>(c.l2_persist) / static_cast<double>(win)));
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     if (stream_pipe) CK(sfx::launch_stream(p, grid, dbg != nullptr, st));
     else             CK(sfx::launch_extract(p, grid, dbg != nullptr, st));
+    if (l2_pin) {                                            // later work on the caller's stream is not ours to steer
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.num_bytes = 0;
+        CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     return SFX_OK;
 }
 
@@ -426,7 +457,7 @@ int sfx_release(int device) {
 int sfx_init_tables(int device, const sfx_tables_host* t) {
     if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
     if (!t || !t->hann || !t->tw1 || !t->tw2 || !t->mel_ab || !t->mel_mask || !t->mel_src || !t->chroma16 || !t->chroma_ny || !t->dct ||
-        !t->edges || t->sr <= 0)
+        !t->edges || !t->chroma_frag || t->sr <= 0)
         return fail(SFX_ERR_ARG, "null table pointer or bad sizes");
     if (t->mel_ps < 3 || (t->mel_ps & 1) == 0 || sfx::kPartOff + 32 * t->mel_ps + 1 > sfx::kExFloats)
         return fail(SFX_ERR_ARG, "mel_ps must be odd and fit the warp tile");
@@ -443,6 +474,16 @@ int sfx_init_tables(int device, const sfx_tables_host* t) {
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(SFX_ERR_CUDA, "libsfx_b200 is built for sm_100a only");
     c.sm_count = prop.multiProcessorCount;
+    if (g_l2_mode != 0 && c.l2_persist == 0 && prop.persistingL2CacheMaxSize > 0) {
+        // set aside the most L2 the device allows for persisting accesses (79 of 126 MB on a B200); device-wide, once
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(prop.persistingL2CacheMaxSize)) == cudaSuccess) {
+            size_t got = 0;
+            if (cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize) == cudaSuccess) c.l2_persist = got;
+            c.l2_window = static_cast<size_t>(prop.accessPolicyMaxWindowSize);
+        } else {
+            cudaGetLastError();
+        }
+    }
     TableSet set;
     set.sr = t->sr;
     int rc;
@@ -459,6 +500,11 @@ int sfx_init_tables(int device, const sfx_tables_host* t) {
     if ((rc = upload(c, t->mel_src, 128 * 3, &set.tb.mel_src))) return rc;
     if ((rc = upload(c, t->chroma16, static_cast<size_t>(sfx::kTunings) * 2 * sfx::kChroma * sfx::kP16Stride, &set.tb.chroma16))) return rc;
     if ((rc = upload(c, t->chroma_ny, static_cast<size_t>(sfx::kTunings) * sfx::kChroma, &set.tb.chroma_ny))) return rc;
+    {
+        const uint32_t* frag = nullptr;
+        if ((rc = upload(c, t->chroma_frag, static_cast<size_t>(sfx::kTunings) * 32 * 2 * 2 * 32 * 4, &frag))) return rc;
+        set.tb.chroma_frag = reinterpret_cast<const uint4*>(frag);
+    }
     std::vector<double> dctT(static_cast<size_t>(sfx::kMels) * sfx::kMels);
     for (int k = 0; k < sfx::kMels; ++k)
         for (int m = 0; m < sfx::kMels; ++m) dctT[static_cast<size_t>(m) * sfx::kMels + k] = t->dct[static_cast<size_t>(k) * sfx::kMels + m];

@@ -258,6 +258,11 @@ __device__ __forceinline__ unsigned pack_half2(float a, float b) {
     return *reinterpret_cast<const unsigned*>(&h);
 }
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+// TMA bulk prefetch of a contiguous global range into L2 (one instruction, no registers, no completion to wait for);
+// ptr 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_prefetch_l2(const void* ptr, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
 
 // ---- TMA bulk copy (global -> shared) completing on an mbarrier
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }

@@ -40,6 +40,7 @@ struct DevTables {
     int mel_ps, mel_flush32;
     const uint16_t* chroma16;   // [100][2][12][1056] half: hi, lo * 2^11
     const float* chroma_ny;     // [100][12]
+    const uint4* chroma_frag;   // [100][32 steps][2 half steps][2 hi/lo][32 lanes] A fragments of the bank
     const double* dctT;     // [128 mel][128 k]  (transposed: coalesced over k)
     const double* edges;    // [101]
     int sr, kmin, kmax;
@@ -55,7 +56,9 @@ struct Params {
     float* out;
     long long out_stride;
     unsigned char* ws;
-    long long cta_scratch_bytes;
+    long long cta_scratch_bytes;    // fused: bytes of a CTA's slice without its FP16 |X|^2 and log-mel rows; split / stream: slice / slot
+    long long cta_p16_bytes;        // fused: bytes of a CTA's FP16 |X|^2 rows; all CTAs' rows form one block at ws + kWsHeader
+    long long cta_lm_bytes;         // fused: bytes of a CTA's log-mel rows; one block right behind the |X|^2 block, then the slices
     int Tmax;
     long long max_samples;  // the scratch slices hold 1 + max_samples / hop frames per clip
     int aligned8;
@@ -75,15 +78,21 @@ __device__ __forceinline__ long long clip_samples(const Params& p, int clip) {
 
 __host__ __device__ inline int rec_frames(int Tmax) { return (Tmax + kWarps - 1) / kWarps * kWarps; }
 
-// bytes of scratch one CTA needs for clips of up to Tmax frames (multiple of 256)
-inline size_t cta_scratch_bytes(int Tmax, int max_pk) {
-    // FP16 |X|^2 rows, log-mel rows, peak records (float4), peak keys (u32, overflow path), hop energy + Nyquist + 1/scale
-    // per frame, peak bins (u8)
-    // (records are kept in one segment per warp: capacity rounded up to kWarps frames)
-    size_t b = static_cast<size_t>(Tmax) * (kP16Stride * 2 + kMels * 4 + 12 + static_cast<size_t>(max_pk) * (4 + 1)) +
+// Fused kernel workspace: header | FP16 |X|^2 rows of all CTAs | log-mel rows of all CTAs | per-CTA slices (everything else).
+// The rows that phase 3 reads back are kept together so that ONE stream access-policy window can pin them in L2
+// (persisting set-aside): they are written once and read once ~100 us later, and would otherwise be pushed out to HBM by
+// the waveform stream in between.
+inline size_t cta_p16_bytes(int Tmax) { return (static_cast<size_t>(Tmax) * kP16Stride * 2 + 255) & ~static_cast<size_t>(255); }
+inline size_t cta_lm_bytes(int Tmax) { return (static_cast<size_t>(Tmax) * kMels * 4 + 255) & ~static_cast<size_t>(255); }
+// bytes of the rest of a CTA's scratch for clips of up to Tmax frames (multiple of 256)
+inline size_t cta_rest_bytes(int Tmax, int max_pk) {
+    // peak records (float4; one segment per warp: capacity rounded up to kWarps frames), peak keys (u32, overflow path),
+    // hop energy + Nyquist + 1/scale per frame, peak bins (u8)
+    size_t b = static_cast<size_t>(Tmax) * (12 + static_cast<size_t>(max_pk) * (4 + 1)) +
                static_cast<size_t>(rec_frames(Tmax)) * max_pk * 16;
     return (b + 255) & ~static_cast<size_t>(255);
 }
+inline size_t cta_scratch_bytes(int Tmax, int max_pk) { return cta_p16_bytes(Tmax) + cta_lm_bytes(Tmax) + cta_rest_bytes(Tmax, max_pk); }
 
 // ---- split pipeline (sfx_split.cu): workspace = header | per-clip peak counters | frame prefix | slices
 constexpr int kSplitChunkMax = 1024;                        // clips per chunk (prep kernel = one 1024-thread block)
@@ -105,15 +114,10 @@ inline size_t split_slice_bytes(int Tmax, int max_pk) {
 }
 
 // ---- stream pipeline (sfx_stream.cu): workspace = header (queue counter + clip order) | per CTA: stream_slots() slices
-// peak records of a slot are kept in one segment per warp of the 16-warp CTA; a segment holds the peaks of
-// ceil(Tmax / 12) frames, and a warp is only handed a frame of a clip while its segment has room for a full frame
-// (at least 13 of the 16 warps transform frames at any time, so a clip's frames always find room)
-__host__ __device__ inline int stream_seg_frames(int Tmax) { return (Tmax + 11) / 12; }
 inline size_t stream_slot_bytes(int Tmax, int max_pk) {
-    // FP16 |X|^2 rows, log-mel rows, hop energy / Nyquist / 1/scale / centroid / roll-off / row max / zero crossings per
-    // frame, peak keys (u32) + bins (u8) of the overflow path, record segments (float4)
-    size_t b = static_cast<size_t>(Tmax) * (kP16Stride * 2 + kMels * 4 + 8 * 4 + static_cast<size_t>(max_pk) * (4 + 1)) +
-               static_cast<size_t>(kStreamWarps) * stream_seg_frames(Tmax) * max_pk * 16;
+    // per frame: FP16 |X|^2 row, log-mel row, the record of per-frame values, max_pk peak records (float4: every frame owns
+    // a fixed segment, its fill level is part of the per-frame record), peak keys (u32) + bins (u8) of the overflow path
+    size_t b = static_cast<size_t>(Tmax) * (kP16Stride * 2 + kMels * 4 + 8 * 4 + static_cast<size_t>(max_pk) * (16 + 4 + 1));
     return (b + 255) & ~static_cast<size_t>(255);
 }
 size_t smem_stream();

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     int* s_hist = reinterpret_cast<int*>(s_mbar + 1);                        // [256]
     int* s_i = s_hist + 256;                                                 // [32]
     float* s_f = reinterpret_cast<float*>(s_i + 32);                         // [32]
+    float* s_lmin = s_f + 32;                                                // [kWarps][32]
+    double* s_lm = reinterpret_cast<double*>(s_lmin + kWarps * 32);          // [kWarps][128]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevTables& tb = p.tb;
@@ -64,11 +66,15 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         msrc[s] = q[0] | (q[1] << 10) | (q[2] << 20);
     }
 
-    // scratch slice of this CTA
-    unsigned char* slice = p.ws + kWsHeader + static_cast<size_t>(blockIdx.x) * p.cta_scratch_bytes;
-    __half* gP16 = reinterpret_cast<__half*>(slice);                                             // [Tmax][kP16Stride]
-    float* gL = reinterpret_cast<float*>(gP16 + static_cast<size_t>(p.Tmax) * kP16Stride);       // [Tmax][128]
-    float4* gRec = reinterpret_cast<float4*>(gL + static_cast<size_t>(p.Tmax) * kMels);
+    // scratch of this CTA: its rows inside the two blocks that hold every CTA's FP16 |X|^2 / log-mel rows (the L2-pinned
+    // part of the workspace), and its slice with the rest
+    unsigned char* rows0 = p.ws + kWsHeader;
+    __half* gP16 = reinterpret_cast<__half*>(rows0 + static_cast<size_t>(blockIdx.x) * p.cta_p16_bytes);           // [Tmax][kP16Stride]
+    float* gL = reinterpret_cast<float*>(rows0 + static_cast<size_t>(gridDim.x) * p.cta_p16_bytes +
+                                         static_cast<size_t>(blockIdx.x) * p.cta_lm_bytes);                        // [Tmax][128]
+    unsigned char* slice = rows0 + static_cast<size_t>(gridDim.x) * (p.cta_p16_bytes + p.cta_lm_bytes) +
+                           static_cast<size_t>(blockIdx.x) * p.cta_scratch_bytes;
+    float4* gRec = reinterpret_cast<float4*>(slice);
     const int seg_cap = rec_frames(p.Tmax) / kWarps * p.max_pk;               // peak records per warp segment
     unsigned* gKey = reinterpret_cast<unsigned*>(gRec + static_cast<size_t>(kWarps) * seg_cap);
     float* gE = reinterpret_cast<float*>(gKey + static_cast<size_t>(p.Tmax) * p.max_pk);        // hop energies [Tmax]
@@ -90,8 +96,9 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     FrameOut fo;
     fo.gP16 = gP16; fo.gL = gL; fo.gRec = gRec; fo.gE = gE; fo.gNy = gNy; fo.gInvS = gInvS;
     fo.npk = nullptr; fo.gSeg = gRec + static_cast<size_t>(warp) * seg_cap; fo.s_wacc = s_wacc; fo.s_f = s_f;
-    fo.gCent = nullptr; fo.gRoll = nullptr; fo.gLmax = nullptr; fo.gZc = nullptr; fo.gFv = nullptr;
-    const ClipSmem cs{s_ex, s_pool, s_wacc, s_edges, s_mbar, s_hist, s_i, s_f};
+    fo.s_lm = s_lm + warp * kMels; fo.s_lmin = s_lmin + warp * 32;
+    fo.gCent = nullptr; fo.gRoll = nullptr; fo.gLmax = nullptr; fo.gZc = nullptr; fo.gFv = nullptr; fo.cursor = nullptr;
+    const ClipSmem cs{s_ex, s_pool, s_wacc, s_edges, s_mbar, s_hist, s_i, s_f, s_lm, s_lmin};
     const ClipSlice sl{gP16, gL, gRec, gKey, gE, gNy, gInvS, gBin, seg_cap};
 
     for (;;) {
@@ -112,7 +119,10 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         // ===================================== phase 1: frames =====================================
         // per-warp running sums live in shared memory (s_wacc[warp][0..2] = centroid, rolloff, rms; s_f = log-mel max)
         if (lane < 2) s_wacc[warp * 16 + lane] = 0.0;
-        if (lane == 0) s_f[warp] = -FLT_MAX;
+        if (lane == 0) { s_f[warp] = -FLT_MAX; s_f[16 + warp] = 0.0f; }
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) fo.s_lm[32 * s4 + lane] = 0.0;
+        fo.s_lmin[lane] = FLT_MAX;
         int acc_zc = 0, wcount = 0;
         __syncwarp();
 
@@ -176,7 +186,8 @@ cudaError_t launch_order(const int32_t* lengths, int B, int* order, cudaStream_t
 
 size_t smem_bytes() {
     return sizeof(float2) * (2560 + 17 * 64) + sizeof(float) * kWarps * kExFloats +
-           sizeof(double) * (256 + kWarps * 16 + 104 + 1) + sizeof(int) * (256 + 32) + sizeof(float) * 32;
+           sizeof(double) * (256 + kWarps * 16 + 104 + 1) + sizeof(int) * (256 + 32) + sizeof(float) * (32 + kWarps * 32) +
+           sizeof(double) * kWarps * kMels;
 }
 
 cudaError_t configure_kernels(int* blocks_per_sm) {

@@ -27,16 +27,22 @@ struct FrameOut {
     int* npk;                                                                          // split: the clip's peak counter
     float4* gSeg;                                                                      // fused: this warp's record segment
     double* s_wacc; float* s_f;                                                        // fused: per-warp accumulators
+    double* s_lm;         // fused: this warp's float64 sums of the log-mel rows of its non-zero frames [128]
+    float* s_lmin;        // fused: this warp's per-lane minimum of those rows [32]
     float* gCent; float* gRoll; float* gLmax; int* gZc;                                // split: per-frame values
     float* gFv;           // stream: per-frame values as one record of kFvStride floats per frame (one live pointer
-                          // instead of seven): [0] hop energy, [1] scaled Nyquist |X|^2, [2] 1/scale, [3] centroid,
+                          // instead of seven): [0] scaled Nyquist |X|^2, [1] 1/scale, [2] hop energy, [3] centroid,
                           // [4] roll-off, [5] row max of log-mel, [6] weighted zero crossings (int), [7] unused
+    int* cursor;          // stream: fill level of the slot's dense peak-record array gRec (shared memory, atomicAdd)
 };
 constexpr int kFvStride = 8;
 
 // shared memory of phases 2-3
 struct ClipSmem {
     float* s_ex; double* s_pool; double* s_wacc; double* s_edges; unsigned long long* s_mbar; int* s_hist; int* s_i; float* s_f;
+    const double* s_lm;   // fused: [kWarps][128] per-warp float64 sums of the unclamped log-mel rows of the non-zero frames,
+    const float* s_lmin;  //        [kWarps][32] per-lane minima of those rows, s_f[16 + w] = all-zero frames seen by warp w
+                          //        (nullptr in the split pipeline: phase 3a then always reads the rows back)
 };
 
 struct ClipSlice {
@@ -84,7 +90,7 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
                 fo.gNy[t] = 0.0f;
                 fo.gInvS[t] = 0.0f;
                 if constexpr (kFrameVals) { fo.gCent[t] = 0.0f; fo.gRoll[t] = 0.0f; fo.gLmax[t] = lm0; fo.gZc[t] = 0; }
-                else fo.s_f[warp] = fmaxf(fo.s_f[warp], lm0);
+                else { fo.s_f[warp] = fmaxf(fo.s_f[warp], lm0); fo.s_f[16 + warp] += 1.0f; }
             }
             if (kDebug) {
                 if (t < p.dbg.T_dbg) {
@@ -113,7 +119,7 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
         for (int m1 = 16; m1 < 24; ++m1) { he = fmaf(re[m1], re[m1], he); he = fmaf(im[m1], im[m1], he); }
         he = warp_sum(he);
         if (lane == 0) {
-            if constexpr (kStream) fo.gFv[static_cast<size_t>(t) * kFvStride] = he;
+            if constexpr (kStream) fo.gFv[static_cast<size_t>(t) * kFvStride + 2] = he;
             else fo.gE[t] = he;
         }
     }
@@ -310,8 +316,8 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
             if constexpr (kStream) {
-                if (lane == 31) fo.gFv[static_cast<size_t>(t) * kFvStride + 1] = fs.Pb[pidx(1024)] * scale;
-                if (lane == 0) fo.gFv[static_cast<size_t>(t) * kFvStride + 2] = __uint_as_float((254u << 23) - sbits);
+                if (lane == 31) fo.gFv[static_cast<size_t>(t) * kFvStride] = fs.Pb[pidx(1024)] * scale;
+                if (lane == 0) fo.gFv[static_cast<size_t>(t) * kFvStride + 1] = __uint_as_float((254u << 23) - sbits);
             } else {
                 if (lane == 31) fo.gNy[t] = fs.Pb[pidx(1024)] * scale;
                 if (lane == 0) fo.gInvS[t] = __uint_as_float((254u << 23) - sbits);      // 1/scale, exact
@@ -361,7 +367,7 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
     // ---- log-mel rows: filter m = 32*s + lane adds its (<= 3) partial sums in a fixed order
     {
         float* Lg = fo.gL + static_cast<size_t>(t) * kMels;
-        float gmax = -FLT_MAX;
+        float gmax = -FLT_MAX, gmin = FLT_MAX;
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4) {
             const int ms = fs.msrc[s4];
@@ -369,11 +375,17 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             const float lm = 3.01029995663981195f * __log2f(fmaxf(1e-10f, mel));   // 10*log10(x)
             Lg[32 * s4 + lane] = lm;
             gmax = fmaxf(gmax, lm);
+            if constexpr (kMode == kModeFused) {       // running sums / minimum for the clamp-free MFCC pooling (phase 3a)
+                fo.s_lm[32 * s4 + lane] += static_cast<double>(lm);
+                gmin = fminf(gmin, lm);
+            }
             if (kDebug) {
                 if (p.dbg.logmel && t < p.dbg.T_dbg)
                     p.dbg.logmel[(static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kMels + 32 * s4 + lane] = lm;
             }
         }
+        if constexpr (kMode == kModeFused) fo.s_lmin[lane] = fminf(fo.s_lmin[lane], gmin);
+        (void)gmin;
         gmax = warp_max(gmax);
         if (lane == 0) {
             if constexpr (kStream) fo.gFv[static_cast<size_t>(t) * kFvStride + 5] = gmax;
@@ -384,7 +396,43 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
 
     // ---- piptrack peak detection on the power spectrum (bins kmin..kmax); the per-peak arithmetic
     //      (parabolic shift, pitch, tuning residual) is done in phase 2 on the compacted records
-    if constexpr (!kSplit) {
+    if constexpr (kStream) {
+        // one pass per chunk of <= 14 rows: the chunk's peaks are ballot-compacted into the tile's mel partial-sum area
+        // (free since the log-mel rows above; 239 records, a row holds <= 16 peaks), then appended, densely and with
+        // coalesced 128-bit stores, to the slot's record array behind one shared-memory atomicAdd.  The tail reads the
+        // records as one dense array whatever warp produced them, in whatever order (median and histogram do not care).
+        const float ref = __fmul_rn(0.1f, pmax);
+        const int kfirst = tb.kmin + lane;
+        const float* q0 = fs.Pb + pidx(kfirst - 1);
+        const float* q1 = fs.Pb + pidx(kfirst);
+        const float* q2 = fs.Pb + pidx(kfirst + 1);
+        const int nrows = (tb.kmax - tb.kmin + 32) >> 5;
+        const int rmax = (tb.kmax - kfirst) >> 5;
+        const unsigned lt = (1u << lane) - 1u;
+        float4* stage = reinterpret_cast<float4*>(fs.part);
+        constexpr int kChunkRows = (kExFloats - kPartOff) / 4 / 16;          // 14
+        for (int r0 = 0; r0 < nrows; r0 += kChunkRows) {
+            const int r1 = min(nrows, r0 + kChunkRows);
+            unsigned cnt = 0;
+#pragma unroll 4
+            for (int r = r0; r < r1; ++r) {
+                const int off = kPRow * r;
+                const float pm = q0[off], pc = q1[off], pp = q2[off];
+                const bool pk = (r <= rmax) & (pc > ref) & (pc > pm) & (pc >= pp);
+                const unsigned bal = __ballot_sync(0xffffffffu, pk);
+                if (pk) stage[cnt + __popc(bal & lt)] = make_float4(pm, pc, pp, __int_as_float(kfirst + 32 * r));
+                cnt += __popc(bal);
+            }
+            __syncwarp();
+            if (cnt) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(fo.cursor, static_cast<int>(cnt));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (unsigned i = lane; i < cnt; i += 32) fo.gRec[base + i] = stage[i];
+            }
+            __syncwarp();
+        }
+    } else if constexpr (!kSplit) {
         // one pass: a row of 32 bins is tested and its peaks are appended (ballot-compacted) to this warp's own record
         // segment of the clip, whose fill level `wcount` the warp carries in a register -- no atomics, no second pass
         const float ref = __fmul_rn(0.1f, pmax);
@@ -723,14 +771,44 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
                       2 * kChroma * kP16Stride * 2, cs.s_mbar);
     {
         const float clampv = __fsub_rn(gmx, 80.0f);
-        if (tid < 256) {
-            const int m = tid & 127, h = tid >> 7;
-            double a = 0.0;
-            for (int t = h; t < T; t += 2) a += static_cast<double>(fmaxf(sl.gL[static_cast<size_t>(t) * kMels + m], clampv));
-            cs.s_pool[h * 128 + m] = a;
+        // power_to_db's clamp max(L, gmax - 80) is the identity on every non-zero frame of most clips (it exists for the
+        // zero tail load_audio pads short clips with, whose rows are the constant 10*log10(1e-10) exactly): phase 1 keeps
+        // per-warp float64 sums of the unclamped rows of its non-zero frames and their minimum, and when that minimum is
+        // not below the clamp the pooled mean follows from the sums and the count of all-zero frames without reading the
+        // [T][128] rows back.  Sums of float32 values in float64 are exact here (53 bits hold 24-bit values over this
+        // range), so both forms give the same bits; otherwise the rows are read (same arithmetic as ever).
+        bool fast = false;
+        if (cs.s_lm != nullptr) {
+            float lmin = cs.s_lmin[tid & (kWarps * 32 - 1)];
+            lmin = -warp_max(-lmin);
+            if (lane == 0) cs.s_f[24 + warp] = lmin;
+            __syncthreads();
+            lmin = cs.s_f[24];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) lmin = fminf(lmin, cs.s_f[24 + w]);
+            fast = lmin >= clampv;
         }
-        __syncthreads();
-        if (tid < 128) cs.s_pool[tid] = (cs.s_pool[tid] + cs.s_pool[128 + tid]) / static_cast<double>(T);
+        if (fast) {
+            if (tid < 128) {
+                float nz = cs.s_f[16];
+#pragma unroll
+                for (int w = 1; w < kWarps; ++w) nz += cs.s_f[16 + w];
+                const float lm0 = 3.01029995663981195f * __log2f(1e-10f);
+                double a = static_cast<double>(nz) * static_cast<double>(fmaxf(lm0, clampv));
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) a += cs.s_lm[w * kMels + tid];
+                cs.s_pool[tid] = a / static_cast<double>(T);
+            }
+        } else {
+            if (tid < 256) {
+                const int m = tid & 127, h = tid >> 7;
+                double a = 0.0;
+                for (int t = h; t < T; t += 2) a += static_cast<double>(fmaxf(sl.gL[static_cast<size_t>(t) * kMels + m], clampv));
+                cs.s_pool[h * 128 + m] = a;
+            }
+            __syncthreads();
+            if (tid < 128) cs.s_pool[tid] = (cs.s_pool[tid] + cs.s_pool[128 + tid]) / static_cast<double>(T);
+        }
         __syncthreads();
         if (tid < p.n_mfcc) {
             double d = 0.0;

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_frames_kernel(const SplitPara
         FrameOut fo;
         fo.gP16 = sl.gP16; fo.gL = sl.gL; fo.gRec = sl.gRec; fo.gE = sl.gE; fo.gNy = sl.gNy; fo.gInvS = sl.gInvS;
         fo.npk = npk_all + c; fo.gSeg = nullptr; fo.s_wacc = nullptr; fo.s_f = nullptr;
-        fo.gCent = sl.gCent; fo.gRoll = sl.gRoll; fo.gLmax = sl.gLmax; fo.gZc = sl.gZc; fo.gFv = nullptr;
+        fo.gCent = sl.gCent; fo.gRoll = sl.gRoll; fo.gLmax = sl.gLmax; fo.gZc = sl.gZc; fo.gFv = nullptr; fo.cursor = nullptr; fo.s_lm = nullptr; fo.s_lmin = nullptr;
         int unused_zc = 0, unused_cnt = 0;
         process_frame<kDebug, kModeSplit>(p, tb, fs, fo, x, n, T, t, clip, lane, warp, unused_zc, unused_cnt);
     }
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_clips_kernel(const SplitParam
     unsigned bank_parity = 0;
     int* queue = reinterpret_cast<int*>(p.ws);
     const int* npk_all = reinterpret_cast<const int*>(p.ws + kSplitNpkOff);
-    const ClipSmem cs{s_ex, s_pool, s_wacc, s_edges, s_mbar, s_hist, s_i, s_f};
+    const ClipSmem cs{s_ex, s_pool, s_wacc, s_edges, s_mbar, s_hist, s_i, s_f, nullptr, nullptr};
 
     for (;;) {
         __syncthreads();

@@ -4,24 +4,31 @@
 // The fused kernel (sfx_kernels.cu) runs a clip's tail (tuning estimate, MFCC, chroma, pooled row) with all 8 warps of its
 // CTA: the tail holds ~12 % of the instructions but 25-40 % of a CTA's time, because it is a chain of scratch round trips
 // and CTA barriers, and it only overlaps with FFT work of the *other* co-resident CTA.  Here every warp is an independent
-// worker that pulls items from a CTA-local scheduler (a few words of shared memory behind a spin lock):
+// worker that pulls items from a CTA-local scheduler (a few words of shared memory, lock-free on the hot path: one 64-bit
+// atomicAdd hands out a frame):
 //   FRAME(slot, t)  phase 1 of STFT frame t of the clip in `slot` (process_frame<., kModeStream>: the code of the other
 //                   pipelines); frames of the next clip are handed out as soon as the current clip's last frame has been
 //                   *taken*, so there is no per-clip barrier and no round imbalance (130 frames over 8 warps);
 //   TAIL(slot)      phases 2-3 of a clip whose frames are all done, executed by ONE warp from start to end
 //                   (clip_tail_warp below: no CTA barrier anywhere).  A tail is latency-bound whoever runs it; run by one
 //                   warp it costs one warp's time instead of eight, and the other 15 keep transforming frames.
-// A CTA owns kSlots scratch slices; a slot is FREE -> FRAMES -> READY -> TAIL -> FREE.  Per-frame descriptors are stored in
-// the slice and summed by the tail warp in frame order, peak records go to the (slot, warp) segment of whichever warp ran
-// the frame, so the pooled row does not depend on which warp ran which frame.
+// A CTA owns kSlots scratch slices; a slot is free -> frames being handed out / run -> ready (tail pending) -> tail -> free.  Per-frame descriptors are stored in
+// the slice and summed by the tail warp in frame order, every frame owns a fixed segment of the slot's peak-record buffer,
+// so the pooled row does not depend on which warp ran which frame.
 //
 // Chroma in the tail: raw = W . |X|^2 on the tensor cores (m16n8k16, FP16 hi/lo bank, FP32 accumulate) with the bank read
 // straight from L2 (all 100 banks are 5 MB and resident): a bank fragment is applied to 32 frames (4 MMA N-tiles) per load,
 // so no shared-memory copy of the bank is needed and any number of tails can run side by side.
 #include "sfx_phases.cuh"
 
+#ifndef SFX_TAIL_SKIP          // experiment: bit 0 skip phase 2, bit 1 skip MFCC, bit 2 skip chroma (rows are then garbage)
+#define SFX_TAIL_SKIP 0
+#endif
+#ifndef SFX_TAIL_CG            // experiment: 1 = the tail's streaming loads bypass L1 (ld.global.cg)
+#define SFX_TAIL_CG 0
+#endif
 #ifndef SFX_STREAM_SLOTS
-#define SFX_STREAM_SLOTS 4
+#define SFX_STREAM_SLOTS 6
 #endif
 
 namespace sfx {
@@ -37,30 +44,75 @@ constexpr int kTRedoCap = 64;
 constexpr int kTKeys = 384;          // u32[kTKeyCap] keys, then u8[kTKeyCap] bins
 constexpr int kTKeyCap = ((kExFloats - kTKeys) * 4 / 5) & ~3;
 
-enum : int { kFree = 0, kFrames = 1, kReady = 2, kTail = 3 };
 enum : int { kWorkExit = 0, kWorkWait = 1, kWorkFrame = 2, kWorkTail = 3, kWorkBad = 4 };
 
 struct Sched {                       // shared memory, every field accessed through volatile or atomics
-    int lock, qdone;
-    int state[kSlots], clip[kSlots], T[kSlots], next[kSlots], done[kSlots];
+    unsigned hot;                    // frame ticket [gen:8 | t:24] of the clip being handed out: atomicAdd(&hot, 1) returns a
+                                     // consistent (gen, t); ring_T / ring_slot[gen & 7] describe generation gen (valid until
+                                     // 8 more clips have been opened); t < T means "frame t of that clip is yours"
+    int ring_slot[8], ring_T[8];
+    int ready_mask;                  // bit s: all frames of slot s are done, its tail is up for grabs
+    int free_mask;                   // bit s: slot s is free
+    int active;                      // slots that are not free
+    int qdone;                       // the batch's clip queue is exhausted
+    int opener;                      // spin lock of the (rare) "put the next clip into a free slot" path
+    int clip[kSlots], T[kSlots], done[kSlots];
+    int npk[kSlots];                 // peak records appended to the slot's dense record array so far
     long long n[kSlots];
-    int cnt[kSlots][kSW];            // peak records in segment (slot, warp)
 };
+static_assert(kSlots >= 2 && kSlots <= 8, "slot masks are 8 bits wide");
+
+#ifdef SFX_STREAM_DIAG
+// cycle counters per (CTA, warp): 0 frames, 1 tails, 2 waiting, 3 scheduler calls, 4 frames run, 5 tails run,
+// 6 tail: sums + phase 2 per-peak loop, 7 tail: median + histogram, 8 tail: MFCC, 9 tail: chroma, 10 tail: epilogue, 11 peaks
+__device__ long long g_prof[148 * 16 * 16];
+#define PROF_ADD(k, v) do { if (lane == 0) g_prof[(blockIdx.x * 16 + (threadIdx.x >> 5)) * 16 + (k)] += (v); } while (0)
+extern "C" int sfx_stream_prof(long long* out, int n, int reset) {
+    int rc = static_cast<int>(cudaMemcpyFromSymbol(out, g_prof, sizeof(long long) * n));
+    if (reset) {
+        static long long zeros[148 * 16 * 16];
+        rc |= static_cast<int>(cudaMemcpyToSymbol(g_prof, zeros, sizeof(zeros)));
+    }
+    return rc;
+}
+__device__ int g_diag[148 * 16 * 24];
+__device__ void diag_dump(Sched* sc, int warp, int reason) {
+    volatile Sched* v = sc;
+    int* d = g_diag + (blockIdx.x * 16 + warp) * 24;
+    d[0] = reason; d[1] = v->opener; d[2] = v->qdone; d[3] = v->ready_mask; d[4] = v->free_mask; d[5] = v->active;
+    d[6] = static_cast<int>(v->hot >> 24); d[7] = static_cast<int>(v->hot & 0xffffffu);
+    for (int s = 0; s < kSlots && s < 4; ++s) { d[11 + s] = v->done[s]; d[15 + s] = v->T[s]; d[19 + s] = v->clip[s]; }
+}
+extern "C" int sfx_stream_diag(int* out, int n) {
+    return static_cast<int>(cudaMemcpyFromSymbol(out, g_diag, sizeof(int) * n));
+}
+#endif
+
+#ifndef SFX_STREAM_DIAG
+#define PROF_ADD(k, v) do { } while (0)
+#endif
 
 struct StreamSlice {
     __half* gP16; float* gL; float* gFv; float4* gRec; unsigned* gKey; unsigned char* gBin;
 };
 
-// layout of a slot: FP16 |X|^2 rows | log-mel rows | per-frame value records | record segments | keys | bins
+// layout of a slot: FP16 |X|^2 rows | log-mel rows | per-frame value records | peak records (max_pk per frame) | keys | bins
 __device__ __forceinline__ StreamSlice stream_slice(unsigned char* base, int Tmax, int max_pk) {
     StreamSlice s;
     s.gP16 = reinterpret_cast<__half*>(base);
     s.gL = reinterpret_cast<float*>(s.gP16 + static_cast<size_t>(Tmax) * kP16Stride);
     s.gFv = s.gL + static_cast<size_t>(Tmax) * kMels;
     s.gRec = reinterpret_cast<float4*>(s.gFv + static_cast<size_t>(Tmax) * kFvStride);
-    s.gKey = reinterpret_cast<unsigned*>(s.gRec + static_cast<size_t>(kSW) * stream_seg_frames(Tmax) * max_pk);
+    s.gKey = reinterpret_cast<unsigned*>(s.gRec + static_cast<size_t>(Tmax) * max_pk);
     s.gBin = reinterpret_cast<unsigned char*>(s.gKey + static_cast<size_t>(Tmax) * max_pk);
     return s;
+}
+
+// ------------------------------------------------------------------------------------------------ one-warp histogram update
+// (measured: aggregating equal bins with match.any and a plain read-modify-write by the lowest lane is slower than the
+// shared-memory atomic -- noise clips 1.14 -> 0.94 M clips/s)
+static __device__ __forceinline__ void hist_add(int* hist, const bool valid, const unsigned bin, const int) {
+    if (valid) atomicAdd(&hist[bin], 1);
 }
 
 // ------------------------------------------------------------------------------------------------ one-warp radix select
@@ -80,13 +132,16 @@ static __device__ __forceinline__ unsigned radix_select_warp(const unsigned* key
 #pragma unroll
         for (int q = 0; q < 8; ++q) hist[lane + 32 * q] = 0;
         __syncwarp();
-        for (int i0 = lane; i0 < np; i0 += 128) {
+        for (int ib = 0; ib < np; ib += 128) {                 // warp-uniform trip count (match / syncwarp inside)
+            const int i0 = ib + lane;
             unsigned k[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) k[u] = (i0 + 32 * u < np) ? keys[i0 + 32 * u] : 0u;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i0 + 32 * u < np && (k[u] & mask) == prefix) atomicAdd(&hist[(k[u] >> shift) & bmask], 1);
+            for (int u = 0; u < 4; ++u) {
+                const bool valid = i0 + 32 * u < np && (k[u] & mask) == prefix;
+                hist_add(hist, valid, (k[u] >> shift) & bmask, lane);
+            }
         }
         __syncwarp();
         int loc[8], sum = 0;
@@ -127,9 +182,34 @@ static __device__ __forceinline__ unsigned radix_select_warp(const unsigned* key
     return prefix;
 }
 
+template <class T>
+static __device__ __forceinline__ T tail_ld(const T* ptr) {
+#if SFX_TAIL_CG
+    return __ldcg(ptr);
+#else
+    return *ptr;
+#endif
+}
+static __device__ __forceinline__ uint4 tail_ldc(const uint4* ptr) {     // constant table
+#if SFX_TAIL_CG
+    return __ldcg(ptr);
+#else
+    return __ldg(ptr);
+#endif
+}
+
+// One frame's contribution to the pooled chroma of rows g and g+8: librosa.util.normalize(norm=inf) -- raw / max|raw| over
+// the 12 classes, with lengths below tiny(float32) (in unscaled units) replaced by 1.  Not inlined: the IEEE division is
+// ~40 instructions with a slow path, and the tail's code size is what its single warp pays for (instruction fetch).
+static __device__ __noinline__ float2 chroma_norm(const float r0, const float r1, const float mx, const float inv_s) {
+    const bool small = mx * inv_s < FLT_MIN;
+    return small ? make_float2(r0 * inv_s, r1 * inv_s) : make_float2(__fdiv_rn(r0, mx), __fdiv_rn(r1, mx));
+}
+
 // ------------------------------------------------------------------------------------------------ chroma of <= 32 frames
 struct ChromaLane {
-    const uint4 *whi0, *whi1, *wlo0, *wlo1;      // this lane's bank rows g, g+8 (hi and lo halves) at its 8 bins of a step
+    const uint4* frag;                           // this lane's A fragments of the tuning's bank: + 128 per 32-bin step,
+                                                 // + 0 / 32 / 64 / 96 = (half step 0 hi, lo, half step 1 hi, lo)
     float wny0, wny1;                            // Nyquist-bin weights of chroma g, g+8
     int g, t4;
 };
@@ -150,27 +230,27 @@ static __device__ __forceinline__ void chroma_group(const ChromaLane& cl, const 
     for (int j = 0; j < NT; ++j)
 #pragma unroll
         for (int q = 0; q < 4; ++q) { acc[j][q] = 0.f; acl[j][q] = 0.f; }
-    uint4 h0 = __ldg(cl.whi0), h1 = __ldg(cl.whi1), l0 = __ldg(cl.wlo0), l1 = __ldg(cl.wlo1);
+    uint4 h0 = tail_ldc(cl.frag), l0 = tail_ldc(cl.frag + 32), h1 = tail_ldc(cl.frag + 64), l1 = tail_ldc(cl.frag + 96);
     uint4 pv[NT];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) pv[j] = prow[j][0];
+    for (int j = 0; j < NT; ++j) pv[j] = tail_ld(prow[j]);
 #pragma unroll 2
     for (int s = 0; s < 32; ++s) {                                  // 32 bins per step; uint4 index = 4 * s (32 halves)
-        const int sn = min(s + 1, 31) * 4;
-        const uint4 nh0 = __ldg(cl.whi0 + sn), nh1 = __ldg(cl.whi1 + sn);
-        const uint4 nl0 = __ldg(cl.wlo0 + sn), nl1 = __ldg(cl.wlo1 + sn);
+        const int sn = min(s + 1, 31);
+        const uint4* fn = cl.frag + sn * 128;
+        const uint4 nh0 = tail_ldc(fn), nl0 = tail_ldc(fn + 32), nh1 = tail_ldc(fn + 64), nl1 = tail_ldc(fn + 96);
         uint4 npv[NT];
 #pragma unroll
-        for (int j = 0; j < NT; ++j) npv[j] = prow[j][sn];
+        for (int j = 0; j < NT; ++j) npv[j] = tail_ld(prow[j] + sn * 4);
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            mma_f16(acc[j], h0.x, h1.x, h0.y, h1.y, pv[j].x, pv[j].y);
-            mma_f16(acl[j], l0.x, l1.x, l0.y, l1.y, pv[j].x, pv[j].y);
+        for (int j = 0; j < NT; ++j) {                              // half step 0: bins 8*t4 .. +3 of the step
+            mma_f16(acc[j], h0.x, h0.y, h0.z, h0.w, pv[j].x, pv[j].y);
+            mma_f16(acl[j], l0.x, l0.y, l0.z, l0.w, pv[j].x, pv[j].y);
         }
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            mma_f16(acc[j], h0.z, h1.z, h0.w, h1.w, pv[j].z, pv[j].w);
-            mma_f16(acl[j], l0.z, l1.z, l0.w, l1.w, pv[j].z, pv[j].w);
+        for (int j = 0; j < NT; ++j) {                              // half step 1: bins 8*t4 + 4 .. +7
+            mma_f16(acc[j], h1.x, h1.y, h1.z, h1.w, pv[j].z, pv[j].w);
+            mma_f16(acl[j], l1.x, l1.y, l1.z, l1.w, pv[j].z, pv[j].w);
         }
         h0 = nh0; h1 = nh1; l0 = nl0; l1 = nl1;
 #pragma unroll
@@ -182,8 +262,8 @@ static __device__ __forceinline__ void chroma_group(const ChromaLane& cl, const 
     for (int j = 0; j < NT; ++j) {
         const int fa = f0 + 8 * j + 2 * cl.t4;                      // this lane's two frames of tile j
         const int fc0 = min(fa, T - 1), fc1 = min(fa + 1, T - 1);
-        const float2 ns0 = *reinterpret_cast<const float2*>(sl.gFv + static_cast<size_t>(fc0) * kFvStride + 1);   // (Ny, 1/scale)
-        const float2 ns1 = *reinterpret_cast<const float2*>(sl.gFv + static_cast<size_t>(fc1) * kFvStride + 1);
+        const float2 ns0 = *reinterpret_cast<const float2*>(sl.gFv + static_cast<size_t>(fc0) * kFvStride);   // (Ny, 1/scale)
+        const float2 ns1 = *reinterpret_cast<const float2*>(sl.gFv + static_cast<size_t>(fc1) * kFvStride);
         const float pn0 = ns0.x, pn1 = ns1.x, is0 = ns0.y, is1 = ns1.y;
         const float r00 = fmaf(cl.wny0, pn0, fmaf(acl[j][0], kLo, acc[j][0]));      // chroma g,   frame fa
         const float r01 = fmaf(cl.wny0, pn1, fmaf(acl[j][1], kLo, acc[j][1]));      // chroma g,   frame fa+1
@@ -196,16 +276,15 @@ static __device__ __forceinline__ void chroma_group(const ChromaLane& cl, const 
             m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
             m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
         }
-        // librosa.util.normalize: lengths below tiny(float32) are replaced by 1 (in unscaled units)
         if (fa < T) {
-            const bool small = m0 * is0 < FLT_MIN;
-            cs0 += static_cast<double>(small ? r00 * is0 : __fdiv_rn(r00, m0));
-            if (hi_row) cs1 += static_cast<double>(small ? r10 * is0 : __fdiv_rn(r10, m0));
+            const float2 v = chroma_norm(r00, r10, m0, is0);
+            cs0 += static_cast<double>(v.x);
+            if (hi_row) cs1 += static_cast<double>(v.y);
         }
         if (fa + 1 < T) {
-            const bool small = m1 * is1 < FLT_MIN;
-            cs0 += static_cast<double>(small ? r01 * is1 : __fdiv_rn(r01, m1));
-            if (hi_row) cs1 += static_cast<double>(small ? r11 * is1 : __fdiv_rn(r11, m1));
+            const float2 v = chroma_norm(r01, r11, m1, is1);
+            cs0 += static_cast<double>(v.x);
+            if (hi_row) cs1 += static_cast<double>(v.y);
         }
     }
 }
@@ -213,11 +292,29 @@ static __device__ __forceinline__ void chroma_group(const ChromaLane& cl, const 
 // ------------------------------------------------------------------------------------------------ tail of one clip, one warp
 // Phases 2-3 + the pooled row (the arithmetic of clip_tail in sfx_phases.cuh, reorganised for 32 threads and no barrier).
 template <bool kDebug>
-static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned char* slot_base, const volatile int* seg_cnt,
-                                                   const int seg_cap, float* tile, const double* s_edges, const int clip,
-                                                   const int T, float* __restrict__ out, const int lane) {
+static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned char* slot_base, float* tile,
+                                                   const double* s_edges, const int clip, const int T, const int np,
+                                                   float* __restrict__ out, const int lane) {
     const DevTables& tb = p.tb;
     const StreamSlice sl = stream_slice(slot_base, p.Tmax, p.max_pk);
+    // The slice was written tens of microseconds ago by the frame warps and has mostly left L2 since; one warp reading it
+    // back is bound by the round trip of each load.  Bulk L2 prefetches (one instruction per range) start the DRAM reads
+    // of everything the tail will stream well before it gets there: the peak records and the log-mel rows now, the
+    // FP16 |X|^2 rows one 32-frame group ahead of the chroma loop.
+    if (lane == 0) {
+        if (np > 0) {
+            for (int off = 0; off < np; off += 4096)
+                bulk_prefetch_l2(sl.gRec + off, static_cast<unsigned>(min(4096, np - off)) * 16u);
+        }
+        for (int t0 = 0; t0 < T; t0 += 64) bulk_prefetch_l2(sl.gL + static_cast<size_t>(t0) * kMels, static_cast<unsigned>(min(64, T - t0)) * kMels * 4u);
+        bulk_prefetch_l2(sl.gP16, static_cast<unsigned>(min(32, T)) * kP16Stride * 2u);
+    }
+#ifdef SFX_STREAM_DIAG
+    long long tp0 = clock64();
+#define PHASE_MARK(k) do { const long long tp1 = clock64(); PROF_ADD(k, tp1 - tp0); tp0 = tp1; } while (0)
+#else
+#define PHASE_MARK(k) do { } while (0)
+#endif
     int* hist = reinterpret_cast<int*>(tile + kTHist);
     uint2* redo_list = reinterpret_cast<uint2*>(tile + kTRedo);
 
@@ -226,7 +323,7 @@ static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned cha
     long long sum_z = 0;
     float gmx = -FLT_MAX;
     for (int t = lane; t < T; t += 32) {
-        const float4 a = *reinterpret_cast<const float4*>(sl.gFv + static_cast<size_t>(t) * kFvStride);        // E, Ny, 1/s, cent
+        const float4 a = *reinterpret_cast<const float4*>(sl.gFv + static_cast<size_t>(t) * kFvStride);        // Ny, 1/s, E, cent
         const float4 b = *reinterpret_cast<const float4*>(sl.gFv + static_cast<size_t>(t) * kFvStride + 4);    // roll, lmax, zc, -
         sum_c += static_cast<double>(a.w);
         sum_r += static_cast<double>(b.x);
@@ -242,33 +339,23 @@ static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned cha
     gmx = warp_max(gmx);
 
     // ===================================== phase 2: tuning =====================================
-    int np = 0;
-#pragma unroll
-    for (int w = 0; w < kSW; ++w) np += seg_cnt[w];
     int tuning_idx = kTunings / 2;
     float thr = 0.0f;
     int nsel = 0, ndiff = 0;
-    if (np > 0) {
+    if (np > 0 && !(SFX_TAIL_SKIP & 1)) {
         const bool in_smem = np <= kTKeyCap;
         unsigned* keys = in_smem ? reinterpret_cast<unsigned*>(tile + kTKeys) : sl.gKey;
         unsigned char* bins = in_smem ? reinterpret_cast<unsigned char*>(tile + kTKeys + kTKeyCap) : sl.gBin;
-        // dense peak index -> record: indices only grow, so the segment boundaries are walked once
-        int seg_w = 0, seg_end = seg_cnt[0], seg_adj = 0;
         auto fetch = [&](int i) -> float4 {
-            if (i >= np) return make_float4(0.f, 1.f, 1.f, __int_as_float(64));       // harmless stand-in past the end
-            while (i >= seg_end) {
-                seg_adj += seg_cap - seg_cnt[seg_w];
-                ++seg_w;
-                seg_end += seg_cnt[seg_w];
-            }
-            return sl.gRec[i + seg_adj];
+            return i < np ? tail_ld(sl.gRec + i) : make_float4(0.f, 1.f, 1.f, __int_as_float(64));   // stand-in past the end
         };
         unsigned kor = 0u, kand = 0xffffffffu;
         int nredo = 0;
         float4 nxt[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) nxt[u] = fetch(lane + u * 32);
-        for (int i0 = lane; i0 < np; i0 += 128) {
+        for (int ib = 0; ib < np; ib += 128) {                 // warp-uniform trip count: the body holds a ballot
+            const int i0 = ib + lane;
             float4 recs[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -350,16 +437,12 @@ static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned cha
             bins[e.x] = static_cast<unsigned char>(peak_bin_exact(__uint_as_float(e.y), s_edges));
         }
         __syncwarp();
+        PHASE_MARK(6);
+        PROF_ADD(11, np);
         if (kDebug) {
             // every peak again with the reference forms only; keys / bins must be identical
-            int sw = 0, send = seg_cnt[0], sadj = 0;
             for (int i = lane; i < np; i += 32) {
-                while (i >= send) {
-                    sadj += seg_cap - seg_cnt[sw];
-                    ++sw;
-                    send += seg_cnt[sw];
-                }
-                const float4 rc = sl.gRec[i + sadj];
+                const float4 rc = sl.gRec[i];
                 const float sh = peak_shift_exact(rc.x, rc.y, rc.z);
                 const float avg = __fsub_rn(rc.z, rc.x) * 0.5f;
                 const unsigned key = fkey(__fadd_rn(rc.y, __fmul_rn(__fmul_rn(0.5f, avg), sh)));
@@ -389,7 +472,8 @@ static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned cha
 #pragma unroll
         for (int q = 0; q < 4; ++q) hist[lane + 32 * q] = 0;
         __syncwarp();
-        for (int i0 = lane; i0 < np; i0 += 128) {
+        for (int ib = 0; ib < np; ib += 128) {
+            const int i0 = ib + lane;
             unsigned k[4];
             int b[4];
 #pragma unroll
@@ -399,8 +483,7 @@ static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned cha
                 b[u] = v ? bins[i0 + 32 * u] : 0;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i0 + 32 * u < np && k[u] >= kthr) atomicAdd(&hist[b[u]], 1);
+            for (int u = 0; u < 4; ++u) hist_add(hist, i0 + 32 * u < np && k[u] >= kthr, static_cast<unsigned>(b[u]), lane);
         }
         __syncwarp();
         {
@@ -435,10 +518,11 @@ static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned cha
         }
     }
 
+    PHASE_MARK(7);
     // ===================================== phase 3a: MFCC ======================================
     // frame mean of max(logmel, gmax - 80) in float64 (even and odd frames summed separately, then added: the order of the
     // fused kernel), then the DCT once per clip.  Lane owns bands 4*lane .. 4*lane+3.
-    {
+    if (!(SFX_TAIL_SKIP & 2)) {
         const float clampv = __fsub_rn(gmx, 80.0f);
         double ae[4] = {0.0, 0.0, 0.0, 0.0}, ao[4] = {0.0, 0.0, 0.0, 0.0};
         const float4* rows = reinterpret_cast<const float4*>(sl.gL) + lane;
@@ -446,7 +530,7 @@ static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned cha
         for (; t + 8 <= T; t += 8) {
             float4 v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = rows[static_cast<size_t>(t + u) * (kMels / 4)];
+            for (int u = 0; u < 8; ++u) v[u] = tail_ld(rows + static_cast<size_t>(t + u) * (kMels / 4));
 #pragma unroll
             for (int u = 0; u < 8; u += 2) {
                 ae[0] += static_cast<double>(fmaxf(v[u].x, clampv));
@@ -483,30 +567,25 @@ static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned cha
         __syncwarp();
     }
 
+    PHASE_MARK(8);
     // ===================================== phase 3b: chroma ====================================
     // raw[c][f] = sum_k W[c][k] |X|^2[k][f]: m16n8k16 FP16 MMAs, A = bank rows (hi and 2^11*lo, separate accumulators) read
     // from L2, B = the frames' scaled FP16 |X|^2 rows.  Lane (g = lane/4, t4 = lane%4) feeds bank rows g, g+8 and frame g of
     // each of the group's 4 tiles with its 8 contiguous bins of every 32-bin step (the same K permutation on both
     // operands leaves the products unchanged).  D fragment: [0..1] = (chroma g, frames 2*t4, 2*t4+1 of the tile),
     // [2..3] = (chroma g+8).
-    {
+    if (!(SFX_TAIL_SKIP & 4)) {
         const int g = lane >> 2, t4 = lane & 3;
-        const int r1 = (g < 4) ? g + 8 : g;                         // bank rows 12..15 do not exist
-        const __half* bank = reinterpret_cast<const __half*>(tb.chroma16) + static_cast<size_t>(tuning_idx) * 2 * kChroma * kP16Stride;
-        const uint4* whi0 = reinterpret_cast<const uint4*>(bank + g * kP16Stride + 8 * t4);
-        const uint4* whi1 = reinterpret_cast<const uint4*>(bank + r1 * kP16Stride + 8 * t4);
-        const uint4* wlo0 = reinterpret_cast<const uint4*>(bank + (kChroma + g) * kP16Stride + 8 * t4);
-        const uint4* wlo1 = reinterpret_cast<const uint4*>(bank + (kChroma + r1) * kP16Stride + 8 * t4);
         const float wny0 = __ldg(tb.chroma_ny + tuning_idx * kChroma + g);
-        const float wny1 = __ldg(tb.chroma_ny + tuning_idx * kChroma + r1);
+        const float wny1 = g < 4 ? __ldg(tb.chroma_ny + tuning_idx * kChroma + g + 8) : 0.0f;
         double cs0 = 0.0, cs1 = 0.0;                                // sums over this lane's frames of chroma g / g+8
-        const ChromaLane cl{whi0, whi1, wlo0, wlo1, wny0, wny1, g, t4};
+        const ChromaLane cl{tb.chroma_frag + static_cast<size_t>(tuning_idx) * (32 * 128) + lane, wny0, wny1, g, t4};
         for (int f0 = 0; f0 < T; f0 += 32) {
-            const int nt = min(4, (T - f0 + 7) >> 3);               // 8-frame tiles of this group
-            if (nt == 4)      chroma_group<4>(cl, sl, f0, T, cs0, cs1);
-            else if (nt == 3) chroma_group<3>(cl, sl, f0, T, cs0, cs1);
-            else if (nt == 2) chroma_group<2>(cl, sl, f0, T, cs0, cs1);
-            else              chroma_group<1>(cl, sl, f0, T, cs0, cs1);
+            if (lane == 0 && f0 + 32 < T)                           // next group's rows on their way to L2
+                bulk_prefetch_l2(sl.gP16 + static_cast<size_t>(f0 + 32) * kP16Stride, static_cast<unsigned>(min(32, T - f0 - 32)) * kP16Stride * 2u);
+            // always four 8-frame tiles (one instantiation: code size): tiles past the clip repeat its last frame, are
+            // multiplied for nothing (the tensor pipe is otherwise idle) and ignored
+            chroma_group<4>(cl, sl, f0, T, cs0, cs1);
         }
         cs0 += __shfl_xor_sync(0xffffffffu, cs0, 1);
         cs1 += __shfl_xor_sync(0xffffffffu, cs1, 1);
@@ -519,12 +598,13 @@ static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned cha
         }
     }
 
+    PHASE_MARK(9);
     // ===================================== epilogue: pooled descriptors ========================
     {
         // pooled rms from the hop energies (frame t spans hops t-2 .. t+1; hops outside [0, T) are zero padding)
         double a = 0.0;
         for (int t = lane; t < T; t += 32) {
-            const float* gE = sl.gFv + static_cast<size_t>(t) * kFvStride;          // hop energies, kFvStride apart
+            const float* gE = sl.gFv + static_cast<size_t>(t) * kFvStride + 2;      // hop energies, kFvStride apart
             float e = (t >= 2) ? gE[-2 * kFvStride] : 0.0f;
             e += (t >= 1) ? gE[-kFvStride] : 0.0f;
             e += gE[0];
@@ -547,72 +627,72 @@ static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned cha
         }
     }
     __syncwarp();
+    PHASE_MARK(10);
 }
 
 // ------------------------------------------------------------------------------------------------ scheduler
-__device__ __forceinline__ void sched_lock(Sched* sc) {
-    const long long t0 = clock64();
-    while (atomicCAS(&sc->lock, 0, 1) != 0) {
-        __nanosleep(32);
-        if (clock64() - t0 > 16000000000ll) __trap();           // the critical sections are a few hundred cycles long
-    }
-    __threadfence_block();
-}
-__device__ __forceinline__ void sched_unlock(Sched* sc) {
-    __threadfence_block();
-    atomicExch(&sc->lock, 0);
-}
-
-// Next item for warp `warp` (called by lane 0).  Returns the kind; slot / t / clip through the references.
-__device__ __forceinline__ int next_work(const Params& p, Sched* sc, int* counter, const int warp, const int seg_cap,
-                                         int& slot, int& t, int& clip) {
+// Next item for the calling warp (lane 0 only).  Returns the kind; slot / t / clip through the references.
+//   1. a clip whose frames are all done: its tail comes first (it frees a slot); claimed by clearing its ready bit
+//   2. a frame: one 64-bit atomicAdd on the ticket word
+//   3. the ticket is exhausted: one warp (spin lock `opener`, taken once per clip) pulls the next clip of the batch into
+//      a free slot and publishes its ticket; it keeps frame 0 for itself
+//   4. nothing to hand out: exit when the batch is exhausted and every slot is free, else poll again
+__device__ __forceinline__ int next_work(const Params& p, Sched* sc, int* counter, int& slot, int& t, int& clip) {
     volatile Sched* v = sc;
-    int kind = kWorkWait;
-    sched_lock(sc);
-    // 1. a clip whose frames are all done: its tail comes first (it frees a slot)
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s)
-        if (kind == kWorkWait && v->state[s] == kReady) { v->state[s] = kTail; slot = s; kind = kWorkTail; }
-    // 2. a frame of a clip that is being transformed (this warp's record segment must have room for a full frame)
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s)
-        if (kind == kWorkWait && v->state[s] == kFrames && v->next[s] < v->T[s] && v->cnt[s][warp] + p.max_pk <= seg_cap) {
-            slot = s; t = v->next[s]; v->next[s] = t + 1; kind = kWorkFrame;
+    const int ready = v->ready_mask;
+    if (ready) {
+        const int s = __ffs(ready) - 1;
+        if (atomicAnd(&sc->ready_mask, ~(1 << s)) & (1 << s)) {
+            __threadfence_block();                       // acquire: the frames' rows and records
+            slot = s;
+            return kWorkTail;
         }
-    // 3. the next clip of the batch into a free slot
-    if (kind == kWorkWait && !v->qdone) {
-        int fs = -1;
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s)
-            if (fs < 0 && v->state[s] == kFree) fs = s;
-        if (fs >= 0) {
-            const int q = atomicAdd(counter, 1);
-            if (q >= p.B) {
-                v->qdone = 1;
-            } else {
-                clip = p.order ? p.order[q] : q;
-                const long long n = clip_samples(p, clip);
-                if (n <= 0) {
-                    kind = kWorkBad;
-                } else {
-                    v->clip[fs] = clip; v->n[fs] = n; v->T[fs] = 1 + static_cast<int>(n / kHop);
-                    v->next[fs] = 1; v->done[fs] = 0;
-#pragma unroll
-                    for (int w = 0; w < kSW; ++w) v->cnt[fs][w] = 0;
-                    v->state[fs] = kFrames;
-                    slot = fs; t = 0; kind = kWorkFrame;
-                }
+        return kWorkWait;                                // somebody else took it: look again
+    }
+    {
+        unsigned h = v->hot;                              // look first: polls of an exhausted ticket must not advance it
+        if (static_cast<int>(h & 0xffffffu) < v->ring_T[(h >> 24) & 7u]) {
+            h = atomicAdd(&sc->hot, 1u);
+            const int g = (h >> 24) & 7u, tt = static_cast<int>(h & 0xffffffu);
+            if (tt < v->ring_T[g]) {
+                slot = v->ring_slot[g];
+                t = tt;
+                return kWorkFrame;
             }
         }
     }
-    // 4. nothing to hand out: done when the batch is exhausted and every slot is free
-    if (kind == kWorkWait && v->qdone) {
-        bool all_free = true;
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) all_free &= v->state[s] == kFree;
-        if (all_free) kind = kWorkExit;
+    if (v->qdone) return v->active == 0 ? kWorkExit : kWorkWait;
+    if (atomicCAS(&sc->opener, 0, 1) != 0) return kWorkWait;
+    __threadfence_block();
+    int kind = kWorkWait;
+    const unsigned h2 = v->hot;                          // a clip may have been published while we queued for the lock
+    const bool exhausted = static_cast<int>(h2 & 0xffffffu) >= v->ring_T[(h2 >> 24) & 7u];
+    const int fm = v->free_mask;
+    if (exhausted && fm && !v->qdone) {
+        const int q = atomicAdd(counter, 1);
+        if (q >= p.B) {
+            v->qdone = 1;
+        } else {
+            clip = p.order ? p.order[q] : q;
+            const long long n = clip_samples(p, clip);
+            if (n <= 0) {
+                kind = kWorkBad;
+            } else {
+                const int s = __ffs(fm) - 1;
+                const int T = 1 + static_cast<int>(n / kHop);
+                atomicAnd(&sc->free_mask, ~(1 << s));
+                atomicAdd(&sc->active, 1);
+                v->clip[s] = clip; v->n[s] = n; v->T[s] = T; v->done[s] = 0; v->npk[s] = 0;
+                const unsigned gen = ((h2 >> 24) + 1u) & 0xffu;
+                v->ring_slot[gen & 7u] = s; v->ring_T[gen & 7u] = T;
+                __threadfence_block();
+                atomicExch(&sc->hot, (gen << 24) | 1u);          // frame 0 is ours
+                slot = s; t = 0; kind = kWorkFrame;
+            }
+        }
     }
-    sched_unlock(sc);
+    __threadfence_block();
+    atomicExch(&sc->opener, 0);
     return kind;
 }
 
@@ -644,6 +724,8 @@ __global__ void __launch_bounds__(kSThreads, 1) sfx_stream_kernel(const __grid_c
     for (int i = tid; i <= kTunings; i += kSThreads) s_edges[i] = tb.edges[i];
     for (int i = tid; i < static_cast<int>(sizeof(Sched) / 4); i += kSThreads) reinterpret_cast<int*>(sc)[i] = 0;
     __syncthreads();
+    if (tid == 0) sc->free_mask = (1 << kSlots) - 1;        // hot = generation 0, ring_T[0] = 0: no frames yet
+    __syncthreads();
 
     FrameSmem fs;
     fs.s_hann = s_hann; fs.s_tw1 = s_tw1; fs.s_tw2 = s_tw2; fs.s_melab = s_melab;
@@ -661,21 +743,33 @@ __global__ void __launch_bounds__(kSThreads, 1) sfx_stream_kernel(const __grid_c
 
     int* counter = reinterpret_cast<int*>(p.ws);
     unsigned char* slots_base = p.ws + kWsHeader + static_cast<size_t>(blockIdx.x) * kSlots * p.cta_scratch_bytes;
-    const int seg_cap = stream_seg_frames(p.Tmax) * p.max_pk;
     volatile Sched* v = sc;
 
     long long wait_since = 0;                            // clock of the first of a run of empty-handed polls
     for (;;) {
         int kind = 0, slot = 0, t = 0, clip = 0;
-        if (lane == 0) kind = next_work(p, sc, counter, warp, seg_cap, slot, t, clip);
+#ifdef SFX_STREAM_DIAG
+        const long long tk0 = clock64();
+#endif
+        if (lane == 0) kind = next_work(p, sc, counter, slot, t, clip);
         kind = __shfl_sync(0xffffffffu, kind, 0);
+#ifdef SFX_STREAM_DIAG
+        const long long tk1 = clock64();
+        PROF_ADD(3, tk1 - tk0);
+#endif
         if (kind == kWorkExit) break;
         if (kind == kWorkWait) {
             // nothing to hand out right now (every slot is waiting for straggler frames or in its tail)
             const long long now = clock64();
             if (wait_since == 0) wait_since = now;
+#ifdef SFX_STREAM_DIAG
+            if (__shfl_sync(0xffffffffu, now - wait_since > 1000000000ll ? 1 : 0, 0)) { if (lane == 0) diag_dump(sc, warp, 1); break; }
+#endif
             if (now - wait_since > 16000000000ll) __trap();     // ~8 s: a scheduler bug must fail loudly, not hang the GPU
             __nanosleep(256);
+#ifdef SFX_STREAM_DIAG
+            PROF_ADD(2, clock64() - tk1);
+#endif
             continue;
         }
         wait_since = 0;
@@ -696,30 +790,38 @@ __global__ void __launch_bounds__(kSThreads, 1) sfx_stream_kernel(const __grid_c
             const float* x = p.wave + static_cast<long long>(clip) * p.row_stride;
             FrameOut fo;
             fo.gP16 = sl.gP16; fo.gL = sl.gL; fo.gRec = sl.gRec; fo.gE = nullptr; fo.gNy = nullptr; fo.gInvS = nullptr;
-            fo.npk = nullptr; fo.gSeg = sl.gRec + static_cast<size_t>(warp) * seg_cap; fo.s_wacc = nullptr; fo.s_f = nullptr;
+            fo.npk = nullptr; fo.gSeg = nullptr; fo.s_wacc = nullptr; fo.s_f = nullptr; fo.cursor = &sc->npk[slot];
+            fo.s_lm = nullptr; fo.s_lmin = nullptr;
             fo.gCent = nullptr; fo.gRoll = nullptr; fo.gLmax = nullptr; fo.gZc = nullptr; fo.gFv = sl.gFv;
-            int unused_zc = 0, wcount = v->cnt[slot][warp];
+            int unused_zc = 0, wcount = 0;
             process_frame<kDebug, kModeStream>(p, tb, fs, fo, x, n, T, t, clip, lane, warp, unused_zc, wcount);
             if (lane == 0) {
-                v->cnt[slot][warp] = wcount;
                 __threadfence_block();                   // the frame's rows and records before the completion count
-                if (atomicAdd(&sc->done[slot], 1) + 1 == T) {
-                    __threadfence_block();
-                    v->state[slot] = kReady;
-                }
+                if (atomicAdd(&sc->done[slot], 1) + 1 == T) atomicOr(&sc->ready_mask, 1 << slot);
             }
             __syncwarp();
+#ifdef SFX_STREAM_DIAG
+            PROF_ADD(0, clock64() - tk1);
+            PROF_ADD(4, 1);
+#endif
         } else {                                         // kWorkTail
             __threadfence_block();
             clip = v->clip[slot];
             const int T = v->T[slot];
             float* out = p.out + static_cast<long long>(clip) * p.out_stride;
-            clip_tail_warp<kDebug>(p, slot_base, &v->cnt[slot][0], seg_cap, fs.Pb, s_edges, clip, T, out, lane);
+#ifndef SFX_STREAM_NOTAIL                                // (experiment: frames only, rows are garbage)
+            clip_tail_warp<kDebug>(p, slot_base, fs.Pb, s_edges, clip, T, v->npk[slot], out, lane);
+#endif
             if (lane == 0) {
                 __threadfence_block();
-                v->state[slot] = kFree;
+                atomicOr(&sc->free_mask, 1 << slot);
+                atomicSub(&sc->active, 1);
             }
             __syncwarp();
+#ifdef SFX_STREAM_DIAG
+            PROF_ADD(1, clock64() - tk1);
+            PROF_ADD(5, 1);
+#endif
         }
     }
 }

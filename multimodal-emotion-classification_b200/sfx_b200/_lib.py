@@ -24,7 +24,8 @@ class TablesHost(C.Structure):
                 ("mel_flush32", C.c_int32),
                 ("hann", C.c_void_p), ("tw1", C.c_void_p), ("tw2", C.c_void_p), ("mel_ab", C.c_void_p),
                 ("mel_mask", C.c_void_p), ("mel_src", C.c_void_p),
-                ("chroma16", C.c_void_p), ("chroma_ny", C.c_void_p), ("dct", C.c_void_p), ("edges", C.c_void_p)]
+                ("chroma16", C.c_void_p), ("chroma_ny", C.c_void_p), ("dct", C.c_void_p), ("edges", C.c_void_p),
+                ("chroma_frag", C.c_void_p)]
 
 
 class DebugOut(C.Structure):
@@ -62,9 +63,10 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(_build.LIB_PATH):
+    path = os.environ.get("SFX_B200_LIB") or _build.LIB_PATH      # SFX_B200_LIB: an A/B build (tools/ab_modes.py, profiling)
+    if path == _build.LIB_PATH and not os.path.exists(path):
         _build.build()
-    lib = C.CDLL(_build.LIB_PATH)
+    lib = C.CDLL(path)
     lib.sfx_abi_version.restype = C.c_int
     lib.sfx_last_error.restype = C.c_char_p
     lib.sfx_device_count.restype = C.c_int
@@ -110,7 +112,7 @@ def load():
     lib.sfx_dnn_forward.restype = C.c_int
     lib.sfx_dnn_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                     C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
-    if lib.sfx_abi_version() != 1:
+    if lib.sfx_abi_version() != 2:
         raise RuntimeError("libsfx_b200.so ABI version mismatch; rebuild with sfx_b200.build.build(force=True)")
     _LIB = lib
     return lib
@@ -141,7 +143,8 @@ def check(rc: int):
 def make_tables_struct(tb: dict):
     """TablesHost pointing into the numpy arrays of tables.build_tables (keeps them alive via .keep)."""
     keep = {k: np.ascontiguousarray(tb[k]) for k in
-            ("hann", "tw1", "tw2", "mel_ab", "mel_mask", "mel_src", "chroma16", "chroma_ny", "dct", "edges")}
+            ("hann", "tw1", "tw2", "mel_ab", "mel_mask", "mel_src", "chroma16", "chroma_ny", "dct", "edges", "chroma_frag")}
+    assert keep["chroma_frag"].dtype == np.uint32
     assert keep["hann"].dtype == np.float32 and keep["chroma16"].dtype == np.float16 and keep["chroma_ny"].dtype == np.float32
     assert keep["dct"].dtype == np.float64 and keep["edges"].dtype == np.float64
     assert keep["mel_ab"].dtype == np.float32 and keep["mel_mask"].dtype == np.uint32 and keep["mel_src"].dtype == np.int32

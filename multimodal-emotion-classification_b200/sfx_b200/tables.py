@@ -16,6 +16,7 @@ Layouts are chosen for the kernels (see DESIGN.md "HBM / SMEM layout"), not for 
   melw   float32[mel_rows][32] transposed/padded sparse mel weights (dense-bank audit layout, host tests only)
   chroma16 float16[100][2][12][1056] one bank per tuning edge as hi + 2^-11 * lo (operands of the tensor-core chroma
                               projection), bin axis zero-padded to 1056; chroma_ny float32[100][12] Nyquist-bin weights;
+  chroma_frag uint32[100][32][2][2][32][4] the same bank as ready-made mma.m16n8k16 A fragments (stream pipeline);
                               chroma_f32 is the dense float32 bank (host tests only)
   dct    float64[128][128]    rows k of the ortho DCT-II
   edges  float64[101]         np.linspace(-0.5, 0.5, 101)
@@ -95,6 +96,22 @@ def split_fp16(x: np.ndarray):
     hi = x.astype(np.float16)
     lo = ((x.astype(np.float64) - hi.astype(np.float64)) * 2048.0).astype(np.float16)
     return hi, lo
+
+
+def chroma_fragments(c_hi: np.ndarray, c_lo: np.ndarray) -> np.ndarray:
+    """A-operand fragments of mma.m16n8k16 for the chroma bank, one 16-byte quad per (tuning, 32-bin step, half step,
+    hi/lo, lane): uint32 [T][32][2][2][32][4].  Lane (g = lane / 4, t4 = lane % 4) of half step m of step s owns bins
+    b0 = 32 s + 8 t4 + 4 m .. b0 + 3 (the same K permutation the kernels apply to the |X|^2 operand) and rows g, g + 8:
+    quad = (W[g][b0:b0+2], W[g+8][b0:b0+2], W[g][b0+2:b0+4], W[g+8][b0+2:b0+4]) as packed half2; rows 12..15 are zero.
+    One coalesced 128-bit load per MMA instead of two strided loads and four register moves."""
+    nt = c_hi.shape[0]
+    a = np.zeros((nt, 2, 16, 1024), dtype=np.uint16)
+    a[:, 0, :N_CHROMA] = np.ascontiguousarray(c_hi[:, :, :1024]).view(np.uint16)
+    a[:, 1, :N_CHROMA] = np.ascontiguousarray(c_lo[:, :, :1024]).view(np.uint16)
+    a = a.reshape(nt, 2, 2, 8, 32, 4, 2, 2, 2).astype(np.uint32)          # [tun, hl, rh, g, s, t4, m, jp, e]
+    u = a[..., 0] | (a[..., 1] << np.uint32(16))                             # [tun, hl, rh, g, s, t4, m, jp]
+    u = u.transpose(0, 4, 6, 1, 3, 5, 7, 2)                                  # [tun, s, m, hl, g, t4, jp, rh]
+    return np.ascontiguousarray(u.reshape(nt, 32, 2, 2, 32, 4))
 
 
 def tuning_edges() -> np.ndarray:
@@ -226,6 +243,7 @@ def build_tables(sr: int = 22050) -> dict:
     c_hi, c_lo = split_fp16(chroma)
     chroma16 = np.ascontiguousarray(np.stack([c_hi, c_lo], axis=1))          # [100][2][12][1056] float16
     chroma_ny = np.ascontiguousarray(chroma[:, :, N_BINS - 1])               # [100][12] float32 (Nyquist bin)
+    chroma_frag = chroma_fragments(c_hi, c_lo)                               # [100][32][2][2][32][4] uint32
     return dict(**chunk, sr=sr, hann=hann, tw1=np.ascontiguousarray(tw1), tw2=np.ascontiguousarray(tw2),
                 mel_dense=mb, melw=melw, mel_lo=mel_lo, mel_off=mel_off, mel_len=mel_len,
-                chroma16=chroma16, chroma_ny=chroma_ny, chroma_f32=chroma, dct=dct_matrix(), edges=edges, pip_kmin=kmin, pip_kmax=kmax)
+                chroma16=chroma16, chroma_ny=chroma_ny, chroma_frag=chroma_frag, chroma_f32=chroma, dct=dct_matrix(), edges=edges, pip_kmin=kmin, pip_kmax=kmax)

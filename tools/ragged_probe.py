@@ -38,10 +38,10 @@ def run(order=None, reps=5):
     return (time.perf_counter() - t0) / reps
 
 
-for mode in (1, 2):
+for mode in (1, 3, 2):
     ex.lib.sfx_set_pipeline(mode)
     t = run()
     ts = run(torch.argsort(ld, descending=True))
-    print(f"pipeline {'fused' if mode == 1 else 'split'}: B={B} frames={frames} as given {t*1e3:.2f} ms "
+    print(f"pipeline {('', 'fused', 'split', 'stream')[mode]}: B={B} frames={frames} as given {t*1e3:.2f} ms "
           f"({frames/t/130/1e6:.3f} M 3s-clip-equivalents/s), longest first {ts*1e3:.2f} ms ({frames/ts/130/1e6:.3f} M)")
 ex.lib.sfx_set_pipeline(0)
