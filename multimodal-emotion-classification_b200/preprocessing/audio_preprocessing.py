@@ -24,7 +24,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if _PKG_ROOT not in sys.path:
     sys.path.insert(0, _PKG_ROOT)
 
-from config import Config  # noqa: E402  (reference :9)
+from sfx_b200._config import Config  # noqa: E402  (reference :9: `from config import Config`; the reference's wins when importable)
 
 
 class ParameterError(ValueError):

@@ -21,8 +21,12 @@ class SpeechDNN:
         if not torch.cuda.is_available():
             from .extractor import NoCudaDeviceError
             raise NoCudaDeviceError("sfx_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.index = self.device.index or 0
+        dev = torch.device("cuda") if device is None else torch.device(device)
+        if dev.type != "cuda":
+            from .extractor import NoCudaDeviceError
+            raise NoCudaDeviceError(f"sfx_b200 runs on CUDA devices only, got {dev}")
+        self.index = dev.index if dev.index is not None else torch.cuda.current_device()   # "cuda" = the current device
+        self.device = torch.device("cuda", self.index)
         widths = [int(w) for w in weights["widths"]]
         n = len(widths) - 1
         self.widths = widths

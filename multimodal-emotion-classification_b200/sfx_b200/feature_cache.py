@@ -23,7 +23,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if _PKG_ROOT not in sys.path:
     sys.path.insert(0, _PKG_ROOT)
 
-from config import Config  # noqa: E402
+from ._config import Config  # noqa: E402
 from preprocessing import audio_preprocessing as _ap  # noqa: E402
 
 
@@ -33,12 +33,6 @@ def one_hot(labels: List[int], num_classes: int) -> np.ndarray:
     for i, idx in enumerate(labels):
         y[i, idx] = 1.0
     return y
-
-
-def augment_features(X: np.ndarray, noise_factor: float = 0.05) -> np.ndarray:
-    """reference :163-166 -- Gaussian noise in (scaled) feature space."""
-    noise = np.random.normal(0, noise_factor, X.shape)
-    return X + noise
 
 
 def _label_of(fp: str, label_from: str, name_map):

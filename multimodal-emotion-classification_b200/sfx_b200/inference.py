@@ -4,23 +4,25 @@ Batched, device-resident speech inference -- the B200 counterpart of the referen
 The reference builds features per file with librosa, scales them with a joblib'd StandardScaler and runs a Keras .h5
 (speech_inference.py:60-105).  Here a whole batch of clips goes waveform -> 56-d features -> scaler -> DNN on the GPU
 (sfx_extract + sfx_dnn_forward) and only the 7 probabilities (and optionally the 64-d fusion tap) come back.
-The result dictionaries have the reference's keys.  Loading the reference's .h5/.pkl artefacts needs TensorFlow/h5py/
-joblib, which are not part of this build: weights are passed as a dict of numpy arrays (see sfx_b200/dnn.py).
+The result dictionaries have the reference's keys.  Weights are a dict of numpy arrays (see sfx_b200/dnn.py) or an .npz written by
+tools/export_weights.py, which runs on the reference side (where TensorFlow / joblib exist) and converts the reference's
+models/speech_model.h5 + speech_scaler.pkl (speech_inference.py:17-34).
 """
 from typing import Dict, List
 
 import numpy as np
 
-from config import Config
+from ._config import Config
 
 
 class BatchedSpeechInference:
     def __init__(self, weights: dict, device=None, sr: int = Config.SAMPLE_RATE):
         import torch
-        from sfx_b200 import get_extractor
-        from sfx_b200.dnn import SpeechDNN
+        from . import get_extractor
+        from .dnn import SpeechDNN
         self.emotions = Config.EMOTIONS
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        dev = torch.device("cuda") if device is None else torch.device(device)
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self.extractor = get_extractor(self.device, sr)
         self.dnn = SpeechDNN(weights, self.device)
 

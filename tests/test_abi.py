@@ -38,7 +38,7 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_abi_version_and_argument_validation():
     lib = _lib.load()
-    assert lib.sfx_abi_version() == 1
+    assert lib.sfx_abi_version() == 2
     assert lib.sfx_launches_per_extract() == 1
     # argument validation happens before any CUDA work
     rc = lib.sfx_extract(99, 22050, None, 0, None, 0, 0, 1, 40, None, 56, None, 0, None)

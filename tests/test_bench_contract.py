@@ -19,7 +19,7 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "clips/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
     assert d["config"]["workload"] == bench.WORKLOAD and d["config"]["n_samples"] == 66150
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] == ("reference" if bench.librosa_available() else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["gpu_launches"] == 0

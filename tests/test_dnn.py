@@ -64,7 +64,7 @@ def test_dnn_forward_matches_oracle():
 @pytest.mark.gpu
 def test_config3_tess_shaped_features_feed_dnn_on_device():
     """BASELINE configs[2]: 2 800 synthetic ~2 s clips zero-padded to 3 s; features stay on the GPU and feed the DNN."""
-    from inference.speech_inference import BatchedSpeechInference
+    from sfx_b200.inference import BatchedSpeechInference
     rng = np.random.default_rng(33)
     B, n = 2800, 66150
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -95,7 +95,7 @@ def test_config3_tess_shaped_features_feed_dnn_on_device():
 @pytest.mark.gpu
 def test_heuristic_predict_batch_thresholds():
     """speech_inference.py:36-58: rms > 0.06 & centroid > 2000 -> angry; rms < 0.02 & centroid < 1500 -> sad; else neutral."""
-    from inference.speech_inference import BatchedSpeechInference
+    from sfx_b200.inference import BatchedSpeechInference
     n = 66150
     t = np.arange(n) / 22050.0
     loud_bright = (0.3 * np.random.default_rng(0).standard_normal(n)).clip(-1, 1).astype(np.float32)      # rms .3, centroid ~5.5k

@@ -107,6 +107,170 @@ def test_config3_tess_shaped_zero_tail(ex):
     assert_parity(got[idx], lp.features_batch(w[idx]))
 
 
+def test_config2_full_batch_oracle_parity(ex):
+    """BASELINE configs[1] at its named size: all 1 440 ~3.7 s clips against the oracle (16-core process pool), both as
+    preprocess_audio sees them (truncated to 3 s, T = 130) and raw (T = 160)."""
+    import oracle_pool
+    n_raw = 81586
+    w, (ref_trunc, ref_raw) = oracle_pool.indexed_batch(1440, n_raw, seed=211, n_used=[N3S, n_raw])
+    d = dev(w)
+    assert_parity(ex.extract(d, n_samples=N3S).cpu().numpy(), ref_trunc)
+    assert_parity(ex.extract(d).cpu().numpy(), ref_raw)
+
+
+def test_config3_full_batch_oracle_parity(ex):
+    """BASELINE configs[2] at its named size: all 2 800 ~2 s clips zero-padded to 3 s (top_db clamp active on every clip)."""
+    import oracle_pool
+    B = 2800
+    rng = np.random.default_rng(212)
+    w, _ = oracle_pool.indexed_batch(B, N3S, seed=212, kinds=synth.KINDS[:2], n_used=[])        # the clips only
+    cut = (44100 * rng.uniform(0.85, 1.15, B)).astype(np.int64)
+    w[np.arange(N3S)[None, :] >= cut[:, None]] = 0.0
+    got = ex.extract(dev(w)).cpu().numpy()
+    assert_parity(got, oracle_pool.oracle_rows(w))
+
+
+def test_config5_at_size_4096_clips_half_to_sixty_seconds(ex):
+    """BASELINE configs[4] at its named size: 4 096 clips, lengths log-uniform in [0.5 s, 60 s] (T = 22 .. 2 584), padded rows
+    + lengths, poisoned padding.  The batch (21.7 GB) is synthesised on the device; oracle parity on 72 sampled clips that
+    include the longest and the shortest; the host entry point on a 384-clip slice must give the device path's rows."""
+    import oracle_pool
+    B, n_min, n_max = 4096, 11025, 1323000
+    rng = np.random.default_rng(213)
+    lens = np.exp(rng.uniform(np.log(n_min), np.log(n_max), size=B)).astype(np.int64)
+    lens[0], lens[-1], lens[B // 2] = n_min, n_max, n_max - 511
+    lens = lens.astype(np.int32)
+    g = torch.Generator(device="cuda").manual_seed(213)
+    w = torch.empty((B, n_max), dtype=torch.float32, device="cuda")
+    t = torch.arange(n_max, device="cuda", dtype=torch.float32) / 22050.0
+    for c0 in range(0, B, 256):                                       # noise rows; every 2nd row a harmonic stack on top
+        blk = w[c0:c0 + 256]
+        blk.normal_(0.0, 0.1, generator=g)
+        f0 = 90.0 + 210.0 * torch.rand((128, 1), device="cuda", generator=g)
+        y = torch.zeros((128, n_max), device="cuda")
+        for h in range(1, 9):
+            y += torch.sin(6.2831853 * h * f0 * t) / h
+        blk[1::2] = 0.3 * y / y.abs().amax(dim=1, keepdim=True) + 0.002 * blk[1::2]
+        del y
+    ld = torch.from_numpy(lens).cuda()
+    w.masked_fill_(torch.arange(n_max, device="cuda")[None, :] >= ld[:, None], 7.0)            # poison: must never be read
+    got = ex.extract(w, ld)
+    assert ex.lib.sfx_launches_per_extract() == 2                     # longest-first order kernel + extractor
+    assert bool(torch.isfinite(got).all())
+    idx = np.unique(np.concatenate([[0, B - 1, B // 2, int(np.argmax(lens)), int(np.argmin(lens))],
+                                    rng.choice(B, size=67, replace=False)]))
+    wl = w[torch.from_numpy(idx).cuda()].cpu().numpy()
+    ref = oracle_pool.oracle_rows(wl, lens[idx])
+    assert_parity(got[torch.from_numpy(idx).cuda()].cpu().numpy(), ref)
+    sl = slice(B // 2 - 192, B // 2 + 192)                            # includes a 60 s clip
+    host = ex.extract_host(w[sl].cpu().numpy(), lens[sl])
+    assert np.array_equal(host, got[sl].cpu().numpy())
+
+
+def test_two_threads_two_sample_rates(ex):
+    """The C ABI from two host threads at once: one extracts at 22 050 Hz in a loop while the other uploads the table sets
+    of new sample rates (which grows the per-device table list) and extracts with them; rows must equal the serial ones."""
+    import threading
+    from sfx_b200.extractor import SpeechFeatureExtractor
+    w22 = dev(synth.make_batch(64, N3S, seed=71))
+    ref22 = ex.extract(w22).clone()
+    rates = (11025, 32000, 12000)
+    waves = {sr: dev(synth.make_batch(8, 2 * sr, seed=72)) for sr in rates}
+    errors, results = [], {}
+
+    def worker_a():
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(40):
+                    if not torch.equal(ex.extract(w22), ref22):
+                        errors.append("22 050 Hz rows changed while another thread initialised tables")
+            s.synchronize()
+        except Exception as e:      # noqa: BLE001
+            errors.append(repr(e))
+
+    def worker_b():
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for sr in rates:
+                    e2 = SpeechFeatureExtractor(torch.device("cuda", 0), sr=sr)
+                    results[sr] = e2.extract(waves[sr]).clone()
+            s.synchronize()
+        except Exception as e:      # noqa: BLE001
+            errors.append(repr(e))
+
+    ta, tb_ = threading.Thread(target=worker_a), threading.Thread(target=worker_b)
+    ta.start(); tb_.start(); ta.join(); tb_.join()
+    assert not errors, errors
+    from sfx_b200 import get_extractor
+    for sr in rates:
+        serial = get_extractor(torch.device("cuda", 0), sr=sr).extract(waves[sr])
+        assert torch.equal(results[sr], serial)
+        assert_parity(serial[:2].cpu().numpy(), np.stack([lp.features_from_audio(x, sr=sr) for x in waves[sr][:2].cpu().numpy()]))
+
+
+def test_host_path_reports_non_finite_clips(ex):
+    """include/sfx.h: a clip with a NaN / Inf sample gets a NaN row and the host entry point returns SFX_ERR_BAD_CLIP after
+    delivering every row; a bad length is rejected before any work."""
+    w = synth.make_batch(9, N3S, seed=73)
+    w[4, 30000] = np.nan
+    w[7, 100] = np.inf
+    out = np.zeros((9, 56), dtype=np.float32)
+    rc = ex.lib.sfx_extract_host(ex.index, 22050, w.ctypes.data, N3S, None, N3S, 9, 40, out.ctypes.data, 56, 0)
+    assert rc == -5 and b"clip 4" in ex.lib.sfx_last_error()
+    good = [0, 1, 2, 3, 5, 6, 8]
+    assert np.isnan(out[[4, 7]]).any(axis=1).all() and np.isfinite(out[good]).all()
+    assert np.array_equal(out[good], ex.extract(dev(w[good])).cpu().numpy())
+    rows = ex.extract_host(w)                                             # the Python wrapper returns the rows
+    assert np.array_equal(np.isnan(rows).any(axis=1), np.isnan(out).any(axis=1))
+    lens = np.array([N3S] * 8 + [0], dtype=np.int32)
+    out2 = np.zeros_like(out)
+    rc = ex.lib.sfx_extract_host(ex.index, 22050, w.ctypes.data, N3S, lens.ctypes.data, N3S, 9, 40, out2.ctypes.data, 56, 0)
+    assert rc == -5 and not out2.any()
+
+
+@pytest.mark.parametrize("mode", ["fused", "stream", "split"])
+def test_every_pipeline_against_the_oracle(ex, mode):
+    """All three schedules of the one arithmetic, forced, on a uniform and a ragged batch (incl. invalid lengths)."""
+    w = synth.make_batch(40, N3S, seed=74)
+    ref = lp.features_batch(w[:12])
+    wr, lens = synth.make_ragged(24, 600, 150000, seed=75)
+    lens[5] = 0
+    good = np.nonzero(lens > 0)[0]
+    refr = lp.features_batch(wr[good[:10]], lens[good[:10]])
+    try:
+        ex.set_pipeline(mode)
+        dbg = {}
+        got = ex.extract(dev(w), debug=dbg).cpu().numpy()
+        assert_parity(got[:12], ref)
+        assert (dbg["clip_info"].cpu().numpy()[:, 6] == 0).all()
+        assert np.array_equal(ex.extract(dev(w)).cpu().numpy(), got)        # non-debug instantiation, bit for bit
+        gr = ex.extract(dev(wr), dev(lens)).cpu().numpy()
+        assert np.isnan(gr[5]).all()
+        assert_parity(gr[good[:10]], refr)
+    finally:
+        ex.set_pipeline("auto")
+
+
+def test_stream_pipeline_agrees_with_fused_on_a_large_batch(ex):
+    """Mode 3 (one persistent 16-warp CTA per SM, warp-granular frame / tail scheduling) runs the arithmetic of the fused kernel:
+    MFCC, zcr, centroid, roll-off and rms bit for bit, chroma to 2e-6 (its MMA accumulates the 1 024 bins in a different order);
+    the rows do not depend on which warp ran which frame."""
+    w = dev(synth.make_batch(1500, N3S, seed=76))
+    try:
+        ex.set_pipeline("fused")
+        a = ex.extract(w)
+        ex.set_pipeline("stream")
+        b = ex.extract(w)
+        c = ex.extract(w)
+    finally:
+        ex.set_pipeline("auto")
+    assert torch.equal(b, c)
+    assert torch.equal(a[:, :40], b[:, :40]) and torch.equal(a[:, 52:], b[:, 52:])
+    assert float((a[:, 40:52] - b[:, 40:52]).abs().max()) < 2e-6
+
+
 def test_config5_variable_length_extremes(ex):
     """BASELINE configs[4] shape: 0.5 s .. 60 s, padded rows + lengths (T = 22 .. 2584)."""
     lens = np.array([11025, 11026, 511, 512, 513, 2047, 2048, 2049, 66150, 123457, 1323000], dtype=np.int32)
@@ -213,7 +377,7 @@ def test_pcm16_host_path_is_the_float_path_on_dequantised_samples(ex):
 
 def test_dropin_module_functions(ex):
     """The reference's tests/test_preprocessing.py:30-67 against the drop-in module, plus values vs the oracle."""
-    from config import Config
+    from sfx_b200._config import Config
     from preprocessing.audio_preprocessing import (extract_chroma, extract_mfcc, extract_spectral_features,
                                                    extract_features_batch)
     audio = np.random.default_rng(0).standard_normal(Config.SAMPLE_RATE * Config.AUDIO_DURATION)   # float64

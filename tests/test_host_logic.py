@@ -15,7 +15,7 @@ from sfx_b200 import shard
 
 def test_dropin_surface_matches_reference():
     import preprocessing.audio_preprocessing as ap
-    from config import Config
+    from sfx_b200._config import Config
     assert (Config.SAMPLE_RATE, Config.AUDIO_DURATION, Config.N_MFCC) == (22050, 3, 40)
     sig = {n: str(inspect.signature(getattr(ap, n))) for n in
            ("load_audio", "extract_mfcc", "extract_chroma", "extract_spectral_features", "preprocess_audio")}
@@ -144,3 +144,32 @@ def _worker(rank, world, port, n_total, ragged):
 def test_feature_cache_allgather_gloo_world2(n_total, ragged):
     port = 29500 + (os.getpid() + n_total) % 2000
     mp.spawn(_worker, args=(2, port, n_total, ragged), nprocs=2, join=True)
+
+
+REFERENCE = "/root/reference"
+PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "multimodal-emotion-classification_b200")
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference checkout exists in the build container only")
+def test_documented_dropin_pythonpath_shadows_preprocessing_only():
+    """PYTHONPATH=multimodal-emotion-classification_b200:<reference>.  Only `preprocessing` may come
+    from this package; `config`, `inference` and `model_training` must resolve to the reference's own modules (its
+    SpeechInference reads Config.SPEECH_MODEL_PATH etc. inside try/except and would silently fall back otherwise)."""
+    import subprocess
+    import sys
+    code = (
+        "import config, inference.speech_inference as si, preprocessing.audio_preprocessing as ap\n"
+        "import model_training, sfx_b200._config as c\n"
+        "print(config.__file__); print(si.__file__); print(ap.__file__); print(model_training.__path__[0] if hasattr(model_training, '__path__') else model_training.__file__)\n"
+        "assert hasattr(config.Config, 'SPEECH_MODEL_PATH') and hasattr(config.Config, 'SECRET_KEY')\n"
+        "assert c.Config is config.Config\n"
+        "assert hasattr(si, 'SpeechInference') and si.preprocess_audio is ap.preprocess_audio\n"
+        "assert ap.load_audio.__defaults__ == (config.Config.SAMPLE_RATE, config.Config.AUDIO_DURATION)\n"
+        "s = si.SpeechInference(); assert s.emotions == config.Config.EMOTIONS\n"
+    )
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([PKG, REFERENCE]))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd="/tmp")
+    assert res.returncode == 0, res.stderr[-2000:]
+    cfg, si, ap, mt = res.stdout.strip().splitlines()[-4:]
+    assert cfg.startswith(REFERENCE) and si.startswith(REFERENCE) and mt.startswith(REFERENCE)
+    assert ap.startswith(PKG)

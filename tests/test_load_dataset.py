@@ -64,7 +64,7 @@ def stub_features(waves):
 
 @pytest.mark.parametrize("label_from,name_map", [("parent", None), ("name", {"happy": "happy", "sad": "sad"})])
 def test_load_dataset_semantics_match_reference_loop(tmp_path, monkeypatch, capsys, label_from, name_map):
-    from model_training import train_speech_model as tsm
+    from sfx_b200 import feature_cache as tsm
     import preprocessing.audio_preprocessing as ap
     make_tree(str(tmp_path))
 
@@ -98,7 +98,7 @@ def test_load_dataset_semantics_match_reference_loop(tmp_path, monkeypatch, caps
 
 @pytest.mark.gpu
 def test_load_dataset_end_to_end_on_gpu(tmp_path):
-    from model_training import train_speech_model as tsm
+    from sfx_b200 import feature_cache as tsm
     import preprocessing.audio_preprocessing as ap
     make_tree(str(tmp_path), n_per=3, seed=4)
     X, y = tsm.load_dataset(str(tmp_path), "**/*.wav", "parent")
