@@ -272,10 +272,12 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
     // Fused kernel: pin the rows phase 3 reads back (FP16 |X|^2, then log-mel, of every CTA: one block of the workspace)
     // in the persisting part of L2 for the duration of the launch.  hitRatio = the fraction of the window's lines the
     // set-aside can hold, so that persisting lines never evict each other.
-    const bool l2_pin = !stream_pipe && c.l2_persist > 0 && g_l2_mode != 0;
+    // (long clips: the block outgrows the window and nothing of it would stay resident anyway -- no pinning then, the
+    // set-aside is simply unused for that launch)
+    const size_t pin_bytes = static_cast<size_t>(grid) * (sfx::cta_p16_bytes(Tmax) + (g_l2_mode == 2 ? sfx::cta_lm_bytes(Tmax) : 0));
+    const bool l2_pin = !stream_pipe && c.l2_persist > 0 && g_l2_mode != 0 && pin_bytes <= c.l2_window;
     if (l2_pin) {
-        size_t win = static_cast<size_t>(grid) * (sfx::cta_p16_bytes(Tmax) + (g_l2_mode == 2 ? sfx::cta_lm_bytes(Tmax) : 0));
-        win = std::min(win, c.l2_window);
+        const size_t win = pin_bytes;
         cudaStreamAttrValue av{};
         av.accessPolicyWindow.base_ptr = static_cast<unsigned char*>(ws) + sfx::kWsHeader;
         av.accessPolicyWindow.num_bytes = win;

@@ -197,9 +197,15 @@ static __device__ unsigned radix_select(const unsigned* keys, int np, int r, int
         const unsigned bmask = (1u << width) - 1u;
         for (int i = tid; i < 256; i += kThreads) s_hist[i] = 0;
         __syncthreads();
-        for (int i = tid; i < np; i += kThreads) {
-            const unsigned key = keys[i];
-            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & bmask], 1);
+        // four independent loads per thread and step: a long clip's keys live in global memory (np > kKeyCap), and one
+        // load in flight per thread made every pass a chain of L2 round trips
+        for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
+            unsigned k4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) k4[u] = (i0 + u * kThreads < np) ? keys[i0 + u * kThreads] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * kThreads < np && (k4[u] & mask) == prefix) atomicAdd(&s_hist[(k4[u] >> shift) & bmask], 1);
         }
         __syncthreads();
         if (warp == 0) {

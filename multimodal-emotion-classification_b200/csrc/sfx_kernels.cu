@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         // ===================================== phase 1: frames =====================================
         // per-warp running sums live in shared memory (s_wacc[warp][0..2] = centroid, rolloff, rms; s_f = log-mel max)
         if (lane < 2) s_wacc[warp * 16 + lane] = 0.0;
-        if (lane == 0) { s_f[warp] = -FLT_MAX; s_f[16 + warp] = 0.0f; }
+        if (lane == 0) { s_f[warp] = -FLT_MAX; s_f[8 + warp] = -1.0f; s_f[16 + warp] = 0.0f; }
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4) fo.s_lm[32 * s4 + lane] = 0.0;
         fo.s_lmin[lane] = FLT_MAX;

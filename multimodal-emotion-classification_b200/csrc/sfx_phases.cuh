@@ -111,6 +111,9 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             return;
         }
     }
+    if constexpr (kMode == kModeFused) {
+        if (lane == 0) fo.s_f[8 + warp] = static_cast<float>(t);       // this warp's last non-zero frame so far (t grows)
+    }
     // ---- energy of hop t (samples [512t, 512t+512) = rows 16..23); librosa.feature.rms of frame t is
     //      sqrt((E[t-2] + E[t-1] + E[t] + E[t+1]) / 2048) and is pooled in the epilogue
     {
@@ -708,9 +711,13 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             if (tid == 0) cs.s_i[4] = static_cast<int>(0xffffffffu);
             __syncthreads();
             unsigned best = 0xffffffffu;
-            for (int i = tid; i < np; i += kThreads) {
-                const unsigned key = keys[i];
-                if (key > ka && key < best) best = key;
+            for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
+                unsigned k4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) k4[u] = (i0 + u * kThreads < np) ? keys[i0 + u * kThreads] : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k4[u] > ka && k4[u] < best) best = k4[u];
             }
             atomicMin(reinterpret_cast<unsigned*>(&cs.s_i[4]), best);
             __syncthreads();
@@ -723,8 +730,19 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         // histogram of the residual bins of peaks with mag >= median
         for (int i = tid; i < 128; i += kThreads) cs.s_hist[i] = 0;
         __syncthreads();
-        for (int i = tid; i < np; i += kThreads)
-            if (keys[i] >= kthr) atomicAdd(&cs.s_hist[bins[i]], 1);
+        for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
+            unsigned k4[4];
+            int b4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool v = i0 + u * kThreads < np;
+                k4[u] = v ? keys[i0 + u * kThreads] : 0u;
+                b4[u] = v ? bins[i0 + u * kThreads] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * kThreads < np && k4[u] >= kthr) atomicAdd(&cs.s_hist[b4[u]], 1);
+        }
         __syncthreads();
         if (warp == 0) {
             int bc = -1, bi = 1 << 20, tot = 0;
@@ -835,8 +853,15 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         float wny[kChroma];
 #pragma unroll
         for (int c = 0; c < kChroma; ++c) wny[c] = __ldg(tb.chroma_ny + tuning_idx * kChroma + c);
+        // Frames behind the clip's last non-zero frame (the zero tail load_audio pads short clips with) have all-zero
+        // |X|^2 rows and add exactly 0 to every chroma sum: the projection stops at Tc = that frame + 1 (cs.s_f[8 + w] =
+        // last non-zero frame seen by warp w, -1 if none); the mean below still divides by T.
+        float lastnz = cs.s_f[8];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) lastnz = fmaxf(lastnz, cs.s_f[8 + w]);
+        const int Tc = min(T, static_cast<int>(lastnz) + 1);
         // full 8-frame tiles: unit = tile x K-half, dealt round-robin to the warps (16 tiles = 4 units per warp)
-        const int nfull = T >> 3, rem = T & 7;
+        const int nfull = Tc >> 3, rem = Tc & 7;
         for (int tile0 = 0; tile0 < nfull; tile0 += kChromaTiles) {
             const int nt = min(kChromaTiles, nfull - tile0);
             for (int u = warp; u < 2 * nt; u += kWarps) {
@@ -884,7 +909,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             __syncthreads();
             for (int fl = tid; fl < nt * 8; fl += kThreads) {
                 const int f = tile0 * 8 + fl;
-                if (f < T) {
+                if (f < Tc) {
                     const float* q = part2 + (fl >> 3) * 192 + (fl & 7);
                     const float pn = sl.gNy[f];                            // scaled Nyquist bin
                     float raw[kChroma];
@@ -908,7 +933,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         // every warp 4 units + 4 steps instead of 5 units for two of them; the 8 partial sums are added in warp order
         if (rem) {
             const int f = nfull * 8 + g;
-            const bool valid = f < T;
+            const bool valid = f < Tc;
             const int k0 = warp * 128 + 8 * t4;                      // steps 4*warp .. 4*warp+3
             const __half* prow = sl.gP16 + static_cast<size_t>(valid ? f : 0) * kP16Stride + k0;
             const int r1 = (g < 4) ? g + 8 : g;

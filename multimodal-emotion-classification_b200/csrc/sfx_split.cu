@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_clips_kernel(const SplitParam
             }
             sz = warp_sum_i(sz);
             lm = warp_max(lm);
-            if (lane == 0) { s_wacc[warp * 16 + 0] = sc; s_wacc[warp * 16 + 1] = sr; s_i[8 + warp] = sz; s_f[warp] = lm; }
+            if (lane == 0) { s_wacc[warp * 16 + 0] = sc; s_wacc[warp * 16 + 1] = sr; s_i[8 + warp] = sz; s_f[warp] = lm;
+                             s_f[8 + warp] = static_cast<float>(T - 1); }      // no zero-tail shortcut here: project all T frames
             if (tid < kWarps) s_i[20 + tid] = tid == 0 ? npk_all[c] : 0;     // all records in segment 0
             if (tid == 0) { s_i[17] = 0; s_i[18] = 0; s_i[19] = -1; }
         }

@@ -15,16 +15,25 @@ import numpy as np
 from ._config import Config
 
 
+def load_weights(path: str) -> dict:
+    """The .npz written by tools/export_weights.py (from the reference's speech_model.h5 + speech_scaler.pkl)."""
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
+
+
 class BatchedSpeechInference:
-    def __init__(self, weights: dict, device=None, sr: int = Config.SAMPLE_RATE):
+    def __init__(self, weights, device=None, sr: int = Config.SAMPLE_RATE):
+        """weights: dict of numpy arrays (sfx_b200/dnn.py) or the path of an .npz from tools/export_weights.py."""
         import torch
+        if isinstance(weights, (str, bytes)) or hasattr(weights, "__fspath__"):
+            weights = load_weights(weights)
         from . import get_extractor
         from .dnn import SpeechDNN
         self.emotions = Config.EMOTIONS
         dev = torch.device("cuda") if device is None else torch.device(device)
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self.extractor = get_extractor(self.device, sr)
-        self.dnn = SpeechDNN(weights, self.device)
+        self.dnn = SpeechDNN(weights, self.device, bn_eps=float(weights.get("bn_eps", 1e-3)))
 
     def forward(self, waves, lengths=None, n_samples=None):
         """cuda float32 [B, L] -> (probs [B,7], tap [B,64], features [B,56]), all device tensors, stream-ordered."""

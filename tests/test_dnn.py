@@ -1,6 +1,8 @@
 """Scope row f1: scaler + speech DNN forward.  CPU: the numpy oracle against an independent PyTorch restatement.
 GPU (-m gpu): sfx_dnn_forward through the C ABI against the oracle, and config 3 (TESS-shaped clips -> features -> DNN
 with device-resident features)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -107,3 +109,44 @@ def test_heuristic_predict_batch_thresholds():
     assert all(abs(sum(r["all_probabilities"]) - 1.0) < 1e-9 and r["confidence"] == 0.9 for r in res)
     spec = lp.extract_spectral_features(quiet_low, 22050)
     assert spec[3] < 0.02 and spec[1] < 1500
+
+
+def test_export_weights_walks_a_keras_style_layer_list(tmp_path):
+    """tools/export_weights.py (reference side): Dense / BatchNormalization / Activation / Dropout stand-ins with Keras'
+    get_weights() orders -> the dict SpeechDNN takes; round trip through .npz and the oracle forward."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import export_weights as ew
+    m = od.random_model(9)
+
+    def layer(kind, weights, **attrs):
+        cls = type(kind, (), {"get_weights": lambda self: weights})
+        obj = cls()
+        for k, v in attrs.items():
+            setattr(obj, k, v)
+        return obj
+
+    layers = [layer("InputLayer", [])]
+    n = len(m["widths"]) - 1
+    for i in range(n):
+        layers.append(layer("Dense", [m[f"kernel{i}"], m[f"bias{i}"]]))
+        if i < n - 1:
+            layers.append(layer("BatchNormalization", [m[f"gamma{i}"], m[f"beta{i}"], m[f"mean{i}"], m[f"var{i}"]], epsilon=1e-3))
+            layers.append(layer("Activation", []))
+            layers.append(layer("Dropout", []))
+    scaler = type("StandardScaler", (), {})()
+    scaler.mean_, scaler.scale_ = m["scaler_mean"], m["scaler_scale"]
+    d = ew.layers_to_npz(layers, scaler)
+    path = os.path.join(tmp_path, "speech_model.npz")
+    np.savez(path, **d)
+    from sfx_b200.inference import load_weights
+    back = load_weights(path)
+    assert back["widths"].tolist() == list(od.WIDTHS) and float(back["bn_eps"]) == pytest.approx(1e-3)
+    for k, v in m.items():
+        assert np.array_equal(back[k], v), k
+    X = feature_like(5, 1, 2)
+    a = od.forward(m, od.scaler_transform(m, X))
+    b = od.forward(back, od.scaler_transform(back, X))
+    assert np.array_equal(a[0], b[0])
+    with pytest.raises(ValueError):
+        ew.layers_to_npz(layers[:3] + [layer("Conv1D", [np.zeros(3)])])
