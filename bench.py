@@ -262,6 +262,34 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa(index):
+    """Pin this rank's host threads to the CPUs local to its GPU (/sys/bus/pci/devices/<bdf>/local_cpulist) BEFORE any pinned
+    host buffer is allocated, so that first-touch places the staging memory on the GPU's NUMA node.  Returns what was found."""
+    info = {"numa_node": None, "cpus_bound": None}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        info["pci"] = bdf
+        node = int(open(base + "/numa_node").read().strip())
+        info["numa_node"] = node
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = sorted(cpus & allowed)
+        if node >= 0 and use and len(use) < len(allowed):
+            os.sched_setaffinity(0, use)
+            info["cpus_bound"] = f"{use[0]}-{use[-1]} ({len(use)})"
+    except Exception as e:      # noqa: BLE001
+        info["note"] = f"not bound: {e}"
+    return info
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -336,6 +364,7 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
@@ -474,7 +503,7 @@ def main():
     pcm_bitwise = bool(torch.equal(h_out16[:64], ex.extract(deq).cpu()))
     e2e = {"value": Be * world * e2e_steps / pcm_s, "unit": "clips/s", "h2d_bytes_per_step": Be * N_SAMPLES * 2,
            "d2h_bytes_per_step": Be * 56 * 4, "clips_per_gpu_per_step": Be, "steps": e2e_steps,
-           "h2d_gb_per_s_per_gpu": Be * e2e_steps * N_SAMPLES * 2 / pcm_s / 1e9,
+           "h2d_gb_per_s_per_gpu": Be * e2e_steps * N_SAMPLES * 2 / pcm_s / 1e9, "host_binding_rank0": numa,
            "input": "16-bit PCM rows as a 22.05 kHz mono WAV file holds them (pinned host memory)",
            "path": "sfx_extract_host_pcm16: pinned int16 PCM rows -> chunked H2D || device x/32768 (soundfile's conversion) + "
                    "kernel || D2H of the 56-float rows",
@@ -482,7 +511,7 @@ def main():
     e2e_f32 = {"value": e2e_f32_value, "unit": "clips/s", "h2d_bytes_per_step": Be * N_SAMPLES * 4,
                "d2h_bytes_per_step": Be * 56 * 4, "clips_per_gpu_per_step": Be, "steps": e2e_steps,
                "h2d_gb_per_s_per_gpu": Be * e2e_steps * N_SAMPLES * 4 / e2e_s / 1e9,
-               "path": "sfx_extract_host: pinned float32 rows -> chunked H2D || kernel || D2H on 2 streams",
+               "path": "sfx_extract_host: pinned float32 rows -> chunked H2D || kernel || D2H on 3 streams",
                "rows_bitwise_equal_device_path": e2e_match}
 
     # file-shaped input: 3 s of 48 kHz mono 16-bit PCM per clip (what a RAVDESS WAV file holds), resampled to 22.05 kHz on

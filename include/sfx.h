@@ -139,7 +139,7 @@ int         sfx_extract_debug(int device, int32_t sr, const float *wave, int64_t
                               void *stream, const sfx_debug_out *dbg);
 
 /* Batched extraction, HOST buffers (the reference-facing plugin path): pinned staging, chunked
- * H2D copy overlapped with the kernel on two streams, D2H of the feature rows, then a stream sync.
+ * H2D copy overlapped with the kernel on three streams, D2H of the feature rows, then a stream sync.
  * host_lengths may be NULL; a length outside [1, row_stride] is rejected with SFX_ERR_BAD_CLIP before any work.
  * Samples are not scanned on the host (that would cost more than the PCIe copy): a clip with a NaN / Inf sample gets a
  * NaN feature row, and the call returns SFX_ERR_BAD_CLIP naming the first such clip after delivering every row (the

@@ -16,18 +16,18 @@
 namespace {
 
 constexpr int kMaxDev = 16;
-constexpr int kHostStreams = 2;
+constexpr int kHostStreams = 3;
 
 struct HostPath {               // cached buffers of sfx_extract_host
-    cudaStream_t stream[kHostStreams] = {nullptr, nullptr};
-    float* d_wave[kHostStreams] = {nullptr, nullptr};
-    int16_t* d_pcm[kHostStreams] = {nullptr, nullptr};   // raw PCM16 rows of sfx_extract_host_pcm16
-    int* d_len[kHostStreams] = {nullptr, nullptr};
-    float* d_out[kHostStreams] = {nullptr, nullptr};
-    void* d_ws[kHostStreams] = {nullptr, nullptr};
-    float* h_stage[kHostStreams] = {nullptr, nullptr};   // pinned staging for pageable input
-    float* h_out[kHostStreams] = {nullptr, nullptr};     // pinned staging for pageable output
-    cudaEvent_t ev_done[kHostStreams] = {nullptr, nullptr};
+    cudaStream_t stream[kHostStreams] = {};
+    float* d_wave[kHostStreams] = {};
+    int16_t* d_pcm[kHostStreams] = {};   // raw PCM16 rows of sfx_extract_host_pcm16
+    int* d_len[kHostStreams] = {};
+    float* d_out[kHostStreams] = {};
+    void* d_ws[kHostStreams] = {};
+    float* h_stage[kHostStreams] = {};   // pinned staging for pageable input
+    float* h_out[kHostStreams] = {};     // pinned staging for pageable output
+    cudaEvent_t ev_done[kHostStreams] = {};
     size_t wave_elems = 0, ws_bytes = 0, out_elems = 0;
     int chunk = 0;
 };
@@ -323,7 +323,10 @@ int extract_host_impl(int device, int32_t sr, const S* host_wave, int64_t row_st
     }
     // rows are copied up to max_samples only (rounded to even for 8-byte alignment of every device row)
     const int64_t dev_stride = (max_samples + 1) & ~int64_t(1);
-    int chunk = chunk_clips > 0 ? chunk_clips : static_cast<int>(std::max<int64_t>(64, (256ll << 20) / (dev_stride * 4)));
+    // default chunk: ~96 MB of float rows (~380 three-second clips).  The copy engine is the bottleneck (a chunk's kernels
+    // take a fifth of its H2D time), so chunks only need to be large enough to amortise launches; smaller chunks shorten the
+    // un-overlapped head (first H2D) and tail (last kernel + D2H) of a call, three buffers keep the H2D queue non-empty
+    int chunk = chunk_clips > 0 ? chunk_clips : static_cast<int>(std::max<int64_t>(64, (96ll << 20) / (dev_stride * 4)));
     chunk = std::min(chunk, B);
     const int out_w = n_mfcc + 16;
     const size_t need_wave = static_cast<size_t>(chunk) * dev_stride;

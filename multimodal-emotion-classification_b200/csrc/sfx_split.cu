@@ -193,12 +193,13 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_clips_kernel(const SplitParam
         {
             double sc = 0.0, sr = 0.0;
             int sz = 0;
-            float lm = -FLT_MAX;
+            float lm = -FLT_MAX, lastnz = -1.0f;
             for (int t = tid; t < T; t += kThreads) {
                 sc += static_cast<double>(sl.gCent[t]);
                 sr += static_cast<double>(sl.gRoll[t]);
                 sz += sl.gZc[t];
                 lm = fmaxf(lm, sl.gLmax[t]);
+                if (sl.gInvS[t] != 0.0f) lastnz = static_cast<float>(t);     // 1/scale is 0 exactly for the all-zero frames
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -207,8 +208,9 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_clips_kernel(const SplitParam
             }
             sz = warp_sum_i(sz);
             lm = warp_max(lm);
+            lastnz = warp_max(lastnz);
             if (lane == 0) { s_wacc[warp * 16 + 0] = sc; s_wacc[warp * 16 + 1] = sr; s_i[8 + warp] = sz; s_f[warp] = lm;
-                             s_f[8 + warp] = static_cast<float>(T - 1); }      // no zero-tail shortcut here: project all T frames
+                             s_f[8 + warp] = lastnz; }       // last non-zero frame: the chroma projection stops there (as in the fused kernel)
             if (tid < kWarps) s_i[20 + tid] = tid == 0 ? npk_all[c] : 0;     // all records in segment 0
             if (tid == 0) { s_i[17] = 0; s_i[18] = 0; s_i[19] = -1; }
         }
