@@ -44,6 +44,7 @@ struct Dnn {
 constexpr int kFR = 32;                      // feature rows per CTA (two 16-row MMA tiles)
 constexpr int kFMaxW = 512;                  // widest layer the fused kernel takes
 constexpr int kFLd = kFMaxW + 8;             // halves per activation row in shared memory (1040 B: conflict-free ldmatrix)
+static_assert(kFMaxW % 64 == 0, "layer widths are padded to 64 inside the activation rows");
 constexpr int kFThreads = 256;
 
 struct FusedLayer { const uint2* bhi; const uint2* blo; const float* scale; const float* shift; int K, N, Kp, Np; };
@@ -58,6 +59,7 @@ struct FusedParams {
 };
 
 __host__ __device__ inline int round16(int x) { return (x + 15) & ~15; }
+__host__ __device__ inline int round64(int x) { return (x + 63) & ~63; }     // K is padded to 4 MMA K steps: the weight loop prefetches four steps
 
 __device__ __forceinline__ void ldmatrix_x4(unsigned (&r)[4], const __half* ptr) {
     const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(ptr));
@@ -116,20 +118,29 @@ __global__ void __launch_bounds__(kFThreads) dnn_fused_kernel(const __grid_const
             float acx[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};      // 2^11 * (hi . lo + lo . hi)
             const uint2* bh = L.bhi + static_cast<size_t>(j) * ksteps * 32 + lane;
             const uint2* bl = L.blo + static_cast<size_t>(j) * ksteps * 32 + lane;
-            uint2 wh = __ldg(bh), wl = __ldg(bl);
-            for (int s = 0; s < ksteps; ++s) {
-                const int sn = min(s + 1, ksteps - 1);
-                const uint2 nwh = __ldg(bh + sn * 32), nwl = __ldg(bl + sn * 32);
+            // weights four K steps ahead of the MMAs that use them (one L2 round trip per 24 MMAs instead of per 6)
+            uint2 wh[4], wl[4];
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    unsigned ah[4], al[4];
-                    ldmatrix_x4(ah, in_hi + m * 16 * kFLd + s * 16 + a_off);
-                    ldmatrix_x4(al, in_lo + m * 16 * kFLd + s * 16 + a_off);
-                    mma16816(acc[m], ah, wh.x, wh.y);
-                    mma16816(acx[m], ah, wl.x, wl.y);
-                    mma16816(acx[m], al, wh.x, wh.y);
+            for (int q = 0; q < 4; ++q) { wh[q] = __ldg(bh + q * 32); wl[q] = __ldg(bl + q * 32); }
+            for (int s0 = 0; s0 < ksteps; s0 += 4) {
+                uint2 nwh[4], nwl[4];
+                const int sn = min(s0 + 4, ksteps - 4);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { nwh[q] = __ldg(bh + (sn + q) * 32); nwl[q] = __ldg(bl + (sn + q) * 32); }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        unsigned ah[4], al[4];
+                        ldmatrix_x4(ah, in_hi + m * 16 * kFLd + (s0 + q) * 16 + a_off);
+                        ldmatrix_x4(al, in_lo + m * 16 * kFLd + (s0 + q) * 16 + a_off);
+                        mma16816(acc[m], ah, wh[q].x, wh[q].y);
+                        mma16816(acx[m], ah, wl[q].x, wl[q].y);
+                        mma16816(acx[m], al, wh[q].x, wh[q].y);
+                    }
                 }
-                wh = nwh; wl = nwl;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { wh[q] = nwh[q]; wl[q] = nwl[q]; }
             }
             // epilogue: D fragment = rows g, g+8 of the 16-row tile, columns 8j + 2*t4, +1
             const int c0 = j * 8 + 2 * t4;
@@ -326,7 +337,7 @@ int sfx_dnn_create(int device, const sfx_dnn_host* h, void** handle) {
     for (int i = 0; i <= h->n_layers; ++i) fits &= h->dims[i] <= kFMaxW;
     if (rc == SFX_OK && fits) {
         for (int l = 0; l < h->n_layers && rc == SFX_OK; ++l) {
-            const int K = h->dims[l], N = h->dims[l + 1], Kp = round16(K), Np = round16(N);
+            const int K = h->dims[l], N = h->dims[l + 1], Kp = round64(K), Np = l + 1 < h->n_layers ? round64(N) : round16(N);
             const int ntiles = Np / 8, ksteps = Kp / 16;
             std::vector<uint2> fh(static_cast<size_t>(ntiles) * ksteps * 32), fl(fh.size());
             auto split = [&](int k, int n, unsigned short& hi, unsigned short& lo) {
@@ -383,8 +394,8 @@ int sfx_dnn_forward(void* handle, const float* feats, int64_t feat_stride, int32
         FusedParams fp{};
         fp.n_layers = d->n_layers;
         for (int l = 0; l < d->n_layers; ++l)
-            fp.L[l] = FusedLayer{d->bhi[l], d->blo[l], d->scale[l], d->shift[l], d->dims[l], d->dims[l + 1], round16(d->dims[l]),
-                                 round16(d->dims[l + 1])};
+            fp.L[l] = FusedLayer{d->bhi[l], d->blo[l], d->scale[l], d->shift[l], d->dims[l], d->dims[l + 1], round64(d->dims[l]),
+                                 l + 1 < d->n_layers ? round64(d->dims[l + 1]) : round16(d->dims[l + 1])};
         fp.pre_mean = d->pre_mean; fp.pre_inv = d->pre_inv;
         fp.feats = feats; fp.feat_stride = feat_stride; fp.B = B;
         fp.probs = probs; fp.probs_stride = probs_stride; fp.tap = tap; fp.tap_stride = tap_stride;

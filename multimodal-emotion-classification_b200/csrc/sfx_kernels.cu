@@ -126,6 +126,9 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         int acc_zc = 0, wcount = 0;
         __syncwarp();
 
+#ifdef SFX_FUSED_DIAG
+        const long long fprof_f0 = clock64();
+#endif
         for (int t = warp; t < T; t += kWarps)
             process_frame<kDebug, kModeFused>(p, tb, fs, fo, x, n, T, t, clip, lane, warp, acc_zc, wcount);
 
@@ -136,9 +139,30 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         }
         __syncthreads();
 
+#ifdef SFX_FUSED_DIAG
+        if (tid == 0) {
+            atomicAdd(&g_fprof[0], static_cast<unsigned long long>(clock64() - fprof_f0));
+            atomicAdd(&g_fprof[7], 1ull);
+        }
+        const long long fprof_t0 = clock64();
+#endif
         clip_tail<kDebug>(p, tb, cs, sl, clip, T, out, bank_parity, tid, lane, warp);
+#ifdef SFX_FUSED_DIAG
+        if (tid == 0) atomicAdd(&g_fprof[6], static_cast<unsigned long long>(clock64() - fprof_t0));
+#endif
     }
 }
+
+#ifdef SFX_FUSED_DIAG
+extern "C" int sfx_fused_prof(unsigned long long* out, int reset) {
+    int rc = static_cast<int>(cudaMemcpyFromSymbol(out, g_fprof, sizeof(g_fprof)));
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        rc |= static_cast<int>(cudaMemcpyToSymbol(g_fprof, z, sizeof(z)));
+    }
+    return rc;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Longest-processing-time-first order of a ragged batch: one CTA, counting sort of the clips by a 256-level logarithmic

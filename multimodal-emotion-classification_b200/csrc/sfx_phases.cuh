@@ -11,6 +11,16 @@
 
 namespace sfx {
 
+// Cycle accounting of the fused kernel (library built with -DSFX_FUSED_DIAG, tools/fused_prof.py): thread 0 of every CTA adds
+// the cycles between phase boundaries to g_fprof[phase]; 0 frames, 1 per-peak loop, 2 median select + histogram, 3 MFCC,
+// 4 wait for the bank, 5 chroma, 6 epilogue, 7 clips
+#ifdef SFX_FUSED_DIAG
+__device__ unsigned long long g_fprof[8];
+#define FPROF_MARK(k) do { if (threadIdx.x == 0) { const long long fp1 = clock64(); atomicAdd(&g_fprof[k], static_cast<unsigned long long>(fp1 - fprof_t)); fprof_t = fp1; } } while (0)
+#else
+#define FPROF_MARK(k) do { } while (0)
+#endif
+
 // shared-memory tables and the calling warp's tile (phase 1)
 struct FrameSmem {
     const float2* s_hann; const float2* s_tw1; const float2* s_tw2; const float2* s_melab;
@@ -258,7 +268,6 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
     //      falling/rising partial sums flushed whenever the filter interval advances
     float cent_t, roll_t;
     {
-        float s[33];
         float run = 0.0f, ks = 0.0f;
         c64 acc = pk(0.0f, 0.0f);                        // (falling, rising) partial sums of the current interval
         float* pq = fs.part + lane * fs.mel_ps;
@@ -293,11 +302,9 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
                 acc = fma2(bc2(P), (j & 1) ? ab.y : ab.x, acc);
                 const float sv = sqrt_approx(P);
                 run += sv;
-                s[j] = run;
                 ks = fmaf(static_cast<float>(j), sv, ks);
             });
         });
-        s[32] = run;
         float accA, accB;
         upk(acc, accA, accB);
         if (lane == 31) {
@@ -308,7 +315,6 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             accB = fmaf(ab1.y, P, accB);
             const float sv = sqrt_approx(P);
             run += sv;
-            s[32] = run;
             ks = fmaf(32.0f, sv, ks);
         }
         pq[0] = accA;
@@ -336,15 +342,22 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
         if (lane == 0) exc = 0.0f;
         const float total = __shfl_sync(0xffffffffu, inc, 31);
         const float thr = __fmul_rn(0.85f, total);
-        // first bin whose cumulative |X| reaches the threshold = number of (monotone) prefix sums below it
-        const float thrL = thr - exc;
-        float cntf = 0.0f;
+        // first bin whose cumulative |X| reaches the threshold.  The prefix sums are monotone, so the lanes whose whole
+        // 32-bin chunk lies below the threshold form a prefix of the warp; the chunk of the first other lane L holds the
+        // bin, and the warp finds it there together: lane j re-reads bin 32 L + j from the tile, one shuffle scan, one
+        // ballot (instead of every lane keeping its 32 running sums in registers and counting through them)
+        const int L = __popc(__ballot_sync(0xffffffffu, inc < thr));
+        int first = 1024;
+        if (L < 32) {                                                  // warp-uniform
+            const float thrL = thr - __shfl_sync(0xffffffffu, exc, L);
+            float pre = sqrt_approx(fs.Pb[kPRow * L + lane]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) cntf += (s[j] < thrL) ? 1.0f : 0.0f;
-        const int cnt = static_cast<int>(cntf);
-        int first = (cnt < 32) ? 32 * lane + cnt : 1024;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            for (int o = 1; o < 32; o <<= 1) {
+                const float v = __shfl_up_sync(0xffffffffu, pre, o);
+                if (lane >= o) pre += v;
+            }
+            first = min(1024, 32 * L + __popc(__ballot_sync(0xffffffffu, pre < thrL)));
+        }
         const float num = warp_sum(fmaf(32.0f * lane, run, ks));
         cent_t = (total < FLT_MIN) ? 0.0f : (num / total) * fs.bin_hz;
         roll_t = static_cast<float>(first) * fs.bin_hz;
@@ -453,8 +466,10 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             const float pm = q0[off], pc = q1[off], pp = q2[off];
             const bool pk = (r <= rmax) & (pc > ref) & (pc > pm) & (pc >= pp);
             const unsigned bal = __ballot_sync(0xffffffffu, pk);
-            st_record_if(pk, fo.gSeg, cnt + __popc(bal & lt), pm, pc, pp, kfirst + 32 * r);
-            cnt += __popc(bal);
+            if (bal) {                                               // warp-uniform: most rows of a tonal frame hold no peak
+                st_record_if(pk, fo.gSeg, cnt + __popc(bal & lt), pm, pc, pp, kfirst + 32 * r);
+                cnt += __popc(bal);
+            }
         }
         wcount = static_cast<int>(cnt);
     } else {
@@ -539,6 +554,9 @@ template <bool kDebug>
 __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, const ClipSmem& cs, const ClipSlice& sl,
                                           const int clip, const int T, float* __restrict__ out, unsigned& bank_parity,
                                           const int tid, const int lane, const int warp) {
+#ifdef SFX_FUSED_DIAG
+    long long fprof_t = clock64();
+#endif
     // ===================================== phase 2: tuning =====================================
     // peak records: segment w of the slice holds cs.s_i[20 + w] records (the split pipeline uses segment 0 only)
     int np = 0;
@@ -671,6 +689,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         };
         if (in_smem) peaks(std::true_type{}); else peaks(std::false_type{});
         __syncthreads();
+        FPROF_MARK(1);
         {
             const int nredo = min(cs.s_i[17], kRedoCap);
             for (int j = tid; j < nredo; j += kThreads) {
@@ -778,6 +797,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         }
     }
 
+    FPROF_MARK(2);
     // ===================================== phase 3a: MFCC ======================================
     // The tuning's FP16 hi/lo chroma bank (50 688 B) is staged into the now-free warp tiles by one TMA bulk copy
     // (cp.async.bulk, completes on an mbarrier) that runs underneath the MFCC pooling.
@@ -828,13 +848,20 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             if (tid < 128) cs.s_pool[tid] = (cs.s_pool[tid] + cs.s_pool[128 + tid]) / static_cast<double>(T);
         }
         __syncthreads();
-        if (tid < p.n_mfcc) {
+        {
+            // DCT-II of the pooled log-mel vector: coefficient k by a pair of threads (bands 0..63 and 64..127, the two
+            // partial sums added in that order), which halves the dependent float64 FMA chain on the tail's critical path
+            const int k = tid >> 1, h = tid & 1;
             double d = 0.0;
-            for (int q = 0; q < kMels; ++q) d = fma(tb.dctT[q * kMels + tid], cs.s_pool[q], d);
-            out[tid] = static_cast<float>(d);
+            if (k < p.n_mfcc)
+                for (int q = 64 * h; q < 64 * h + 64; ++q) d = fma(tb.dctT[q * kMels + k], cs.s_pool[q], d);
+            const double o = __shfl_xor_sync(0xffffffffu, d, 1);
+            if (k < p.n_mfcc && h == 0) out[k] = static_cast<float>(d + o);
         }
     }
+    FPROF_MARK(3);
     mbar_wait(cs.s_mbar, bank_parity);                     // chroma bank has landed in shared memory
+    FPROF_MARK(4);
     bank_parity ^= 1u;
 
     // ===================================== phase 3b: chroma ====================================
@@ -995,6 +1022,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
     }
     __syncthreads();
 
+    FPROF_MARK(5);
     // ===================================== epilogue: pooled row ================================
     if (warp == 1) {
         // pooled rms from the hop energies (frame t spans hops t-2 .. t+1; hops outside [0, T) are zero padding)

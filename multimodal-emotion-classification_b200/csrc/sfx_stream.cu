@@ -558,10 +558,13 @@ static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned cha
         for (int k0 = 0; k0 < p.n_mfcc; k0 += 32) {
             const int k = k0 + lane;
             if (k < p.n_mfcc) {
-                double d = 0.0;
+                double d0 = 0.0, d1 = 0.0;                   // bands 0..63 and 64..127, added in that order (as clip_tail)
 #pragma unroll 8
-                for (int q = 0; q < kMels; ++q) d = fma(tb.dctT[q * kMels + k], pool[q], d);
-                out[k] = static_cast<float>(d);
+                for (int q = 0; q < 64; ++q) {
+                    d0 = fma(tb.dctT[q * kMels + k], pool[q], d0);
+                    d1 = fma(tb.dctT[(q + 64) * kMels + k], pool[q + 64], d1);
+                }
+                out[k] = static_cast<float>(d0 + d1);
             }
         }
         __syncwarp();
