@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SFX_ABI_VERSION 2
+#define SFX_ABI_VERSION 3
 #define SFX_N_CHROMA    12
 #define SFX_N_SPECTRAL  4      /* [zcr, spectral_centroid, spectral_rolloff, rms] (reference :33-37) */
 #define SFX_N_FFT       2048
@@ -70,6 +70,8 @@ typedef struct {
     const double *edges;         /* [101] */
     const uint32_t*chroma_frag;  /* [100][32][2][2][32][4] the bank as mma.m16n8k16 A fragments: (tuning, 32-bin step,
                                   * half step, hi/lo, lane) -> one 16-byte quad (stream pipeline; see tables.py) */
+    const uint8_t *chroma_umma;  /* [100][16][4096] the bank as tcgen05 B-operand shared-memory images (K-major, 128-byte
+                                  * swizzle), one per (tuning, 64-bin block); used by builds with SFX_CHROMA_UMMA */
 } sfx_tables_host;
 
 /* Optional per-clip / per-frame intermediates for parity triage (device pointers, any may be NULL). */
@@ -105,14 +107,16 @@ size_t      sfx_workspace_bytes_batch(int device, int64_t max_samples, int64_t B
  * CTAs), whose clips are processed longest first; split pipeline: 3 per chunk of <= 1024 clips). */
 int         sfx_launches_per_extract(void);
 
-/* Pipeline selection: 0 = auto (default), 1 = fused, 2 = split, 3 = stream.  One arithmetic, three schedules:
+/* Pipeline selection: 0 = auto (default), 1 = fused, 2 = split, 3 = stream, 4 = fused_umma.  One arithmetic:
  *   stream  one persistent 16-warp CTA per SM; every warp pulls STFT frames or whole per-clip tails (tuning estimate,
  *           MFCC, chroma, pooled row) from a CTA-local scheduler, so a tail occupies one warp while 15 keep transforming
  *           frames.  Highest throughput on large batches.
  *   fused   persistent 8-warp CTAs, two per SM, one clip per CTA at a time (frames, barrier, tail by all 8 warps).
  *   split   frame-parallel two-kernel pipeline per chunk of <= 1024 clips: lowest latency for small batches.
+ *   fused_umma  the fused kernel with its chroma projection on tcgen05 (UMMA, accumulator in tensor memory) instead of
+ *           mma.sync: same throughput (measured), kept as the A/B of the two tensor paths.
  * auto = split for batches that fit one chunk of at most 1024 clips (256 when ragged), stream above that.  Also settable
- * through the environment variable SFX_PIPELINE=auto|fused|split|stream before the first call.  The mode is read once per
+ * through the environment variable SFX_PIPELINE=auto|fused|split|stream|fused_umma before the first call.  The mode is read once per
  * call (atomically); call sfx_workspace_bytes again after changing it. */
 int         sfx_set_pipeline(int mode);
 

@@ -89,7 +89,7 @@ bool snapshot(int device, int sr, LaunchCtx* out) {
 // kAutoLarge.
 constexpr int kAutoSplitMaxB = 1024;
 constexpr int kAutoSplitMaxBRagged = 256;
-constexpr int kPipeFused = 1, kPipeSplit = 2, kPipeStream = 3;
+constexpr int kPipeFused = 1, kPipeSplit = 2, kPipeStream = 3, kPipeFusedUmma = 4;
 #ifndef SFX_AUTO_LARGE
 #define SFX_AUTO_LARGE 1        // measured (tools/ab_modes.py, bench mix): fused 1.78 M clips/s, stream 1.42 M
 #endif
@@ -99,6 +99,7 @@ std::atomic<int> g_pipeline{[] {
     if (e && std::strcmp(e, "split") == 0) return kPipeSplit;
     if (e && std::strcmp(e, "fused") == 0) return kPipeFused;
     if (e && std::strcmp(e, "stream") == 0) return kPipeStream;
+    if (e && std::strcmp(e, "fused_umma") == 0) return kPipeFusedUmma;
     return 0;
 }()};
 // L2 pinning of the fused kernel's read-back rows: SFX_L2_PIN = 0 (off) | 1 (FP16 |X|^2 rows, default) | 2 (+ log-mel rows)
@@ -188,7 +189,7 @@ size_t pipeline_ws_bytes(const LaunchCtx& c, int pipe, int64_t max_samples, int6
     }
     size_t grid = static_cast<size_t>(c.grid_max);
     if (B > 0) grid = std::min<size_t>(grid, static_cast<size_t>(B));
-    return sfx::kWsHeader + sfx::cta_scratch_bytes(Tmax, c.max_pk) * grid;
+    return sfx::kWsHeader + sfx::cta_scratch_bytes(Tmax, c.max_pk, pipe == kPipeFusedUmma) * grid;
 }
 
 // workspace that covers every pipeline the current mode may select for a batch of B clips (B <= 0: any batch size)
@@ -252,14 +253,14 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
         g_last_launches = launches;
         return SFX_OK;
     }
-    const bool stream_pipe = pipe == kPipeStream;
+    const bool stream_pipe = pipe == kPipeStream, umma = pipe == kPipeFusedUmma;
     const size_t slice = stream_pipe ? sfx::stream_slot_bytes(Tmax, c.max_pk) * sfx::stream_slots()
-                                     : sfx::cta_scratch_bytes(Tmax, c.max_pk);
+                                     : sfx::cta_scratch_bytes(Tmax, c.max_pk, umma);
     const int grid = static_cast<int>(std::min<int64_t>(B, stream_pipe ? c.sm_count * c.stream_per_sm : c.grid_max));
     if (ws_bytes < sfx::kWsHeader + slice * static_cast<size_t>(grid))
         return fail(SFX_ERR_WORKSPACE, "workspace smaller than sfx_workspace_bytes(device, max_samples)");
     p.cta_scratch_bytes = static_cast<long long>(stream_pipe ? sfx::stream_slot_bytes(Tmax, c.max_pk) : sfx::cta_rest_bytes(Tmax, c.max_pk));
-    p.cta_p16_bytes = static_cast<long long>(sfx::cta_p16_bytes(Tmax));
+    p.cta_p16_bytes = static_cast<long long>(sfx::cta_p16_bytes(Tmax, umma));
     p.cta_lm_bytes = static_cast<long long>(sfx::cta_lm_bytes(Tmax));
     CK(cudaMemsetAsync(ws, 0, sfx::kWsQueueBytes, st));
     g_last_launches = 1;
@@ -274,7 +275,7 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
     // set-aside can hold, so that persisting lines never evict each other.
     // (long clips: the block outgrows the window and nothing of it would stay resident anyway -- no pinning then, the
     // set-aside is simply unused for that launch)
-    const size_t pin_bytes = static_cast<size_t>(grid) * (sfx::cta_p16_bytes(Tmax) + (g_l2_mode == 2 ? sfx::cta_lm_bytes(Tmax) : 0));
+    const size_t pin_bytes = static_cast<size_t>(grid) * (sfx::cta_p16_bytes(Tmax, umma) + (g_l2_mode == 2 ? sfx::cta_lm_bytes(Tmax) : 0));
     const bool l2_pin = !stream_pipe && c.l2_persist > 0 && g_l2_mode != 0 && pin_bytes <= c.l2_window;
     if (l2_pin) {
         const size_t win = pin_bytes;
@@ -287,7 +288,7 @@ int do_extract(int device, int sr, const float* wave, int64_t row_stride, const 
         CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
     }
     if (stream_pipe) CK(sfx::launch_stream(p, grid, dbg != nullptr, st));
-    else             CK(sfx::launch_extract(p, grid, dbg != nullptr, st));
+    else             CK(sfx::launch_extract(p, grid, dbg != nullptr, umma, st));
     if (l2_pin) {                                            // later work on the caller's stream is not ours to steer
         cudaStreamAttrValue av{};
         av.accessPolicyWindow.num_bytes = 0;
@@ -440,7 +441,7 @@ int sfx_device_count(void) {
 int sfx_launches_per_extract(void) { return g_last_launches; }
 
 int sfx_set_pipeline(int mode) {
-    if (mode < 0 || mode > 3) return fail(SFX_ERR_ARG, "pipeline mode must be 0 (auto), 1 (fused), 2 (split) or 3 (stream)");
+    if (mode < 0 || mode > 4) return fail(SFX_ERR_ARG, "pipeline mode must be 0 (auto), 1 (fused), 2 (split), 3 (stream) or 4 (fused_umma)");
     g_pipeline.store(mode);
     return SFX_OK;
 }
@@ -462,7 +463,7 @@ int sfx_release(int device) {
 int sfx_init_tables(int device, const sfx_tables_host* t) {
     if (device < 0 || device >= kMaxDev) return fail(SFX_ERR_ARG, "device index out of range");
     if (!t || !t->hann || !t->tw1 || !t->tw2 || !t->mel_ab || !t->mel_mask || !t->mel_src || !t->chroma16 || !t->chroma_ny || !t->dct ||
-        !t->edges || !t->chroma_frag || t->sr <= 0)
+        !t->edges || !t->chroma_frag || !t->chroma_umma || t->sr <= 0)
         return fail(SFX_ERR_ARG, "null table pointer or bad sizes");
     if (t->mel_ps < 3 || (t->mel_ps & 1) == 0 || sfx::kPartOff + 32 * t->mel_ps + 1 > sfx::kExFloats)
         return fail(SFX_ERR_ARG, "mel_ps must be odd and fit the warp tile");
@@ -510,6 +511,7 @@ int sfx_init_tables(int device, const sfx_tables_host* t) {
         if ((rc = upload(c, t->chroma_frag, static_cast<size_t>(sfx::kTunings) * 32 * 2 * 2 * 32 * 4, &frag))) return rc;
         set.tb.chroma_frag = reinterpret_cast<const uint4*>(frag);
     }
+    if ((rc = upload(c, t->chroma_umma, static_cast<size_t>(sfx::kTunings) * 16 * 4096, &set.tb.chroma_umma))) return rc;
     std::vector<double> dctT(static_cast<size_t>(sfx::kMels) * sfx::kMels);
     for (int k = 0; k < sfx::kMels; ++k)
         for (int m = 0; m < sfx::kMels; ++m) dctT[static_cast<size_t>(m) * sfx::kMels + k] = t->dct[static_cast<size_t>(k) * sfx::kMels + m];
@@ -519,6 +521,10 @@ int sfx_init_tables(int device, const sfx_tables_host* t) {
     set.tb.sr = t->sr; set.tb.kmin = t->pip_kmin; set.tb.kmax = t->pip_kmax;
     CK(sfx::configure_kernels(&c.blocks_per_sm));
     if (c.blocks_per_sm < 1) return fail(SFX_ERR_CUDA, "kernel does not fit on an SM");
+    if (const char* e = std::getenv("SFX_BLOCKS_PER_SM")) {      // experiment: override the occupancy calculator's answer
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= 4) c.blocks_per_sm = v;
+    }
     c.grid_max = c.sm_count * c.blocks_per_sm;
     CK(sfx::configure_split(&c.frames_per_sm, &c.clips_per_sm));
     if (c.frames_per_sm < 1 || c.clips_per_sm < 1) return fail(SFX_ERR_CUDA, "split kernels do not fit on an SM");

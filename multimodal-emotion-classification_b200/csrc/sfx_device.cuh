@@ -297,6 +297,65 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     }
 }
 
+// ---- tcgen05 (UMMA + tensor memory), used by the SFX_CHROMA_UMMA build of the fused kernel's chroma projection
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s_nx(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {   // no expect_tx
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(unsigned* smem_dst, unsigned ncols) {      // one warp, converged
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {        // one warp, converged
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// shared-memory matrix descriptor of a K-major operand block with the 128-byte swizzle: rows of 128 bytes, 8-row atoms of
+// 1 KB (stride byte offset 1024), start address 1 KB aligned plus k * 32 bytes for the k-th 16-element K step of the block
+__device__ __forceinline__ unsigned long long umma_desc_sw128(unsigned smem_addr) {
+    return static_cast<unsigned long long>((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | (static_cast<unsigned long long>(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, FP16 operands, FP32 accumulate; issued by one thread
+__device__ __forceinline__ void umma_f16(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {               // arrives on bar when all prior MMAs are done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 consecutive FP32 columns of this thread's TMEM lane (warp w reads lanes 32*(w%4) .. +31)
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
+    unsigned r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// byte offset, inside a clip's UMMA-image |X|^2 scratch, of the 16-byte chunk c (8 bins) of K block kb of frame t
+__device__ __forceinline__ size_t umma_p16_offset(int Tmax, int t, int kb, int c) {
+    const int tile = t >> 7, r = t & 127;
+    const int na = min(16, ((Tmax + 7) >> 3) - 16 * tile);          // 8-row atoms of this tile (the last tile may be short)
+    return static_cast<size_t>(tile) * (16 * 16 * 1024) + static_cast<size_t>(kb) * na * 1024 + (r >> 3) * 1024 + (r & 7) * 128 +
+           ((c ^ (r & 7)) << 4);
+}
+
 // raw samples of STFT frame t (zero padded) -> re[m1] = x[2m], im[m1] = x[2m+1], m = 32*m1 + lane
 __device__ __forceinline__ void load_frame(const float* __restrict__ x, long long n, int t, int lane, bool aligned8,
                                            float (&re)[32], float (&im)[32]) {

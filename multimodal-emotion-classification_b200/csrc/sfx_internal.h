@@ -41,6 +41,7 @@ struct DevTables {
     const uint16_t* chroma16;   // [100][2][12][1056] half: hi, lo * 2^11
     const float* chroma_ny;     // [100][12]
     const uint4* chroma_frag;   // [100][32 steps][2 half steps][2 hi/lo][32 lanes] A fragments of the bank
+    const unsigned char* chroma_umma;   // [100][16 K blocks][4096] tcgen05 B-operand images of the bank
     const double* dctT;     // [128 mel][128 k]  (transposed: coalesced over k)
     const double* edges;    // [101]
     int sr, kmin, kmax;
@@ -82,7 +83,12 @@ __host__ __device__ inline int rec_frames(int Tmax) { return (Tmax + kWarps - 1)
 // The rows that phase 3 reads back are kept together so that ONE stream access-policy window can pin them in L2
 // (persisting set-aside): they are written once and read once ~100 us later, and would otherwise be pushed out to HBM by
 // the waveform stream in between.
-inline size_t cta_p16_bytes(int Tmax) { return (static_cast<size_t>(Tmax) * kP16Stride * 2 + 255) & ~static_cast<size_t>(255); }
+// (UMMA build: the rows are stored as the shared-memory images of 128-frame x 64-bin operand blocks, 8-row atoms of 1 KB,
+//  16 K blocks per atom row group: ceil(Tmax / 8) * 16 KB)
+inline size_t cta_p16_bytes(int Tmax, bool umma = false) {
+    if (umma) return static_cast<size_t>((Tmax + 7) / 8) * 16 * 1024;
+    return (static_cast<size_t>(Tmax) * kP16Stride * 2 + 255) & ~static_cast<size_t>(255);
+}
 inline size_t cta_lm_bytes(int Tmax) { return (static_cast<size_t>(Tmax) * kMels * 4 + 255) & ~static_cast<size_t>(255); }
 // bytes of the rest of a CTA's scratch for clips of up to Tmax frames (multiple of 256)
 inline size_t cta_rest_bytes(int Tmax, int max_pk) {
@@ -92,7 +98,9 @@ inline size_t cta_rest_bytes(int Tmax, int max_pk) {
                static_cast<size_t>(rec_frames(Tmax)) * max_pk * 16;
     return (b + 255) & ~static_cast<size_t>(255);
 }
-inline size_t cta_scratch_bytes(int Tmax, int max_pk) { return cta_p16_bytes(Tmax) + cta_lm_bytes(Tmax) + cta_rest_bytes(Tmax, max_pk); }
+inline size_t cta_scratch_bytes(int Tmax, int max_pk, bool umma = false) {
+    return cta_p16_bytes(Tmax, umma) + cta_lm_bytes(Tmax) + cta_rest_bytes(Tmax, max_pk);
+}
 
 // ---- split pipeline (sfx_split.cu): workspace = header | per-clip peak counters | frame prefix | slices
 constexpr int kSplitChunkMax = 1024;                        // clips per chunk (prep kernel = one 1024-thread block)
@@ -129,7 +137,7 @@ size_t smem_bytes();
 cudaError_t configure_split(int* frames_per_sm, int* clips_per_sm);
 cudaError_t launch_split_chunk(const SplitParams& q, int grid_frames, int grid_clips, bool debug, cudaStream_t stream);
 cudaError_t configure_kernels(int* blocks_per_sm);
-cudaError_t launch_extract(const Params& p, int grid, bool debug, cudaStream_t stream);
+cudaError_t launch_extract(const Params& p, int grid, bool debug, bool umma, cudaStream_t stream);
 cudaError_t launch_order(const int32_t* lengths, int B, int* order, cudaStream_t stream);
 
 // Host pipelines (sfx_extract_host*, sfx_preprocess_host_pcm16): on an early error return the pipeline's streams are drained,

@@ -20,7 +20,9 @@
 namespace sfx {
 
 // ------------------------------------------------------------------------------------------------
-template <bool kDebug>
+// kUmma: the chroma projection of phase 3b on tcgen05 (UMMA, accumulator in tensor memory, operands as bulk-copied
+// shared-memory images) instead of mma.sync: pipeline mode 4, an A/B of the two tensor paths in one library.
+template <bool kDebug, bool kUmma>
 __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_hann = reinterpret_cast<float2*>(smem_raw);
@@ -37,6 +39,8 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     float* s_f = reinterpret_cast<float*>(s_i + 32);                         // [32]
     float* s_lmin = s_f + 32;                                                // [kWarps][32]
     double* s_lm = reinterpret_cast<double*>(s_lmin + kWarps * 32);          // [kWarps][128]
+    unsigned long long* s_ubar = reinterpret_cast<unsigned long long*>(s_lm + kWarps * kMels);   // [8] UMMA build: mbarriers
+    unsigned* s_tmem = reinterpret_cast<unsigned*>(s_ubar + 7);              // tensor-memory base address
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevTables& tb = p.tb;
@@ -56,6 +60,16 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     }
     for (int i = tid; i <= kTunings; i += kThreads) s_edges[i] = tb.edges[i];
     if (tid == 0) mbar_init(s_mbar, 1);
+    UmmaState us;
+    if constexpr (kUmma) {
+        if (tid == 0) {
+            for (int i = 0; i < 7; ++i) mbar_init(s_ubar + i, 1);
+        }
+        if (warp == 0) tmem_alloc(s_tmem, 32);             // 32 FP32 columns x 128 lanes: the chroma accumulator tile
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
     unsigned bank_parity = 0;
     const unsigned mel_mask = tb.mel_mask[lane];
     const int mel_ps = tb.mel_ps;
@@ -98,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     fo.npk = nullptr; fo.gSeg = gRec + static_cast<size_t>(warp) * seg_cap; fo.s_wacc = s_wacc; fo.s_f = s_f;
     fo.s_lm = s_lm + warp * kMels; fo.s_lmin = s_lmin + warp * 32;
     fo.gCent = nullptr; fo.gRoll = nullptr; fo.gLmax = nullptr; fo.gZc = nullptr; fo.gFv = nullptr; fo.cursor = nullptr;
-    const ClipSmem cs{s_ex, s_pool, s_wacc, s_edges, s_mbar, s_hist, s_i, s_f, s_lm, s_lmin};
+    const ClipSmem cs{s_ex, s_pool, s_wacc, s_edges, s_mbar, s_hist, s_i, s_f, s_lm, s_lmin, s_ubar, kUmma ? *s_tmem : 0u};
     const ClipSlice sl{gP16, gL, gRec, gKey, gE, gNy, gInvS, gBin, seg_cap};
 
     for (;;) {
@@ -130,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         const long long fprof_f0 = clock64();
 #endif
         for (int t = warp; t < T; t += kWarps)
-            process_frame<kDebug, kModeFused>(p, tb, fs, fo, x, n, T, t, clip, lane, warp, acc_zc, wcount);
+            process_frame<kDebug, kUmma ? kModeFusedUmma : kModeFused>(p, tb, fs, fo, x, n, T, t, clip, lane, warp, acc_zc, wcount);
 
         // per-warp partials
         {
@@ -146,10 +160,15 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         }
         const long long fprof_t0 = clock64();
 #endif
-        clip_tail<kDebug>(p, tb, cs, sl, clip, T, out, bank_parity, tid, lane, warp);
+        clip_tail<kDebug, kUmma>(p, tb, cs, sl, clip, T, out, bank_parity, tid, lane, warp, &us);
 #ifdef SFX_FUSED_DIAG
         if (tid == 0) atomicAdd(&g_fprof[6], static_cast<unsigned long long>(clock64() - fprof_t0));
 #endif
+    }
+    if constexpr (kUmma) {
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) tmem_dealloc(cs.tmem, 32);
     }
 }
 
@@ -211,22 +230,30 @@ cudaError_t launch_order(const int32_t* lengths, int B, int* order, cudaStream_t
 size_t smem_bytes() {
     return sizeof(float2) * (2560 + 17 * 64) + sizeof(float) * kWarps * kExFloats +
            sizeof(double) * (256 + kWarps * 16 + 104 + 1) + sizeof(int) * (256 + 32) + sizeof(float) * (32 + kWarps * 32) +
-           sizeof(double) * kWarps * kMels;
+           sizeof(double) * kWarps * kMels + sizeof(unsigned long long) * 8;
 }
 
 cudaError_t configure_kernels(int* blocks_per_sm) {
     const int smem = static_cast<int>(smem_bytes());
-    cudaError_t e = cudaFuncSetAttribute(sfx_extract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(sfx_extract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, sfx_extract_kernel<false>, kThreads, smem);
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(sfx_extract_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(sfx_extract_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(sfx_extract_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(sfx_extract_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    // (the occupancy calculator answers 1 for the tcgen05 instantiations although two of their CTAs do share an SM -- 2 x 32
+    //  of the 512 tensor-memory columns, same registers and shared memory; the mma.sync instantiation's answer is used for both)
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, sfx_extract_kernel<false, false>, kThreads, smem);
 }
 
-cudaError_t launch_extract(const Params& p, int grid, bool debug, cudaStream_t stream) {
+cudaError_t launch_extract(const Params& p, int grid, bool debug, bool umma, cudaStream_t stream) {
     const size_t smem = smem_bytes();
-    if (debug) sfx_extract_kernel<true><<<grid, kThreads, smem, stream>>>(p);
-    else       sfx_extract_kernel<false><<<grid, kThreads, smem, stream>>>(p);
+    if (umma) {
+        if (debug) sfx_extract_kernel<true, true><<<grid, kThreads, smem, stream>>>(p);
+        else       sfx_extract_kernel<false, true><<<grid, kThreads, smem, stream>>>(p);
+    } else {
+        if (debug) sfx_extract_kernel<true, false><<<grid, kThreads, smem, stream>>>(p);
+        else       sfx_extract_kernel<false, false><<<grid, kThreads, smem, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 

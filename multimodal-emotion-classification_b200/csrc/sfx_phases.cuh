@@ -53,7 +53,13 @@ struct ClipSmem {
     const double* s_lm;   // fused: [kWarps][128] per-warp float64 sums of the unclamped log-mel rows of the non-zero frames,
     const float* s_lmin;  //        [kWarps][32] per-lane minima of those rows, s_f[16 + w] = all-zero frames seen by warp w
                           //        (nullptr in the split pipeline: phase 3a then always reads the rows back)
+    unsigned long long* s_ubar;   // UMMA build of the fused kernel: 7 mbarriers = full[3], empty[3], accumulator ready
+    unsigned tmem;                //   base address of the CTA's 32 tensor-memory columns
 };
+
+// running state of the UMMA chroma pipeline of one CTA (registers, identical in every thread): operand blocks issued since
+// the kernel started (stage = blocks % 3, mbarrier parity = (blocks / 3) & 1) and accumulator tiles completed
+struct UmmaState { unsigned blocks = 0, tiles = 0; };
 
 struct ClipSlice {
     __half* gP16; float* gL; float4* gRec; unsigned* gKey; float* gE; float* gNy; float* gInvS; unsigned char* gBin;
@@ -66,14 +72,16 @@ struct ClipSlice {
 //   kModeSplit : per-frame values in the clip's slice, record space reserved with one global atomic per frame
 //   kModeStream: per-frame values in the clip's slice (summed in frame order by the tail warp: deterministic whatever
 //                warp ran the frame), peaks appended to the calling warp's own record segment of the clip's slot
-constexpr int kModeFused = 0, kModeSplit = 1, kModeStream = 2;
+constexpr int kModeFused = 0, kModeSplit = 1, kModeStream = 2, kModeFusedUmma = 3;   // 3 = fused, |X|^2 rows stored as tcgen05 operand images
 
 template <bool kDebug, int kMode>
 __device__ __forceinline__ void process_frame(const Params& p, const DevTables& tb, const FrameSmem& fs, const FrameOut& fo,
                                               const float* __restrict__ x, const long long n, const int T, const int t,
                                               const int clip, const int lane, const int warp, int& acc_zc, int& wcount) {
     constexpr bool kSplit = kMode == kModeSplit;          // records through a global atomic per frame
-    constexpr bool kFrameVals = kMode != kModeFused;       // per-frame centroid / roll-off / zero crossings / row max stored
+    constexpr bool kFused = kMode == kModeFused || kMode == kModeFusedUmma;
+    constexpr bool kUmmaRows = kMode == kModeFusedUmma;    // |X|^2 rows go into the shared-memory images of the UMMA A operand
+    constexpr bool kFrameVals = !kFused;                   // per-frame centroid / roll-off / zero crossings / row max stored
     constexpr bool kStream = kMode == kModeStream;         // ... as one record per frame (fo.gFv)
     float re[32], im[32];
     load_frame(x, n, t, lane, fs.aligned8, re, im);
@@ -90,9 +98,16 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             float* Lg = fo.gL + static_cast<size_t>(t) * kMels;
 #pragma unroll
             for (int s4 = 0; s4 < 4; ++s4) Lg[32 * s4 + lane] = lm0;
-            uint4* dst = reinterpret_cast<uint4*>(fo.gP16 + static_cast<size_t>(t) * kP16Stride + 32 * lane);
+            if constexpr (kUmmaRows) {
+                unsigned char* img = reinterpret_cast<unsigned char*>(fo.gP16);
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(0u, 0u, 0u, 0u);
+                for (int q4 = 0; q4 < 4; ++q4)
+                    *reinterpret_cast<uint4*>(img + umma_p16_offset(p.Tmax, t, lane >> 1, (lane & 1) * 4 + q4)) = make_uint4(0u, 0u, 0u, 0u);
+            } else {
+                uint4* dst = reinterpret_cast<uint4*>(fo.gP16 + static_cast<size_t>(t) * kP16Stride + 32 * lane);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(0u, 0u, 0u, 0u);
+            }
             if constexpr (kStream) {
                 if (lane < kFvStride) fo.gFv[static_cast<size_t>(t) * kFvStride + lane] = lane == 5 ? lm0 : 0.0f;
             } else if (lane == 0) {
@@ -121,7 +136,7 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             return;
         }
     }
-    if constexpr (kMode == kModeFused) {
+    if constexpr (kFused) {
         if (lane == 0) fo.s_f[8 + warp] = static_cast<float>(t);       // this warp's last non-zero frame so far (t grows)
     }
     // ---- energy of hop t (samples [512t, 512t+512) = rows 16..23); librosa.feature.rms of frame t is
@@ -321,9 +336,19 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
         pq[1] = accB;
         if (lane == 0) fs.part[32 * fs.mel_ps] = 0.0f;   // zero slot read by filters with < 3 contributing lanes
         {
-            uint4* dst = reinterpret_cast<uint4*>(fo.gP16 + static_cast<size_t>(t) * kP16Stride + 32 * lane);
+            if constexpr (kUmmaRows) {
+                // the row goes straight into the shared-memory images of the tcgen05 A operand (K-major, 128-byte swizzle):
+                // this lane's 32 bins are 4 of the 8 16-byte chunks of K block lane / 2
+                unsigned char* img = reinterpret_cast<unsigned char*>(fo.gP16);
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
+                for (int q4 = 0; q4 < 4; ++q4)
+                    *reinterpret_cast<uint4*>(img + umma_p16_offset(p.Tmax, t, lane >> 1, (lane & 1) * 4 + q4)) =
+                        make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
+            } else {
+                uint4* dst = reinterpret_cast<uint4*>(fo.gP16 + static_cast<size_t>(t) * kP16Stride + 32 * lane);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
+            }
             if constexpr (kStream) {
                 if (lane == 31) fo.gFv[static_cast<size_t>(t) * kFvStride] = fs.Pb[pidx(1024)] * scale;
                 if (lane == 0) fo.gFv[static_cast<size_t>(t) * kFvStride + 1] = __uint_as_float((254u << 23) - sbits);
@@ -391,7 +416,7 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             const float lm = 3.01029995663981195f * __log2f(fmaxf(1e-10f, mel));   // 10*log10(x)
             Lg[32 * s4 + lane] = lm;
             gmax = fmaxf(gmax, lm);
-            if constexpr (kMode == kModeFused) {       // running sums / minimum for the clamp-free MFCC pooling (phase 3a)
+            if constexpr (kFused) {       // running sums / minimum for the clamp-free MFCC pooling (phase 3a)
                 fo.s_lm[32 * s4 + lane] += static_cast<double>(lm);
                 gmin = fminf(gmin, lm);
             }
@@ -400,7 +425,7 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
                     p.dbg.logmel[(static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kMels + 32 * s4 + lane] = lm;
             }
         }
-        if constexpr (kMode == kModeFused) fo.s_lmin[lane] = fminf(fo.s_lmin[lane], gmin);
+        if constexpr (kFused) fo.s_lmin[lane] = fminf(fo.s_lmin[lane], gmin);
         (void)gmin;
         gmax = warp_max(gmax);
         if (lane == 0) {
@@ -550,10 +575,10 @@ static __device__ __noinline__ int peak_bin_exact(float pitch, const double* s_e
 // ------------------------------------------------------------------------------------------------ phases 2-3
 // Expects (set up by the caller, followed by __syncthreads): cs.s_i[20 + w] = peak records in segment w, cs.s_i[17] = cs.s_i[18] = 0, cs.s_i[19] = ~0, cs.s_f[w] = per-warp log-mel
 // max, cs.s_wacc[w*16 + 0/1] = per-warp centroid / roll-off sums, cs.s_i[8+w] = per-warp weighted zero-crossing counts.
-template <bool kDebug>
+template <bool kDebug, bool kUmmaTail = false>
 __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, const ClipSmem& cs, const ClipSlice& sl,
                                           const int clip, const int T, float* __restrict__ out, unsigned& bank_parity,
-                                          const int tid, const int lane, const int warp) {
+                                          const int tid, const int lane, const int warp, UmmaState* us = nullptr) {
 #ifdef SFX_FUSED_DIAG
     long long fprof_t = clock64();
 #endif
@@ -804,9 +829,11 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
     __half* sW = reinterpret_cast<__half*>(cs.s_ex);       // [2][12][kP16Stride]
     fence_proxy_async_smem();                           // generic-proxy accesses of the tiles precede the async write
     __syncthreads();
-    if (tid == 0)
-        bulk_copy_g2s(sW, tb.chroma16 + static_cast<size_t>(tuning_idx) * 2 * kChroma * kP16Stride,
-                      2 * kChroma * kP16Stride * 2, cs.s_mbar);
+    if constexpr (!kUmmaTail) {
+        if (tid == 0)
+            bulk_copy_g2s(sW, tb.chroma16 + static_cast<size_t>(tuning_idx) * 2 * kChroma * kP16Stride,
+                          2 * kChroma * kP16Stride * 2, cs.s_mbar);
+    }
     {
         const float clampv = __fsub_rn(gmx, 80.0f);
         // power_to_db's clamp max(L, gmax - 80) is the identity on every non-zero frame of most clips (it exists for the
@@ -860,9 +887,11 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         }
     }
     FPROF_MARK(3);
-    mbar_wait(cs.s_mbar, bank_parity);                     // chroma bank has landed in shared memory
+    if constexpr (!kUmmaTail) {
+        mbar_wait(cs.s_mbar, bank_parity);                 // chroma bank has landed in shared memory
+        bank_parity ^= 1u;
+    }
     FPROF_MARK(4);
-    bank_parity ^= 1u;
 
     // ===================================== phase 3b: chroma ====================================
     // raw[c][t] = sum_k W[c][k] |X|^2[k][t] on the tensor cores: m16n8k16 FP16 MMAs with FP32 accumulators.  A = bank
@@ -872,14 +901,160 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
     // are added in a fixed order, then each frame is normalised by its max (librosa norm=inf).  The clip's last,
     // incomplete tile is split by steps instead (below).
     {
-        float* part2 = cs.s_ex + (2 * kChroma * kP16Stride) / 2;        // [kChromaTiles][2][96] floats after the bank
         const int g = lane >> 2, t4 = lane & 3;
+        (void)g; (void)t4;
         double csum[kChroma];                                        // per-thread sums over its frames
 #pragma unroll
         for (int c = 0; c < kChroma; ++c) csum[c] = 0.0;
         float wny[kChroma];
 #pragma unroll
         for (int c = 0; c < kChroma; ++c) wny[c] = __ldg(tb.chroma_ny + tuning_idx * kChroma + c);
+      if constexpr (kUmmaTail) {
+        // tcgen05 form: D[128 frames x 32] (+)= A[128 frames x 64 bins] . B[32 x 64 bins]^T per 64-bin K block, FP16 operands,
+        // FP32 accumulator in tensor memory; columns 0..11 = W_hi . |X|^2, 16..27 = 2^11 W_lo . |X|^2.  Phase 1 stored the
+        // rows as the shared-memory images of the A blocks, the host built the B images of every tuning, so an operand block
+        // is ONE contiguous bulk copy (cp.async.bulk, no tensor map) into a 3-stage ring in the warp tiles; thread 0 issues
+        // copies and MMAs (4 x K=16 per block), tcgen05.commit frees a stage / publishes the accumulator, warps 0-3 read
+        // their 32 tensor-memory lanes (one frame per thread) and normalise.
+        float lastnz = cs.s_f[8];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) lastnz = fmaxf(lastnz, cs.s_f[8 + w]);
+        const int Tc = min(T, static_cast<int>(lastnz) + 1);           // frames behind the last non-zero one add exactly 0
+        // stage ring: first 1 KB boundary inside the warp tiles, 3 x (16 KB A | 4 KB B)
+        const unsigned ring = (smem_u32(cs.s_ex) + 1023u) & ~1023u;
+        unsigned char* ring_g = reinterpret_cast<unsigned char*>(cs.s_ex) + (ring - smem_u32(cs.s_ex));
+        constexpr unsigned kStageBytes = 20480u, kIdesc = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+        const unsigned char* bimg = tb.chroma_umma + static_cast<size_t>(tuning_idx) * (16 * 4096);
+        const unsigned char* aimg = reinterpret_cast<const unsigned char*>(sl.gP16);
+        const int natoms = (p.Tmax + 7) >> 3;
+        // full and large partial tiles on the tensor cores; a remainder of fewer than 32 frames (3 s clips: frames 128, 129)
+        // is not worth a 16-block operand stream and goes through the FP32 pipes below
+        const int n_umma = (Tc >> 7) + ((Tc & 127) >= 32 ? 1 : 0);
+        for (int tile = 0; tile < n_umma; ++tile) {
+            const int na_alloc = min(16, natoms - 16 * tile);                        // atoms the tile owns in the scratch image
+            const int na = min(na_alloc, (Tc - 128 * tile + 7) >> 3);                // atoms that hold frames of this clip
+            if (tid == 0) {
+                const unsigned c0 = us->blocks;
+                auto issue_copy = [&](int i) {
+                    const unsigned c = c0 + i, st = c % 3u;
+                    if (c >= 3u) mbar_wait(cs.s_ubar + 3 + st, ((c / 3u) - 1u) & 1u);   // the MMAs that read this stage are done
+                    mbar_expect_tx(cs.s_ubar + st, static_cast<unsigned>(na) * 1024u + 4096u);
+                    bulk_copy_g2s_nx(ring_g + st * kStageBytes, aimg + static_cast<size_t>(tile) * (16 * 16 * 1024) +
+                                     static_cast<size_t>(i) * na_alloc * 1024, static_cast<unsigned>(na) * 1024u, cs.s_ubar + st);
+                    bulk_copy_g2s_nx(ring_g + st * kStageBytes + 16384, bimg + static_cast<size_t>(i) * 4096, 4096u, cs.s_ubar + st);
+                };
+                issue_copy(0);
+                issue_copy(1);
+                issue_copy(2);
+                for (int i = 0; i < 16; ++i) {
+                    const unsigned c = c0 + i, st = c % 3u;
+                    mbar_wait(cs.s_ubar + st, (c / 3u) & 1u);
+                    tc_fence_after();
+                    const unsigned long long ad = umma_desc_sw128(ring + st * kStageBytes);
+                    const unsigned long long bd = umma_desc_sw128(ring + st * kStageBytes + 16384u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(cs.tmem, ad + 2ull * k, bd + 2ull * k, kIdesc, (i | k) != 0 ? 1u : 0u);
+                    umma_commit(cs.s_ubar + 3 + st);
+                    if (i + 3 < 16) issue_copy(i + 3);            // into the stage these MMAs are reading: waits for their commit
+                }
+                umma_commit(cs.s_ubar + 6);
+                mbar_wait(cs.s_ubar + 6, us->tiles & 1u);              // the tile's accumulator is complete (one poller:
+            }                                                          // everybody else sleeps at the barrier below)
+            us->blocks += 16u;
+            us->tiles += 1u;
+            __syncthreads();
+            tc_fence_after();
+            if (warp < 4) {
+                float v[32];
+                tmem_ld32(cs.tmem + (static_cast<unsigned>(warp * 32) << 16), v);
+                const int f = tile * 128 + warp * 32 + lane;
+                if (f < Tc) {
+                    const float pn = sl.gNy[f];                            // scaled Nyquist bin
+                    float raw[kChroma];
+                    float mx = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < kChroma; ++c) {
+                        raw[c] = fmaf(wny[c], pn, fmaf(v[16 + c], 1.0f / 2048.0f, v[c]));
+                        mx = fmaxf(mx, fabsf(raw[c]));
+                    }
+                    // librosa.util.normalize: lengths below tiny(float32) are replaced by 1 (in unscaled units)
+                    const float inv_s = sl.gInvS[f];
+                    const bool small = mx * inv_s < FLT_MIN;
+#pragma unroll
+                    for (int c = 0; c < kChroma; ++c)
+                        csum[c] += static_cast<double>(small ? raw[c] * inv_s : __fdiv_rn(raw[c], mx));
+                }
+            }
+            tc_fence_before();
+            __syncthreads();                                           // every reader is done before the next tile overwrites
+        }
+        // remainder frames on the FP32 pipes: work item = (frame, chroma class, 128-bin slice), one per thread (3 s clips:
+        // 2 frames x 12 x 8 = 192 items), loads batched four 8-bin chunks deep, 8-lane shuffle tree over the slices, the
+        // (frame, class) sums meet in shared memory and one thread per frame normalises
+        {
+            const int f0 = n_umma * 128, nrem = Tc - f0;               // 0 <= nrem < 32
+            const __half* bank = reinterpret_cast<const __half*>(tb.chroma16) + static_cast<size_t>(tuning_idx) * 2 * kChroma * kP16Stride;
+            float* s_rem = reinterpret_cast<float*>(cs.s_pool);        // [nrem][12] (the pooled log-mel vector is consumed)
+            const int nitems = nrem * kChroma * 8;
+            for (int base = 0; base < nitems; base += kThreads) {      // CTA-uniform trip count (shuffles inside)
+                const int item = base + tid;
+                const bool valid = item < nitems;
+                const int part = item & 7, c = (item >> 3) % kChroma, fi = valid ? item / (8 * kChroma) : 0;
+                const int f = f0 + fi;
+                float acc = 0.0f;
+                if (valid) {
+                    const __half* wh = bank + c * kP16Stride + 128 * part;
+                    const __half* wl = bank + (kChroma + c) * kP16Stride + 128 * part;
+#pragma unroll 1
+                    for (int ch0 = 0; ch0 < 16; ch0 += 4) {
+                        uint4 pv[4], hv[4], lv[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int bin0 = 128 * part + 8 * (ch0 + q);
+                            pv[q] = *reinterpret_cast<const uint4*>(aimg + umma_p16_offset(p.Tmax, f, bin0 >> 6, (bin0 >> 3) & 7));
+                            hv[q] = *reinterpret_cast<const uint4*>(wh + 8 * (ch0 + q));
+                            lv[q] = *reinterpret_cast<const uint4*>(wl + 8 * (ch0 + q));
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const __half2* ph = reinterpret_cast<const __half2*>(&pv[q]);
+                            const __half2* hh = reinterpret_cast<const __half2*>(&hv[q]);
+                            const __half2* hl = reinterpret_cast<const __half2*>(&lv[q]);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 x = __half22float2(ph[e]), a = __half22float2(hh[e]), b2 = __half22float2(hl[e]);
+                                acc = fmaf(fmaf(b2.x, 1.0f / 2048.0f, a.x), x.x, acc);
+                                acc = fmaf(fmaf(b2.y, 1.0f / 2048.0f, a.y), x.y, acc);
+                            }
+                        }
+                    }
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                if (valid && part == 0) s_rem[fi * kChroma + c] = acc;
+            }
+            __syncthreads();
+            if (tid < nrem) {
+                const int f = f0 + tid;
+                const float pn = sl.gNy[f];
+                float raw[kChroma];
+                float mx = 0.0f;
+#pragma unroll
+                for (int c = 0; c < kChroma; ++c) {
+                    raw[c] = fmaf(wny[c], pn, s_rem[tid * kChroma + c]);
+                    mx = fmaxf(mx, fabsf(raw[c]));
+                }
+                const float inv_s = sl.gInvS[f];
+                const bool small = mx * inv_s < FLT_MIN;
+#pragma unroll
+                for (int c = 0; c < kChroma; ++c)
+                    csum[c] += static_cast<double>(small ? raw[c] * inv_s : __fdiv_rn(raw[c], mx));
+            }
+            __syncthreads();
+        }
+      } else {
+        float* part2 = cs.s_ex + (2 * kChroma * kP16Stride) / 2;        // [kChromaTiles][2][96] floats after the bank
         // Frames behind the clip's last non-zero frame (the zero tail load_audio pads short clips with) have all-zero
         // |X|^2 rows and add exactly 0 to every chroma sum: the projection stops at Tc = that frame + 1 (cs.s_f[8 + w] =
         // last non-zero frame seen by warp w, -1 if none); the mean below still divides by T.
@@ -1012,6 +1187,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             }
             __syncthreads();
         }
+      }
 #pragma unroll
         for (int c = 0; c < kChroma; ++c) {
             double v = csum[c];

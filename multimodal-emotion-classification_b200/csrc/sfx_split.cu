@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_clips_kernel(const SplitParam
     unsigned bank_parity = 0;
     int* queue = reinterpret_cast<int*>(p.ws);
     const int* npk_all = reinterpret_cast<const int*>(p.ws + kSplitNpkOff);
-    const ClipSmem cs{s_ex, s_pool, s_wacc, s_edges, s_mbar, s_hist, s_i, s_f, nullptr, nullptr};
+    const ClipSmem cs{s_ex, s_pool, s_wacc, s_edges, s_mbar, s_hist, s_i, s_f, nullptr, nullptr, nullptr, 0u};
 
     for (;;) {
         __syncthreads();

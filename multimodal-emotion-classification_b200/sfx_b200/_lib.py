@@ -25,7 +25,7 @@ class TablesHost(C.Structure):
                 ("hann", C.c_void_p), ("tw1", C.c_void_p), ("tw2", C.c_void_p), ("mel_ab", C.c_void_p),
                 ("mel_mask", C.c_void_p), ("mel_src", C.c_void_p),
                 ("chroma16", C.c_void_p), ("chroma_ny", C.c_void_p), ("dct", C.c_void_p), ("edges", C.c_void_p),
-                ("chroma_frag", C.c_void_p)]
+                ("chroma_frag", C.c_void_p), ("chroma_umma", C.c_void_p)]
 
 
 class DebugOut(C.Structure):
@@ -50,7 +50,7 @@ EXPORTS = ["sfx_dnn_create", "sfx_dnn_destroy", "sfx_dnn_workspace_bytes", "sfx_
            "sfx_preprocess_host_pcm16", "sfx_frontend_last_error", "sfx_frontend_release", "sfx_release",
            "sfx_workspace_bytes_batch"]
 BENCH_EXPORTS = ["sfx_measure_fp32_peak"]          # include/sfx_bench.h -> libsfx_bench.so (bench.py / tests only)
-PIPELINES = {"auto": 0, "fused": 1, "split": 2, "stream": 3}
+PIPELINES = {"auto": 0, "fused": 1, "split": 2, "stream": 3, "fused_umma": 4}
 ERR_BAD_CLIP = -5
 
 
@@ -112,7 +112,7 @@ def load():
     lib.sfx_dnn_forward.restype = C.c_int
     lib.sfx_dnn_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                     C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
-    if lib.sfx_abi_version() != 2:
+    if lib.sfx_abi_version() != 3:
         raise RuntimeError("libsfx_b200.so ABI version mismatch; rebuild with sfx_b200.build.build(force=True)")
     _LIB = lib
     return lib
@@ -143,7 +143,7 @@ def check(rc: int):
 def make_tables_struct(tb: dict):
     """TablesHost pointing into the numpy arrays of tables.build_tables (keeps them alive via .keep)."""
     keep = {k: np.ascontiguousarray(tb[k]) for k in
-            ("hann", "tw1", "tw2", "mel_ab", "mel_mask", "mel_src", "chroma16", "chroma_ny", "dct", "edges", "chroma_frag")}
+            ("hann", "tw1", "tw2", "mel_ab", "mel_mask", "mel_src", "chroma16", "chroma_ny", "dct", "edges", "chroma_frag", "chroma_umma")}
     assert keep["chroma_frag"].dtype == np.uint32
     assert keep["hann"].dtype == np.float32 and keep["chroma16"].dtype == np.float16 and keep["chroma_ny"].dtype == np.float32
     assert keep["dct"].dtype == np.float64 and keep["edges"].dtype == np.float64

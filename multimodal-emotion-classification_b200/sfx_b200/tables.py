@@ -114,6 +114,24 @@ def chroma_fragments(c_hi: np.ndarray, c_lo: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(u.reshape(nt, 32, 2, 2, 32, 4))
 
 
+def chroma_umma_images(c_hi: np.ndarray, c_lo: np.ndarray) -> np.ndarray:
+    """B operand of the tcgen05 chroma projection (csrc: SFX_CHROMA_UMMA), one shared-memory image per (tuning, 64-bin K block):
+    32 rows (0..11 = hi of chroma class c, 16..27 = 2^11 * lo, the rest zero) x 64 FP16 bins, K-major with the 128-byte swizzle
+    the UMMA shared-memory descriptor expects (8-row x 128-byte atoms, 16-byte chunk index XOR row-in-atom), so that one bulk
+    copy of 4 096 contiguous bytes lands it ready to use.  uint8 [T][16][4096]."""
+    nt = c_hi.shape[0]
+    rows = np.zeros((nt, 32, 1024), dtype=np.uint16)
+    rows[:, :N_CHROMA] = np.ascontiguousarray(c_hi[:, :, :1024]).view(np.uint16)
+    rows[:, 16:16 + N_CHROMA] = np.ascontiguousarray(c_lo[:, :, :1024]).view(np.uint16)
+    blk = rows.reshape(nt, 32, 16, 8, 8)                       # [tun, n, kb, chunk, half-in-chunk]
+    n = np.arange(32)
+    out = np.zeros((nt, 16, 4, 8, 8, 8), dtype=np.uint16)      # [tun, kb, atom, row-in-atom, chunk position, half]
+    for c in range(8):
+        pos = c ^ (n & 7)
+        out[:, :, n >> 3, n & 7, pos, :] = blk[:, :, :, c, :].transpose(0, 2, 1, 3)
+    return np.ascontiguousarray(out).view(np.uint8).reshape(nt, 16, 4096)
+
+
 def tuning_edges() -> np.ndarray:
     return np.linspace(-0.5, 0.5, N_TUNINGS + 1)
 
@@ -244,6 +262,7 @@ def build_tables(sr: int = 22050) -> dict:
     chroma16 = np.ascontiguousarray(np.stack([c_hi, c_lo], axis=1))          # [100][2][12][1056] float16
     chroma_ny = np.ascontiguousarray(chroma[:, :, N_BINS - 1])               # [100][12] float32 (Nyquist bin)
     chroma_frag = chroma_fragments(c_hi, c_lo)                               # [100][32][2][2][32][4] uint32
+    chroma_umma = chroma_umma_images(c_hi, c_lo)                             # [100][16][4096] uint8
     return dict(**chunk, sr=sr, hann=hann, tw1=np.ascontiguousarray(tw1), tw2=np.ascontiguousarray(tw2),
                 mel_dense=mb, melw=melw, mel_lo=mel_lo, mel_off=mel_off, mel_len=mel_len,
-                chroma16=chroma16, chroma_ny=chroma_ny, chroma_frag=chroma_frag, chroma_f32=chroma, dct=dct_matrix(), edges=edges, pip_kmin=kmin, pip_kmax=kmax)
+                chroma16=chroma16, chroma_ny=chroma_ny, chroma_frag=chroma_frag, chroma_umma=chroma_umma, chroma_f32=chroma, dct=dct_matrix(), edges=edges, pip_kmin=kmin, pip_kmax=kmax)

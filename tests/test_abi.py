@@ -38,7 +38,7 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_abi_version_and_argument_validation():
     lib = _lib.load()
-    assert lib.sfx_abi_version() == 2
+    assert lib.sfx_abi_version() == 3
     assert lib.sfx_launches_per_extract() == 1
     # argument validation happens before any CUDA work
     rc = lib.sfx_extract(99, 22050, None, 0, None, 0, 0, 1, 40, None, 56, None, 0, None)
@@ -47,8 +47,8 @@ def test_abi_version_and_argument_validation():
     assert rc == -1
     assert lib.sfx_workspace_bytes(0, 66150) == 0 or torch.cuda.is_available()
     assert lib.sfx_workspace_bytes_batch(0, 66150, 1) == 0 or torch.cuda.is_available()
-    assert lib.sfx_set_pipeline(4) == -1 and lib.sfx_set_pipeline(-1) == -1
-    for mode in (3, 2, 1, 0):
+    assert lib.sfx_set_pipeline(5) == -1 and lib.sfx_set_pipeline(-1) == -1
+    for mode in (4, 3, 2, 1, 0):
         assert lib.sfx_set_pipeline(mode) == 0
 
 

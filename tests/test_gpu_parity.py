@@ -230,7 +230,7 @@ def test_host_path_reports_non_finite_clips(ex):
     assert rc == -5 and not out2.any()
 
 
-@pytest.mark.parametrize("mode", ["fused", "stream", "split"])
+@pytest.mark.parametrize("mode", ["fused", "fused_umma", "stream", "split"])
 def test_every_pipeline_against_the_oracle(ex, mode):
     """All three schedules of the one arithmetic, forced, on a uniform and a ragged batch (incl. invalid lengths)."""
     w = synth.make_batch(40, N3S, seed=74)
@@ -251,6 +251,31 @@ def test_every_pipeline_against_the_oracle(ex, mode):
         assert_parity(gr[good[:10]], refr)
     finally:
         ex.set_pipeline("auto")
+
+
+def test_tcgen05_chroma_agrees_with_mma_sync_on_a_large_batch(ex):
+    """Mode 4 = the fused kernel with phase 3b on tcgen05 (UMMA, accumulator in tensor memory, operands bulk-copied as
+    shared-memory images, remainder frames on the FP32 pipes): everything but chroma bit for bit, chroma to 2e-6; zero-tail
+    clips (partial tiles), all-zero clips (no tile at all) and clips of 1 .. 300 frames included."""
+    w = synth.make_batch(1200, N3S, seed=77)
+    w[5] = 0.0
+    wd = dev(w)
+    wr, lens = synth.make_ragged(400, 300, 153600, seed=78)
+    lens[:8] = [1, 511, 512, 4096 * 16 - 1, 65536, 65536 + 511, 153600, 16384]
+    wrd, ld = dev(wr), dev(lens)
+    try:
+        ex.set_pipeline("fused")
+        a, ar = ex.extract(wd), ex.extract(wrd, ld)
+        ex.set_pipeline("fused_umma")
+        b, br = ex.extract(wd), ex.extract(wrd, ld)
+        b2 = ex.extract(wd)
+    finally:
+        ex.set_pipeline("auto")
+    assert torch.equal(b, b2)
+    for x, y in ((a, b), (ar, br)):
+        assert torch.equal(x[:, :40], y[:, :40]) and torch.equal(x[:, 52:], y[:, 52:])
+        assert float((x[:, 40:52] - y[:, 40:52]).abs().max()) < 2e-6
+    assert_parity(br[:12].cpu().numpy(), lp.features_batch(wr[:12], lens[:12]))
 
 
 def test_stream_pipeline_agrees_with_fused_on_a_large_batch(ex):

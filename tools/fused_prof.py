@@ -17,7 +17,7 @@ dev = torch.device("cuda", 0)
 ex = get_extractor(dev)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 pool = bench.synth_pool(B, 66150, seed=7, device=dev)
-ex.set_pipeline("fused")
+ex.set_pipeline(os.environ.get("SFX_PROF_MODE", "fused"))
 buf = np.zeros(8, dtype=np.uint64)
 names = ["frames", "per-peak", "select+hist", "mfcc", "bank wait", "chroma", "tail total", "clips"]
 for kind, w in [("mix", pool)] + [(bench.KINDS[k], pool[k::4].contiguous()) for k in range(4)]:
