@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     double* s_lm = reinterpret_cast<double*>(s_lmin + kWarps * 32);          // [kWarps][128]
     unsigned long long* s_ubar = reinterpret_cast<unsigned long long*>(s_lm + kWarps * kMels);   // [8] UMMA build: mbarriers
     unsigned* s_tmem = reinterpret_cast<unsigned*>(s_ubar + 7);              // tensor-memory base address
+    int* s_msrc = reinterpret_cast<int*>(s_ubar + 8);                        // [128] partial-sum slot words of the mel filters
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevTables& tb = p.tb;
@@ -73,11 +74,11 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     unsigned bank_parity = 0;
     const unsigned mel_mask = tb.mel_mask[lane];
     const int mel_ps = tb.mel_ps;
-    int msrc[4];                                   // 3 x 10-bit partial-sum slots per filter 32*s + lane
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const int* q = tb.mel_src + (32 * s + lane) * 3;
-        msrc[s] = q[0] | (q[1] << 10) | (q[2] << 20);
+    // 3 x 10-bit partial-sum slots per mel filter, read from shared memory once per frame (kept in registers they were
+    // spilled: the frame loop has none to spare)
+    for (int m = tid; m < kMels; m += kThreads) {
+        const int* q = tb.mel_src + m * 3;
+        s_msrc[m] = q[0] | (q[1] << 10) | (q[2] << 20);
     }
 
     // scratch of this CTA: its rows inside the two blocks that hold every CTA's FP16 |X|^2 / log-mel rows (the L2-pinned
@@ -103,8 +104,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     fs.ex = reinterpret_cast<float2*>(fs.Pb);
     fs.part = fs.Pb + kPartOff;                        // mel partial sums [32][mel_ps] + zero slot
     fs.mel_mask = mel_mask; fs.mel_ps = mel_ps;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) fs.msrc[s] = msrc[s];
+    fs.s_msrc = s_msrc;
     fs.bin_hz = static_cast<float>(static_cast<double>(tb.sr) / kNfft);
     fs.aligned8 = p.aligned8 != 0;
     FrameOut fo;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
 extern "C" int sfx_fused_prof(unsigned long long* out, int reset) {
     int rc = static_cast<int>(cudaMemcpyFromSymbol(out, g_fprof, sizeof(g_fprof)));
     if (reset) {
-        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long z[16] = {};
         rc |= static_cast<int>(cudaMemcpyToSymbol(g_fprof, z, sizeof(z)));
     }
     return rc;
@@ -230,7 +230,7 @@ cudaError_t launch_order(const int32_t* lengths, int B, int* order, cudaStream_t
 size_t smem_bytes() {
     return sizeof(float2) * (2560 + 17 * 64) + sizeof(float) * kWarps * kExFloats +
            sizeof(double) * (256 + kWarps * 16 + 104 + 1) + sizeof(int) * (256 + 32) + sizeof(float) * (32 + kWarps * 32) +
-           sizeof(double) * kWarps * kMels + sizeof(unsigned long long) * 8;
+           sizeof(double) * kWarps * kMels + sizeof(unsigned long long) * 8 + sizeof(int) * kMels;
 }
 
 cudaError_t configure_kernels(int* blocks_per_sm) {

@@ -15,7 +15,7 @@ namespace sfx {
 // the cycles between phase boundaries to g_fprof[phase]; 0 frames, 1 per-peak loop, 2 median select + histogram, 3 MFCC,
 // 4 wait for the bank, 5 chroma, 6 epilogue, 7 clips
 #ifdef SFX_FUSED_DIAG
-__device__ unsigned long long g_fprof[8];
+__device__ unsigned long long g_fprof[16];   // 8..10 = finer marks inside phase 2 (before / after the radix select, upper median)
 #define FPROF_MARK(k) do { if (threadIdx.x == 0) { const long long fp1 = clock64(); atomicAdd(&g_fprof[k], static_cast<unsigned long long>(fp1 - fprof_t)); fprof_t = fp1; } } while (0)
 #else
 #define FPROF_MARK(k) do { } while (0)
@@ -28,6 +28,7 @@ struct FrameSmem {
     float2* ex;           // the same tile as float2
     float* part;          // mel partial sums inside the tile
     unsigned mel_mask; int mel_ps; int msrc[4];
+    const int* s_msrc;    // fused kernel: the msrc words of all 128 filters in shared memory (read per frame; msrc[] unused)
     float bin_hz; bool aligned8;
 };
 
@@ -409,15 +410,34 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
     {
         float* Lg = fo.gL + static_cast<size_t>(t) * kMels;
         float gmax = -FLT_MAX, gmin = FLT_MAX;
+        // every load of the section is issued before its first store (the compiler cannot tell that the running sums and
+        // the partial-sum slots do not overlap, and would otherwise chain each band's loads behind the previous band's
+        // store): slot words, partial sums, then the running float64 sums
+        int ms4[4];
+        float pa[4], pb[4], pc[4];
+        double lsum[4];
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4) {
-            const int ms = fs.msrc[s4];
-            const float mel = (fs.part[ms & 1023] + fs.part[(ms >> 10) & 1023]) + fs.part[ms >> 20];
+            if constexpr (kFused) ms4[s4] = fs.s_msrc[32 * s4 + lane];
+            else ms4[s4] = fs.msrc[s4];
+        }
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            pa[s4] = fs.part[ms4[s4] & 1023];
+            pb[s4] = fs.part[(ms4[s4] >> 10) & 1023];
+            pc[s4] = fs.part[ms4[s4] >> 20];
+            if constexpr (kFused) lsum[s4] = fo.s_lm[32 * s4 + lane];
+        }
+        float lmin_old = 0.0f;
+        if constexpr (kFused) lmin_old = fo.s_lmin[lane];
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            const float mel = (pa[s4] + pb[s4]) + pc[s4];
             const float lm = 3.01029995663981195f * __log2f(fmaxf(1e-10f, mel));   // 10*log10(x)
             Lg[32 * s4 + lane] = lm;
             gmax = fmaxf(gmax, lm);
             if constexpr (kFused) {       // running sums / minimum for the clamp-free MFCC pooling (phase 3a)
-                fo.s_lm[32 * s4 + lane] += static_cast<double>(lm);
+                fo.s_lm[32 * s4 + lane] = lsum[s4] + static_cast<double>(lm);
                 gmin = fminf(gmin, lm);
             }
             if (kDebug) {
@@ -425,8 +445,8 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
                     p.dbg.logmel[(static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kMels + 32 * s4 + lane] = lm;
             }
         }
-        if constexpr (kFused) fo.s_lmin[lane] = fminf(fo.s_lmin[lane], gmin);
-        (void)gmin;
+        if constexpr (kFused) fo.s_lmin[lane] = fminf(lmin_old, gmin);
+        (void)gmin; (void)lsum; (void)lmin_old;
         gmax = warp_max(gmax);
         if (lane == 0) {
             if constexpr (kStream) fo.gFv[static_cast<size_t>(t) * kFvStride + 5] = gmax;
@@ -745,11 +765,13 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             if (diff) atomicAdd(&cs.s_i[16], diff);
         }
         __syncthreads();
+        FPROF_MARK(8);
         int cle = 0;
         const int r0 = (np - 1) >> 1;
         const unsigned ka = radix_select(keys, np, r0, cs.s_hist, cs.s_i + 4, cle, static_cast<unsigned>(cs.s_i[18]),
                                          static_cast<unsigned>(cs.s_i[19]));
         unsigned kb = ka;
+        FPROF_MARK(9);
         if ((np & 1) == 0 && cle <= (np >> 1)) {
             // upper median = smallest key above ka
             if (tid == 0) cs.s_i[4] = static_cast<int>(0xffffffffu);
@@ -768,6 +790,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             kb = static_cast<unsigned>(cs.s_i[4]);
             __syncthreads();
         }
+        FPROF_MARK(10);
         const float fa = fkey_inv(ka), fb = fkey_inv(kb);
         thr = ((np & 1) == 0) ? __fmul_rn(__fadd_rn(fa, fb), 0.5f) : fa;
         const unsigned kthr = fkey(thr);

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_frames_kernel(const SplitPara
     fs.mel_mask = mel_mask; fs.mel_ps = mel_ps;
 #pragma unroll
     for (int s = 0; s < 4; ++s) fs.msrc[s] = msrc[s];
+    fs.s_msrc = nullptr;
     fs.bin_hz = static_cast<float>(static_cast<double>(tb.sr) / kNfft);
     fs.aligned8 = p.aligned8 != 0;
 

@@ -741,6 +741,7 @@ __global__ void __launch_bounds__(kSThreads, 1) sfx_stream_kernel(const __grid_c
         const int* q = tb.mel_src + (32 * s + lane) * 3;
         fs.msrc[s] = q[0] | (q[1] << 10) | (q[2] << 20);
     }
+    fs.s_msrc = nullptr;
     fs.bin_hz = static_cast<float>(static_cast<double>(tb.sr) / kNfft);
     fs.aligned8 = p.aligned8 != 0;
 

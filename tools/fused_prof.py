@@ -18,7 +18,7 @@ ex = get_extractor(dev)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 pool = bench.synth_pool(B, 66150, seed=7, device=dev)
 ex.set_pipeline(os.environ.get("SFX_PROF_MODE", "fused"))
-buf = np.zeros(8, dtype=np.uint64)
+buf = np.zeros(16, dtype=np.uint64)
 names = ["frames", "per-peak", "select+hist", "mfcc", "bank wait", "chroma", "tail total", "clips"]
 for kind, w in [("mix", pool)] + [(bench.KINDS[k], pool[k::4].contiguous()) for k in range(4)]:
     out = torch.empty((w.shape[0], 56), device=dev)
@@ -33,5 +33,7 @@ for kind, w in [("mix", pool)] + [(bench.KINDS[k], pool[k::4].contiguous()) for 
     ex.lib.sfx_fused_prof(buf.ctypes.data_as(ctypes.c_void_p), 1)
     n = float(buf[7])
     print(f"{kind}: {w.shape[0] / e0.elapsed_time(e1) / 1e3:.3f} M clips/s; cycles per clip per CTA: " +
-          ", ".join(f"{nm} {float(buf[i]) / n:.0f}" for i, nm in enumerate(names[:7])), flush=True)
+          ", ".join(f"{nm} {float(buf[i]) / n:.0f}" for i, nm in enumerate(names[:7])) +
+          f"; inside select+hist: redo {float(buf[8]) / n:.0f}, radix select {float(buf[9]) / n:.0f}, upper median "
+          f"{float(buf[10]) / n:.0f}, (select+hist above = histogram + argmax only)", flush=True)
 ex.set_pipeline("auto")
