@@ -72,6 +72,25 @@ __device__ __forceinline__ c64 rot_mi(c64 v) { float a, b; upk(v, a, b); return 
 __device__ __forceinline__ c64 rot_pi(c64 v) { float a, b; upk(v, a, b); return pk(-b, a); }   // +i * v
 __device__ __forceinline__ c64 bc2(float c) { return pk(c, c); }                                // (c, c)
 __device__ __forceinline__ c64 neg2(c64 v) { float a, b; upk(v, a, b); return pk(-a, -b); }
+// Hann phases of a lane's two samples of a row, (cos, cos', sin, sin')(pi (2 lane + e) / 1024), e = 0, 1: the 512-byte table
+// process_frame builds the window from (threads 0..31 of the CTA fill it; s_hann is 16-byte aligned)
+__device__ __forceinline__ void fill_hann_phases(float2* s_hann, int tid) {
+    if (tid < 32) {
+        float s0, c0, s1, c1;
+        sincospif(static_cast<float>(2 * tid) * (1.0f / 1024.0f), &s0, &c0);
+        sincospif(static_cast<float>(2 * tid + 1) * (1.0f / 1024.0f), &s1, &c1);
+        reinterpret_cast<float4*>(s_hann)[tid] = make_float4(c0, c1, s0, s1);
+    }
+}
+// cos / sin of r * 2 pi / 32, r = 0..15 (the row phase of the Hann window, see process_frame)
+__device__ constexpr float kCos32[16] = {1.0f, 0.9807852804032304f, 0.9238795325112867f, 0.8314696123025452f, 0.7071067811865476f,
+                                         0.5555702330196023f, 0.38268343236508984f, 0.19509032201612833f, 0.0f,
+                                         -0.1950903220161282f, -0.3826834323650897f, -0.555570233019602f, -0.7071067811865475f,
+                                         -0.8314696123025453f, -0.9238795325112867f, -0.9807852804032304f};
+__device__ constexpr float kSin32[16] = {0.0f, 0.19509032201612825f, 0.3826834323650898f, 0.5555702330196022f, 0.7071067811865475f,
+                                         0.8314696123025452f, 0.9238795325112867f, 0.9807852804032304f, 1.0f,
+                                         0.9807852804032304f, 0.9238795325112867f, 0.8314696123025455f, 0.7071067811865476f,
+                                         0.5555702330196022f, 0.3826834323650899f, 0.1950903220161286f};
 __device__ __forceinline__ c64 conj2(c64 v) { float a, b; upk(v, a, b); return pk(a, -b); }
 // v * w for complex v and w = (wr, wi): wr * v + wi * (i v)
 __device__ __forceinline__ c64 cmul(c64 v, float wr, float wi) { return fma2(rot_pi(v), bc2(wi), mul2(v, bc2(wr))); }

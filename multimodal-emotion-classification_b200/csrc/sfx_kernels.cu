@@ -26,7 +26,7 @@ template <bool kDebug, bool kUmma>
 __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_hann = reinterpret_cast<float2*>(smem_raw);
-    float2* s_tw1 = s_hann + 1024;
+    float2* s_tw1 = s_hann + 64;                                             // (s_hann: 32 lanes x (cos, cos', sin, sin'))
     float2* s_tw2 = s_tw1 + 1024;
     float2* s_melab = s_tw2 + 512;                                           // [33*32]  (tw2: rows k2 < 16 only)
     float* s_ex = reinterpret_cast<float*>(s_melab + 17 * 64);               // [kWarps][kExFloats]
@@ -51,7 +51,6 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     for (int i = tid; i < 1024; i += kThreads) {
         const int r = i >> 5, l = i & 31;
         const int d = (r >> 1) * 64 + 2 * l + (r & 1);
-        s_hann[(r & 15) * 64 + 2 * l + (r >> 4)] = tb.hann[i];        // rows r, r + 16 side by side
         s_tw1[d] = tb.tw1[i];
         if (i < 512) s_tw2[d] = tb.tw2[i];
     }
@@ -59,6 +58,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         const int r = i >> 5, l = i & 31;
         s_melab[(r >> 1) * 64 + 2 * l + (r & 1)] = tb.mel_ab[i];      // row 32 (Nyquist) lands at 16*64 + 2*lane
     }
+    fill_hann_phases(s_hann, tid);
     for (int i = tid; i <= kTunings; i += kThreads) s_edges[i] = tb.edges[i];
     if (tid == 0) mbar_init(s_mbar, 1);
     UmmaState us;
@@ -228,7 +228,7 @@ cudaError_t launch_order(const int32_t* lengths, int B, int* order, cudaStream_t
 }
 
 size_t smem_bytes() {
-    return sizeof(float2) * (2560 + 17 * 64) + sizeof(float) * kWarps * kExFloats +
+    return sizeof(float2) * (64 + 1536 + 17 * 64) + sizeof(float) * kWarps * kExFloats +
            sizeof(double) * (256 + kWarps * 16 + 104 + 1) + sizeof(int) * (256 + 32) + sizeof(float) * (32 + kWarps * 32) +
            sizeof(double) * kWarps * kMels + sizeof(unsigned long long) * 8 + sizeof(int) * kMels;
 }

@@ -23,7 +23,8 @@ __device__ unsigned long long g_fprof[16];   // 8..10 = finer marks inside phase
 
 // shared-memory tables and the calling warp's tile (phase 1)
 struct FrameSmem {
-    const float2* s_hann; const float2* s_tw1; const float2* s_tw2; const float2* s_melab;
+    const float2* s_hann;    // 32 x (cos, cos', sin, sin'): the Hann phases of a lane's two samples per row (fill_hann_phases)
+    const float2* s_tw1; const float2* s_tw2; const float2* s_melab;
     float* Pb;            // this warp's exchange / |X|^2 tile [kExFloats]
     float2* ex;           // the same tile as float2
     float* part;          // mel partial sums inside the tile
@@ -190,14 +191,24 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
     //      radix-32 pass over m1.  From here on each complex sample z[m1] = (x[2n], x[2n+1]), n = lane + 32 m1, is one
     //      packed register pair; the window table holds rows r and r + 16 of a lane side by side.
     c64 z[32];
-    sfor<16>([&](auto R) {
-        constexpr int r = decltype(R)::value;
-        const ulonglong2 h = *reinterpret_cast<const ulonglong2*>(fs.s_hann + r * 64 + 2 * lane);
-        const c64 za = mul2(pk(re[r], im[r]), h.x);
-        const c64 xb = pk(re[r + 16], im[r + 16]);
-        z[r] = fma2(xb, h.y, za);
-        z[r + 16] = fma2(xb, neg2(h.y), za);
-    });
+    {
+        // No window table: sample n = 64 r + 2 lane + e of the frame has phase theta(lane, e) + r * 2 pi / 32, so
+        //   w[n] = 0.5 - 0.5 cos(theta + r phi) = 0.5 - (0.5 cos r phi) cos theta + (0.5 sin r phi) sin theta
+        // is two packed FMAs on the lane's (cos theta, sin theta) pairs (one 128-bit load per frame) with immediate row
+        // constants, and row r + 16 is half a turn further: w[n + 1024] = 1 - w[n].  Saves the 64 shared-memory wavefronts
+        // per frame of an 8 KB table on the kernel's busiest pipe; values within 1 ulp(0.5) of the rounded exact ones.
+        const float4 cs4 = reinterpret_cast<const float4*>(fs.s_hann)[lane];
+        const c64 C = pk(cs4.x, cs4.y), S = pk(cs4.z, cs4.w);
+        sfor<16>([&](auto R) {
+            constexpr int r = decltype(R)::value;
+            const c64 w = fma2(C, bc2(-0.5f * kCos32[r]), fma2(S, bc2(0.5f * kSin32[r]), bc2(0.5f)));
+            const c64 w16 = sub2(bc2(1.0f), w);
+            const c64 za = mul2(pk(re[r], im[r]), w);
+            const c64 xb = pk(re[r + 16], im[r + 16]);
+            z[r] = fma2(xb, w16, za);
+            z[r + 16] = fma2(xb, neg2(w16), za);
+        });
+    }
     // ---- 1024-pt complex FFT: radix-32 over m1, twiddle, transpose, radix-32 over m2
     fft32p<2>(z);
     // exchange tile: float4 slot (k1/2)*33 + lane holds rows k1, k1+1 of column `lane`
@@ -494,26 +505,35 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             __syncwarp();
         }
     } else if constexpr (!kSplit) {
-        // one pass: a row of 32 bins is tested and its peaks are appended (ballot-compacted) to this warp's own record
-        // segment of the clip, whose fill level `wcount` the warp carries in a register -- no atomics, no second pass
+        // one pass over groups of 128 bins: a lane takes four consecutive bins with one 128-bit load (conflict-free in the
+        // padded tile), their outer neighbours come from the adjacent lanes by shuffle (the group's two edge bins by one
+        // extra load), so a bin costs a third of the shared-memory wavefronts of three shifted row reads.  The peaks of
+        // each of the four bin positions are appended (ballot-compacted) to this warp's own record segment of the clip,
+        // whose fill level `wcount` the warp carries in a register -- no atomics, no second pass.  (The order of a frame's
+        // records differs from bin order; median and histogram do not depend on it.)
         const float ref = __fmul_rn(0.1f, pmax);
-        const int kfirst = tb.kmin + lane;
-        const float* q0 = fs.Pb + pidx(kfirst - 1);
-        const float* q1 = fs.Pb + pidx(kfirst);
-        const float* q2 = fs.Pb + pidx(kfirst + 1);
-        const int nrows = (tb.kmax - tb.kmin + 32) >> 5;          // <= 31 (bins 1..1023, 32 per row)
-        const int rmax = (tb.kmax - kfirst) >> 5;                 // this lane's last row inside the range (-1: none)
         const unsigned lt = (1u << lane) - 1u;
         unsigned cnt = static_cast<unsigned>(wcount);
-#pragma unroll 4
-        for (int r = 0; r < nrows; ++r) {
-            const int off = kPRow * r;
-            const float pm = q0[off], pc = q1[off], pp = q2[off];
-            const bool pk = (r <= rmax) & (pc > ref) & (pc > pm) & (pc >= pp);
-            const unsigned bal = __ballot_sync(0xffffffffu, pk);
-            if (bal) {                                               // warp-uniform: most rows of a tonal frame hold no peak
-                st_record_if(pk, fo.gSeg, cnt + __popc(bal & lt), pm, pc, pp, kfirst + 32 * r);
-                cnt += __popc(bal);
+        const int kmin = tb.kmin, kmax = tb.kmax;
+        for (int gq = kmin >> 7; gq <= (kmax >> 7); ++gq) {
+            const int b0 = 128 * gq + 4 * lane;
+            const float4 v = *reinterpret_cast<const float4*>(fs.Pb + pidx(b0));
+            float edge = 0.0f;
+            if ((lane == 0 && gq > 0) || lane == 31) edge = fs.Pb[pidx(lane == 0 ? 128 * gq - 1 : 128 * gq + 128)];
+            float vl = __shfl_up_sync(0xffffffffu, v.w, 1), vr = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (lane == 0) vl = edge;
+            if (lane == 31) vr = edge;
+            const float w[6] = {vl, v.x, v.y, v.z, v.w, vr};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float pm = w[i], pc = w[i + 1], pp = w[i + 2];
+                const int k = b0 + i;
+                const bool pk = (k >= kmin) & (k <= kmax) & (pc > ref) & (pc > pm) & (pc >= pp);
+                const unsigned bal = __ballot_sync(0xffffffffu, pk);
+                if (bal) {                                           // warp-uniform: most of a tonal frame holds no peak
+                    st_record_if(pk, fo.gSeg, cnt + __popc(bal & lt), pm, pc, pp, k);
+                    cnt += __popc(bal);
+                }
             }
         }
         wcount = static_cast<int>(cnt);
@@ -1085,51 +1105,64 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
 #pragma unroll
         for (int w = 1; w < kWarps; ++w) lastnz = fmaxf(lastnz, cs.s_f[8 + w]);
         const int Tc = min(T, static_cast<int>(lastnz) + 1);
-        // full 8-frame tiles: unit = tile x K-half, dealt round-robin to the warps (16 tiles = 4 units per warp)
+        // full 8-frame tiles, 16 per pass (= 16 units, 2 per warp)
         const int nfull = Tc >> 3, rem = Tc & 7;
         for (int tile0 = 0; tile0 < nfull; tile0 += kChromaTiles) {
             const int nt = min(kChromaTiles, nfull - tile0);
-            for (int u = warp; u < 2 * nt; u += kWarps) {
-                const int tl = u >> 1, kh = u & 1;
-                const int f = (tile0 + tl) * 8 + g;
-                constexpr bool valid = true;
-                const __half* prow = sl.gP16 + static_cast<size_t>(f) * kP16Stride + kh * 512 + 8 * t4;
+            // unit = pair of tiles x K-half: every bank fragment read from shared memory feeds the MMAs of two tiles (16
+            // frames), which halves the bank's shared-memory traffic (it was 64 wavefronts per frame, a tenth of the kernel's)
+            const int npair = (nt + 1) >> 1;
+            for (int u = warp; u < 2 * npair; u += kWarps) {
+                const int pr = u >> 1, kh = u & 1;
+                const bool vB = 2 * pr + 1 < nt;                      // an odd tile count leaves the last pair half empty
+                const int fA = (tile0 + 2 * pr) * 8 + g, fB = fA + (vB ? 8 : 0);
+                const __half* prowA = sl.gP16 + static_cast<size_t>(fA) * kP16Stride + kh * 512 + 8 * t4;
+                const __half* prowB = sl.gP16 + static_cast<size_t>(fB) * kP16Stride + kh * 512 + 8 * t4;
                 const int r1 = (g < 4) ? g + 8 : g;                  // bank rows 12..15 do not exist
                 const __half* whi0 = sW + g * kP16Stride + kh * 512 + 8 * t4;
                 const __half* whi1 = sW + r1 * kP16Stride + kh * 512 + 8 * t4;
                 const __half* wlo0 = whi0 + kChroma * kP16Stride;
                 const __half* wlo1 = whi1 + kChroma * kP16Stride;
-                // two accumulator sets per bank half (even / odd steps) so that four MMA chains are in flight; lanes
+                // one accumulator set per tile and bank half: four MMA chains in flight; lanes
                 // g >= 4 feed bank row g again as the non-existent rows 12..15, whose D rows are never read
-                float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f};
-                float acc2[4] = {0.f, 0.f, 0.f, 0.f}, acl2[4] = {0.f, 0.f, 0.f, 0.f};
+                float acc[2][4] = {}, acl[2][4] = {};
 #pragma unroll 1
-                for (int kb0 = 0; kb0 < 16; kb0 += 8) {
-                    uint4 pv[8];
+                for (int kb0 = 0; kb0 < 16; kb0 += 4) {
+                    uint4 pa[4], pb[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        pv[i] = valid ? *reinterpret_cast<const uint4*>(prow + (kb0 + i) * 32) : make_uint4(0u, 0u, 0u, 0u);
+                    for (int i = 0; i < 4; ++i) {
+                        pa[i] = *reinterpret_cast<const uint4*>(prowA + (kb0 + i) * 32);
+                        pb[i] = *reinterpret_cast<const uint4*>(prowB + (kb0 + i) * 32);
+                    }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < 4; ++i) {
                         const int o = (kb0 + i) * 32;
                         const uint4 h0 = *reinterpret_cast<const uint4*>(whi0 + o);
                         const uint4 h1 = *reinterpret_cast<const uint4*>(whi1 + o);
                         const uint4 l0 = *reinterpret_cast<const uint4*>(wlo0 + o);
                         const uint4 l1 = *reinterpret_cast<const uint4*>(wlo1 + o);
-                        mma_f16(acc, h0.x, h1.x, h0.y, h1.y, pv[i].x, pv[i].y);
-                        mma_f16(acc2, h0.z, h1.z, h0.w, h1.w, pv[i].z, pv[i].w);
-                        mma_f16(acl, l0.x, l1.x, l0.y, l1.y, pv[i].x, pv[i].y);
-                        mma_f16(acl2, l0.z, l1.z, l0.w, l1.w, pv[i].z, pv[i].w);
+                        mma_f16(acc[0], h0.x, h1.x, h0.y, h1.y, pa[i].x, pa[i].y);
+                        mma_f16(acc[1], h0.x, h1.x, h0.y, h1.y, pb[i].x, pb[i].y);
+                        mma_f16(acl[0], l0.x, l1.x, l0.y, l1.y, pa[i].x, pa[i].y);
+                        mma_f16(acl[1], l0.x, l1.x, l0.y, l1.y, pb[i].x, pb[i].y);
+                        mma_f16(acc[0], h0.z, h1.z, h0.w, h1.w, pa[i].z, pa[i].w);
+                        mma_f16(acc[1], h0.z, h1.z, h0.w, h1.w, pb[i].z, pb[i].w);
+                        mma_f16(acl[0], l0.z, l1.z, l0.w, l1.w, pa[i].z, pa[i].w);
+                        mma_f16(acl[1], l0.z, l1.z, l0.w, l1.w, pb[i].z, pb[i].w);
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { acc[q] += acc2[q]; acl[q] += acl2[q]; }
                 // D fragment: [0..1] = (chroma g, frames 2*t4, 2*t4+1), [2..3] = (chroma g+8, same frames)
                 constexpr float kLo = 1.0f / 2048.0f;
-                float* dst = part2 + (tl * 2 + kh) * 96;
-                *reinterpret_cast<float2*>(dst + g * 8 + 2 * t4) = make_float2(fmaf(acl[0], kLo, acc[0]), fmaf(acl[1], kLo, acc[1]));
-                if (g < 4)
-                    *reinterpret_cast<float2*>(dst + (g + 8) * 8 + 2 * t4) = make_float2(fmaf(acl[2], kLo, acc[2]), fmaf(acl[3], kLo, acc[3]));
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h == 1 && !vB) break;
+                    float* dst = part2 + ((2 * pr + h) * 2 + kh) * 96;
+                    *reinterpret_cast<float2*>(dst + g * 8 + 2 * t4) =
+                        make_float2(fmaf(acl[h][0], kLo, acc[h][0]), fmaf(acl[h][1], kLo, acc[h][1]));
+                    if (g < 4)
+                        *reinterpret_cast<float2*>(dst + (g + 8) * 8 + 2 * t4) =
+                            make_float2(fmaf(acl[h][2], kLo, acc[h][2]), fmaf(acl[h][3], kLo, acc[h][3]));
+                }
             }
             __syncthreads();
             for (int fl = tid; fl < nt * 8; fl += kThreads) {

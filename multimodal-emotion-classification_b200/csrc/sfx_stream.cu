@@ -704,7 +704,7 @@ template <bool kDebug>
 __global__ void __launch_bounds__(kSThreads, 1) sfx_stream_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_hann = reinterpret_cast<float2*>(smem_raw);
-    float2* s_tw1 = s_hann + 1024;
+    float2* s_tw1 = s_hann + 64;                     // (s_hann: 32 lanes x (cos, cos', sin, sin'), fill_hann_phases)
     float2* s_tw2 = s_tw1 + 1024;
     float2* s_melab = s_tw2 + 512;                                           // [33*32]  (tw2: rows k2 < 16 only)
     float* s_ex = reinterpret_cast<float*>(s_melab + 17 * 64);               // [kSW][kExFloats]
@@ -713,10 +713,10 @@ __global__ void __launch_bounds__(kSThreads, 1) sfx_stream_kernel(const __grid_c
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevTables& tb = p.tb;
+    fill_hann_phases(s_hann, tid);
     for (int i = tid; i < 1024; i += kSThreads) {
         const int r = i >> 5, l = i & 31;
         const int d = (r >> 1) * 64 + 2 * l + (r & 1);
-        s_hann[(r & 15) * 64 + 2 * l + (r >> 4)] = tb.hann[i];        // rows r, r + 16 side by side
         s_tw1[d] = tb.tw1[i];
         if (i < 512) s_tw2[d] = tb.tw2[i];
     }
@@ -832,7 +832,7 @@ __global__ void __launch_bounds__(kSThreads, 1) sfx_stream_kernel(const __grid_c
 
 // ------------------------------------------------------------------------------------------------ host
 size_t smem_stream() {
-    return sizeof(float2) * (2560 + 17 * 64) + sizeof(float) * kSW * kExFloats + sizeof(double) * 104 + sizeof(Sched);
+    return sizeof(float2) * (64 + 1536 + 17 * 64) + sizeof(float) * kSW * kExFloats + sizeof(double) * 104 + sizeof(Sched);
 }
 int stream_slots() { return kSlots; }
 
