@@ -515,6 +515,7 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
         const unsigned lt = (1u << lane) - 1u;
         unsigned cnt = static_cast<unsigned>(wcount);
         const int kmin = tb.kmin, kmax = tb.kmax;
+        const unsigned krange = static_cast<unsigned>(kmax - kmin);       // bin k is inside iff unsigned(k - kmin) <= krange
         for (int gq = kmin >> 7; gq <= (kmax >> 7); ++gq) {
             const int b0 = 128 * gq + 4 * lane;
             const float4 v = *reinterpret_cast<const float4*>(fs.Pb + pidx(b0));
@@ -528,7 +529,7 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             for (int i = 0; i < 4; ++i) {
                 const float pm = w[i], pc = w[i + 1], pp = w[i + 2];
                 const int k = b0 + i;
-                const bool pk = (k >= kmin) & (k <= kmax) & (pc > ref) & (pc > pm) & (pc >= pp);
+                const bool pk = (static_cast<unsigned>(k - kmin) <= krange) & (pc > ref) & (pc > pm) & (pc >= pp);
                 const unsigned bal = __ballot_sync(0xffffffffu, pk);
                 if (bal) {                                           // warp-uniform: most of a tonal frame holds no peak
                     st_record_if(pk, fo.gSeg, cnt + __popc(bal & lt), pm, pc, pp, k);
@@ -921,6 +922,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         {
             // DCT-II of the pooled log-mel vector: coefficient k by a pair of threads (bands 0..63 and 64..127, the two
             // partial sums added in that order), which halves the dependent float64 FMA chain on the tail's critical path
+            // (six threads per coefficient through shared memory measured 0.4 % slower: one more barrier)
             const int k = tid >> 1, h = tid & 1;
             double d = 0.0;
             if (k < p.n_mfcc)
@@ -1098,6 +1100,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         }
       } else {
         float* part2 = cs.s_ex + (2 * kChroma * kP16Stride) / 2;        // [kChromaTiles][2][96] floats after the bank
+        float* part3 = part2 + kChromaTiles * 2 * 96;                   // [kWarps][96]: the incomplete tile, split by steps
         // Frames behind the clip's last non-zero frame (the zero tail load_audio pads short clips with) have all-zero
         // |X|^2 rows and add exactly 0 to every chroma sum: the projection stops at Tc = that frame + 1 (cs.s_f[8 + w] =
         // last non-zero frame seen by warp w, -1 if none); the mean below still divides by T.
@@ -1105,10 +1108,18 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
 #pragma unroll
         for (int w = 1; w < kWarps; ++w) lastnz = fmaxf(lastnz, cs.s_f[8 + w]);
         const int Tc = min(T, static_cast<int>(lastnz) + 1);
-        // full 8-frame tiles, 16 per pass (= 16 units, 2 per warp)
+        // full 8-frame tiles, 16 per pass (= 16 units, 2 per warp); the clip's last, incomplete tile (Tc % 8 frames) rides
+        // along with the last pass: its 32 steps are split evenly over the 8 warps (4 each), so that 130 frames cost every
+        // warp 2 units + 4 steps, one barrier and one normalisation instead of a pass of their own
         const int nfull = Tc >> 3, rem = Tc & 7;
-        for (int tile0 = 0; tile0 < nfull; tile0 += kChromaTiles) {
-            const int nt = min(kChromaTiles, nfull - tile0);
+        const int npass = max(1, (nfull + kChromaTiles - 1) / kChromaTiles);
+        // normalisation: a pair of threads per frame, six classes each (half = tid & 1), the frame maximum by one shuffle
+        const int half = tid & 1;
+        double csum6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};              // per-thread sums over its frames, classes 6*half..+5
+        for (int pass = 0; pass < npass; ++pass) {
+            const int tile0 = pass * kChromaTiles;
+            const int nt = min(kChromaTiles, nfull - tile0);           // 0 when the clip has no full tile at all
+            const bool tail_pass = (pass == npass - 1) && rem;
             // unit = pair of tiles x K-half: every bank fragment read from shared memory feeds the MMAs of two tiles (16
             // frames), which halves the bank's shared-memory traffic (it was 64 wavefronts per frame, a tenth of the kernel's)
             const int npair = (nt + 1) >> 1;
@@ -1164,86 +1175,87 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
                             make_float2(fmaf(acl[h][2], kLo, acc[h][2]), fmaf(acl[h][3], kLo, acc[h][3]));
                 }
             }
-            __syncthreads();
-            for (int fl = tid; fl < nt * 8; fl += kThreads) {
-                const int f = tile0 * 8 + fl;
-                if (f < Tc) {
-                    const float* q = part2 + (fl >> 3) * 192 + (fl & 7);
-                    const float pn = sl.gNy[f];                            // scaled Nyquist bin
-                    float raw[kChroma];
-                    float mx = 0.0f;
+            if (tail_pass) {
+                const int f = nfull * 8 + g;
+                const bool valid = f < Tc;
+                const int k0 = warp * 128 + 8 * t4;                      // steps 4*warp .. 4*warp+3
+                const __half* prow = sl.gP16 + static_cast<size_t>(valid ? f : 0) * kP16Stride + k0;
+                const int r1 = (g < 4) ? g + 8 : g;
+                const __half* whi0 = sW + g * kP16Stride + k0;
+                const __half* whi1 = sW + r1 * kP16Stride + k0;
+                const __half* wlo0 = whi0 + kChroma * kP16Stride;
+                const __half* wlo1 = whi1 + kChroma * kP16Stride;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f};
+                uint4 pv[4];
 #pragma unroll
-                    for (int c = 0; c < kChroma; ++c) {
-                        raw[c] = fmaf(wny[c], pn, q[c * 8] + q[96 + c * 8]);
+                for (int i = 0; i < 4; ++i) pv[i] = valid ? *reinterpret_cast<const uint4*>(prow + i * 32) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int o = i * 32;
+                    const uint4 h0 = *reinterpret_cast<const uint4*>(whi0 + o);
+                    const uint4 h1 = *reinterpret_cast<const uint4*>(whi1 + o);
+                    const uint4 l0 = *reinterpret_cast<const uint4*>(wlo0 + o);
+                    const uint4 l1 = *reinterpret_cast<const uint4*>(wlo1 + o);
+                    mma_f16(acc, h0.x, h1.x, h0.y, h1.y, pv[i].x, pv[i].y);
+                    mma_f16(acc, h0.z, h1.z, h0.w, h1.w, pv[i].z, pv[i].w);
+                    mma_f16(acl, l0.x, l1.x, l0.y, l1.y, pv[i].x, pv[i].y);
+                    mma_f16(acl, l0.z, l1.z, l0.w, l1.w, pv[i].z, pv[i].w);
+                }
+                constexpr float kLo = 1.0f / 2048.0f;
+                float* dst = part3 + warp * 96;
+                *reinterpret_cast<float2*>(dst + g * 8 + 2 * t4) = make_float2(fmaf(acl[0], kLo, acc[0]), fmaf(acl[1], kLo, acc[1]));
+                if (g < 4)
+                    *reinterpret_cast<float2*>(dst + (g + 8) * 8 + 2 * t4) = make_float2(fmaf(acl[2], kLo, acc[2]), fmaf(acl[3], kLo, acc[3]));
+            }
+            __syncthreads();
+            const int nfr = nt * 8 + (tail_pass ? rem : 0);             // frames to normalise in this pass (<= 135)
+            for (int fl0 = 0; fl0 < nfr; fl0 += kThreads / 2) {         // (CTA-uniform trip count: the shuffle below is full-warp)
+                const int fl = fl0 + (tid >> 1);
+                const bool live = fl < nfr;
+                const int f = tile0 * 8 + (live ? fl : 0);
+                const float pn = sl.gNy[f];                              // scaled Nyquist bin
+                const float inv_s = sl.gInvS[f];
+                float raw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                float mx = 0.0f;
+                if (!live) {
+                } else if (fl < nt * 8) {
+                    const float* q = part2 + (fl >> 3) * 192 + (fl & 7) + 48 * half;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        raw[c] = fmaf(wny[6 * half + c], pn, q[c * 8] + q[96 + c * 8]);
                         mx = fmaxf(mx, fabsf(raw[c]));
                     }
-                    // librosa.util.normalize: lengths below tiny(float32) are replaced by 1 (in unscaled units)
-                    const float inv_s = sl.gInvS[f];
-                    const bool small = mx * inv_s < FLT_MIN;
+                } else {
+                    const float* q = part3 + (fl - nt * 8) + 48 * half;   // the 8 step-quarters are added in warp order
 #pragma unroll
-                    for (int c = 0; c < kChroma; ++c)
-                        csum[c] += static_cast<double>(small ? raw[c] * inv_s : __fdiv_rn(raw[c], mx));
+                    for (int c = 0; c < 6; ++c) {
+                        float v = q[c * 8];
+#pragma unroll
+                        for (int w = 1; w < kWarps; ++w) v += q[w * 96 + c * 8];
+                        raw[c] = fmaf(wny[6 * half + c], pn, v);
+                        mx = fmaxf(mx, fabsf(raw[c]));
+                    }
+                }
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                // librosa.util.normalize: lengths below tiny(float32) are replaced by 1 (in unscaled units)
+                const bool small = mx * inv_s < FLT_MIN;
+                if (live) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c)
+                        csum6[c] += static_cast<double>(small ? raw[c] * inv_s : __fdiv_rn(raw[c], mx));
                 }
             }
             __syncthreads();
         }
-        // remainder tile (T % 8 frames): its 32 steps are split evenly over the 8 warps (4 each), so that 130 frames cost
-        // every warp 4 units + 4 steps instead of 5 units for two of them; the 8 partial sums are added in warp order
-        if (rem) {
-            const int f = nfull * 8 + g;
-            const bool valid = f < Tc;
-            const int k0 = warp * 128 + 8 * t4;                      // steps 4*warp .. 4*warp+3
-            const __half* prow = sl.gP16 + static_cast<size_t>(valid ? f : 0) * kP16Stride + k0;
-            const int r1 = (g < 4) ? g + 8 : g;
-            const __half* whi0 = sW + g * kP16Stride + k0;
-            const __half* whi1 = sW + r1 * kP16Stride + k0;
-            const __half* wlo0 = whi0 + kChroma * kP16Stride;
-            const __half* wlo1 = whi1 + kChroma * kP16Stride;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f};
-            uint4 pv[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pv[i] = valid ? *reinterpret_cast<const uint4*>(prow + i * 32) : make_uint4(0u, 0u, 0u, 0u);
+        for (int c = 0; c < 6; ++c) {
+            double v = csum6[c];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int o = i * 32;
-                const uint4 h0 = *reinterpret_cast<const uint4*>(whi0 + o);
-                const uint4 h1 = *reinterpret_cast<const uint4*>(whi1 + o);
-                const uint4 l0 = *reinterpret_cast<const uint4*>(wlo0 + o);
-                const uint4 l1 = *reinterpret_cast<const uint4*>(wlo1 + o);
-                mma_f16(acc, h0.x, h1.x, h0.y, h1.y, pv[i].x, pv[i].y);
-                mma_f16(acc, h0.z, h1.z, h0.w, h1.w, pv[i].z, pv[i].w);
-                mma_f16(acl, l0.x, l1.x, l0.y, l1.y, pv[i].x, pv[i].y);
-                mma_f16(acl, l0.z, l1.z, l0.w, l1.w, pv[i].z, pv[i].w);
-            }
-            constexpr float kLo = 1.0f / 2048.0f;
-            float* dst = part2 + warp * 96;
-            *reinterpret_cast<float2*>(dst + g * 8 + 2 * t4) = make_float2(fmaf(acl[0], kLo, acc[0]), fmaf(acl[1], kLo, acc[1]));
-            if (g < 4)
-                *reinterpret_cast<float2*>(dst + (g + 8) * 8 + 2 * t4) = make_float2(fmaf(acl[2], kLo, acc[2]), fmaf(acl[3], kLo, acc[3]));
-            __syncthreads();
-            if (tid < rem) {
-                const int fr = nfull * 8 + tid;
-                const float* q = part2 + tid;
-                const float pn = sl.gNy[fr];
-                float raw[kChroma];
-                float mx = 0.0f;
-#pragma unroll
-                for (int c = 0; c < kChroma; ++c) {
-                    float v = q[c * 8];
-#pragma unroll
-                    for (int w = 1; w < kWarps; ++w) v += q[w * 96 + c * 8];
-                    raw[c] = fmaf(wny[c], pn, v);
-                    mx = fmaxf(mx, fabsf(raw[c]));
-                }
-                const float inv_s = sl.gInvS[fr];
-                const bool small = mx * inv_s < FLT_MIN;
-#pragma unroll
-                for (int c = 0; c < kChroma; ++c)
-                    csum[c] += static_cast<double>(small ? raw[c] * inv_s : __fdiv_rn(raw[c], mx));
-            }
-            __syncthreads();
+            for (int o = 16; o > 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane < 2) cs.s_wacc[warp * 16 + 3 + 6 * lane + c] = v;
         }
       }
+      if constexpr (kUmmaTail) {
 #pragma unroll
         for (int c = 0; c < kChroma; ++c) {
             double v = csum[c];
@@ -1251,6 +1263,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == 0) cs.s_wacc[warp * 16 + 3 + c] = v;
         }
+      }
     }
     __syncthreads();
 
