@@ -198,24 +198,32 @@ __device__ __forceinline__ int pidx(int k) { return k + 4 * (k >> 5); }   // pad
 
 // ------------------------------------------------------------------------------------------------
 // CTA-wide radix select over the clip's peak magnitudes: key of the element of ascending rank r.
-// count_le = number of elements <= that key.  All threads must call; uses s_hist[256], s_sel[4].
+// count_le = number of elements <= that key; has_next / next = the key of rank r + 1 when the select determined it on the
+// way (the median of an even count needs both).  All threads must call.  h0, h1, h2 = three 256-int histograms.
 // kor / kand = OR / AND of all keys: only the bits in which the keys differ are examined, 8 per pass from the top, so
 // the first pass already spreads over up to 256 bins (keys are order-preserving float bits and a clip's peak
 // magnitudes share their leading exponent bits) instead of piling shared-memory atomics onto a handful of bins.
-static __device__ unsigned radix_select(const unsigned* keys, int np, int r, int* s_hist, int* s_sel, int& count_le,
-                                        unsigned kor, unsigned kand) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// One barrier per pass: the histograms rotate (the one of pass p + 1 is cleared during pass p: its last readers passed the
+// barrier of pass p - 1), and every warp scans the finished histogram itself instead of waiting for warp 0 to publish the
+// bucket.  As soon as the surviving bucket holds <= kSelCand keys they are collected (one more scan) and ranked by counting,
+// every warp for itself -- typically after one or two of the four passes.
+constexpr int kSelCand = 64;
+static __device__ unsigned radix_select(const unsigned* keys, int np, int r, int* h0, int* h1, int* h2, int& count_le,
+                                        unsigned kor, unsigned kand, unsigned& next, bool& has_next) {
+    const int tid = threadIdx.x, lane = tid & 31;
     const unsigned diff = kor ^ kand;
     int remaining = 32 - __clz(diff);                       // differing bits are [0, remaining)
     unsigned mask = remaining >= 32 ? 0u : ~((1u << remaining) - 1u);
     unsigned prefix = kand & mask;
     int less = 0, equal = np;
-    while (remaining > 0) {
+    int* cur = h0; int* nxt = h1; int* third = h2;
+    for (int i = tid; i < 256; i += kThreads) cur[i] = 0;
+    __syncthreads();
+    while (remaining > 0 && equal > kSelCand) {
         const int width = min(8, remaining);
         const int shift = remaining - width;
         const unsigned bmask = (1u << width) - 1u;
-        for (int i = tid; i < 256; i += kThreads) s_hist[i] = 0;
-        __syncthreads();
+        for (int i = tid; i < 256; i += kThreads) nxt[i] = 0;
         // four independent loads per thread and step: a long clip's keys live in global memory (np > kKeyCap), and one
         // load in flight per thread made every pass a chain of L2 round trips
         for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
@@ -224,14 +232,14 @@ static __device__ unsigned radix_select(const unsigned* keys, int np, int r, int
             for (int u = 0; u < 4; ++u) k4[u] = (i0 + u * kThreads < np) ? keys[i0 + u * kThreads] : 0u;
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (i0 + u * kThreads < np && (k4[u] & mask) == prefix) atomicAdd(&s_hist[(k4[u] >> shift) & bmask], 1);
+                if (i0 + u * kThreads < np && (k4[u] & mask) == prefix) atomicAdd(&cur[(k4[u] >> shift) & bmask], 1);
         }
         __syncthreads();
-        if (warp == 0) {
+        {
             int loc[8];
             int sum = 0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) { loc[q] = s_hist[lane * 8 + q]; sum += loc[q]; }
+            for (int q = 0; q < 8; ++q) { loc[q] = cur[lane * 8 + q]; sum += loc[q]; }
             int inc = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -241,34 +249,63 @@ static __device__ unsigned radix_select(const unsigned* keys, int np, int r, int
             const int exc = inc - sum;
             const unsigned bal = __ballot_sync(0xffffffffu, inc > r);
             const int L = __ffs(bal) - 1;
-            if (lane == L) {
-                int rr = r - exc, cum = 0, sel = 0, eq = 0;
-                bool done = false;
+            int rr = r - exc, cum = 0, sel = 0, eq = 0;
+            bool done = false;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (!done) {
-                        if (cum + loc[u] > rr) { done = true; sel = u; eq = loc[u]; }
-                        else cum += loc[u];
-                    }
+            for (int u = 0; u < 8; ++u) {
+                if (!done) {
+                    if (cum + loc[u] > rr) { done = true; sel = u; eq = loc[u]; }
+                    else cum += loc[u];
                 }
-                s_sel[0] = lane * 8 + sel;
-                s_sel[1] = rr - cum;
-                s_sel[2] = exc + cum;
-                s_sel[3] = eq;
             }
+            const int bucket = __shfl_sync(0xffffffffu, lane * 8 + sel, L);
+            r = __shfl_sync(0xffffffffu, rr - cum, L);
+            less += __shfl_sync(0xffffffffu, exc + cum, L);
+            equal = __shfl_sync(0xffffffffu, eq, L);
+            prefix |= static_cast<unsigned>(bucket) << shift;
+            mask |= bmask << shift;
+            remaining = shift;
         }
-        __syncthreads();
-        const int bucket = s_sel[0];
-        r = s_sel[1];
-        less += s_sel[2];
-        equal = s_sel[3];
-        prefix |= static_cast<unsigned>(bucket) << shift;
-        mask |= bmask << shift;
-        remaining = shift;
-        __syncthreads();
+        int* t = cur; cur = nxt; nxt = third; third = t;
     }
-    count_le = less + equal;
-    return prefix;
+    if (remaining == 0) {                                  // every differing bit consumed: `equal` copies of one key
+        count_le = less + equal;
+        next = prefix;
+        has_next = r + 1 < equal;
+        return prefix;
+    }
+    // candidate stage: cur is cleared and unused; cur[0] = count, cur[1 ..] = the bucket's keys in arrival order
+    for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
+        unsigned k4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) k4[u] = (i0 + u * kThreads < np) ? keys[i0 + u * kThreads] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + u * kThreads < np && (k4[u] & mask) == prefix) cur[1 + atomicAdd(&cur[0], 1)] = static_cast<int>(k4[u]);
+    }
+    __syncthreads();
+    const int nc = equal;                                   // == cur[0]
+    const unsigned* cand = reinterpret_cast<const unsigned*>(cur + 1);
+    // lane ranks candidates lane and lane + 32 (ties by list position); the one of rank r is the answer
+    const unsigned my0 = lane < nc ? cand[lane] : 0xffffffffu, my1 = lane + 32 < nc ? cand[lane + 32] : 0xffffffffu;
+    int rk0 = 0, rk1 = 0;
+    for (int j = 0; j < nc; ++j) {
+        const unsigned kj = cand[j];
+        rk0 += (kj < my0) | ((kj == my0) & (j < lane));
+        rk1 += (kj < my1) | ((kj == my1) & (j < lane + 32));
+    }
+    const bool hit0 = lane < nc && rk0 == r, hit1 = lane + 32 < nc && rk1 == r;
+    const bool nx0 = lane < nc && rk0 == r + 1, nx1 = lane + 32 < nc && rk1 == r + 1;
+    const unsigned b0 = __ballot_sync(0xffffffffu, hit0), b1 = __ballot_sync(0xffffffffu, hit1);
+    const unsigned n0 = __ballot_sync(0xffffffffu, nx0), n1 = __ballot_sync(0xffffffffu, nx1);
+    const unsigned key = b0 ? __shfl_sync(0xffffffffu, my0, __ffs(b0) - 1) : __shfl_sync(0xffffffffu, my1, __ffs(b1) - 1);
+    has_next = (n0 | n1) != 0u;
+    next = n0 ? __shfl_sync(0xffffffffu, my0, __ffs(n0) - 1) : __shfl_sync(0xffffffffu, my1, n1 ? __ffs(n1) - 1 : 0);
+    int le = (lane < nc && my0 <= key ? 1 : 0) + (lane + 32 < nc && my1 <= key ? 1 : 0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) le += __shfl_xor_sync(0xffffffffu, le, o);
+    count_le = less + le;
+    return key;
 }
 
 // D(16x8, f32) += A(16x16, f16, row) * B(16x8, f16, col): warp-level tensor-core MMA, FP32 accumulate

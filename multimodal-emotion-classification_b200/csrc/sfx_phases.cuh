@@ -789,27 +789,34 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         FPROF_MARK(8);
         int cle = 0;
         const int r0 = (np - 1) >> 1;
-        const unsigned ka = radix_select(keys, np, r0, cs.s_hist, cs.s_i + 4, cle, static_cast<unsigned>(cs.s_i[18]),
-                                         static_cast<unsigned>(cs.s_i[19]));
+        unsigned knext = 0u;
+        bool has_next = false;
+        // (histograms 1 and 2 of the select live in s_pool, free between the redo list above and the MFCC pooling)
+        const unsigned ka = radix_select(keys, np, r0, cs.s_hist, reinterpret_cast<int*>(cs.s_pool), reinterpret_cast<int*>(cs.s_pool) + 256,
+                                         cle, static_cast<unsigned>(cs.s_i[18]), static_cast<unsigned>(cs.s_i[19]), knext, has_next);
         unsigned kb = ka;
         FPROF_MARK(9);
-        if ((np & 1) == 0 && cle <= (np >> 1)) {
-            // upper median = smallest key above ka
-            if (tid == 0) cs.s_i[4] = static_cast<int>(0xffffffffu);
-            __syncthreads();
-            unsigned best = 0xffffffffu;
-            for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
-                unsigned k4[4];
+        if ((np & 1) == 0) {
+            if (has_next) {
+                kb = knext;                                  // the select ranked the key of rank r0 + 1 as well
+            } else if (cle <= (np >> 1)) {
+                // upper median = smallest key above ka
+                if (tid == 0) cs.s_i[4] = static_cast<int>(0xffffffffu);
+                __syncthreads();
+                unsigned best = 0xffffffffu;
+                for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
+                    unsigned k4[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) k4[u] = (i0 + u * kThreads < np) ? keys[i0 + u * kThreads] : 0u;
+                    for (int u = 0; u < 4; ++u) k4[u] = (i0 + u * kThreads < np) ? keys[i0 + u * kThreads] : 0u;
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (k4[u] > ka && k4[u] < best) best = k4[u];
+                    for (int u = 0; u < 4; ++u)
+                        if (k4[u] > ka && k4[u] < best) best = k4[u];
+                }
+                atomicMin(reinterpret_cast<unsigned*>(&cs.s_i[4]), best);
+                __syncthreads();
+                kb = static_cast<unsigned>(cs.s_i[4]);
+                __syncthreads();
             }
-            atomicMin(reinterpret_cast<unsigned*>(&cs.s_i[4]), best);
-            __syncthreads();
-            kb = static_cast<unsigned>(cs.s_i[4]);
-            __syncthreads();
         }
         FPROF_MARK(10);
         const float fa = fkey_inv(ka), fb = fkey_inv(kb);
