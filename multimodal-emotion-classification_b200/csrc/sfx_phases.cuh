@@ -276,13 +276,6 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
     }
     pmax = warp_max(pmax);
     __syncwarp();
-    // ---- warm L2 with the newest hop of this warp's next frame (its other three hops are shared with
-    //      frames the neighbouring warps are reading now)
-    {
-        constexpr int ahead = kMode == kModeStream ? kStreamWarps : kWarps;
-        const long long nh = static_cast<long long>(kHop) * (t + ahead) + kHop + lane * 32;
-        if (!kSplit && lane < 16 && nh < n) prefetch_l2(x + nh);
-    }
     if (kDebug) {
         if (p.dbg.P && t < p.dbg.T_dbg) {
             float* dP = p.dbg.P + (static_cast<size_t>(clip) * p.dbg.T_dbg + t) * kPStride;
