@@ -63,12 +63,37 @@ def _features_1clip(audio, sr, n_mfcc):
     return row, np.result_type(audio.dtype, np.float32)
 
 
+class UnsupportedAudioFormat(ValueError):
+    """The file is not something the built-in RIFF/WAVE reader decodes (mp3 / ogg / flac, compressed WAVE tags) and no host
+    decoder is importable.  The reference's librosa.load goes through soundfile / audioread for these (config.py:49 lets
+    the Flask app accept mp3 and ogg); this drop-in uses the same two packages when they are installed and otherwise
+    raises this ValueError subclass, which the reference's routes report like any other unreadable upload."""
+
+
+def _host_decode(file_path, why):
+    """(float32 [frames, channels], rate) through soundfile, else audioread -- the decoders behind librosa.load."""
+    try:
+        import soundfile
+        x, rate = soundfile.read(file_path, dtype="float32", always_2d=True)
+        return np.ascontiguousarray(x), int(rate)
+    except ImportError:
+        pass
+    try:
+        import audioread
+        with audioread.audio_open(file_path) as fh:
+            rate, channels = int(fh.samplerate), int(fh.channels)
+            pcm = np.frombuffer(b"".join(fh), dtype="<i2")
+        return (pcm[:len(pcm) // channels * channels].reshape(-1, channels).astype(np.float32) / 32768.0), rate
+    except ImportError:
+        raise UnsupportedAudioFormat(f"{file_path}: {why}; install soundfile or audioread to decode it on the host") from None
+
+
 def _wav_chunks(file_path):
     """(fmt tuple, raw data bytes) of a RIFF/WAVE file."""
     with open(file_path, "rb") as fh:
         data = fh.read()
     if len(data) < 12 or data[:4] != b"RIFF" or data[8:12] != b"WAVE":
-        raise ValueError(f"{file_path}: not a RIFF/WAVE file (only WAV decoding is built in)")
+        raise UnsupportedAudioFormat(f"{file_path}: not a RIFF/WAVE file (only WAV decoding is built in)")
     pos, fmt, raw = 12, None, None
     while pos + 8 <= len(data):
         cid, size = data[pos:pos + 4], struct.unpack("<I", data[pos + 4:pos + 8])[0]
@@ -112,11 +137,11 @@ def _read_wav(file_path):
         elif bits == 32:
             x = (np.frombuffer(raw, dtype="<i4").astype(np.float64) / 2147483648.0).astype(np.float32)
         else:
-            raise ValueError(f"{file_path}: unsupported PCM width {bits}")
+            raise UnsupportedAudioFormat(f"{file_path}: unsupported PCM width {bits}")
     elif tag == 3:
         x = np.frombuffer(raw, dtype="<f4" if bits == 32 else "<f8").astype(np.float32)
     else:
-        raise ValueError(f"{file_path}: unsupported WAVE format tag {tag}")
+        raise UnsupportedAudioFormat(f"{file_path}: unsupported WAVE format tag {tag}")
     x = x[:len(x) // channels * channels].reshape(-1, channels)
     return x, int(rate)
 
@@ -129,7 +154,10 @@ def load_audio(file_path, sr=Config.SAMPLE_RATE, duration=Config.AUDIO_DURATION)
     rates are resampled with a polyphase Kaiser filter (scipy.signal.resample_poly), which is NOT librosa's
     soxr_hq resampler: that front-end is row f3 ("next") of the scope table and carries no parity claim.
     """
-    x, native = _read_wav(file_path)
+    try:
+        x, native = _read_wav(file_path)
+    except UnsupportedAudioFormat as e:                    # mp3 / ogg / compressed WAVE: the host decoders of librosa.load
+        x, native = _host_decode(file_path, str(e).split(": ", 1)[-1])
     if duration is not None:
         x = x[:int(round(native * duration))]
     audio = x.mean(axis=1, dtype=np.float32) if x.shape[1] > 1 else x[:, 0]

@@ -64,9 +64,18 @@ def test_load_audio_pad_trim_and_mono(tmp_path):
     _write_wav(p3, rng.uniform(-0.5, 0.5, size=(48000, 1)), 48000)
     audio3, sr3 = ap.load_audio(p3)
     assert sr3 == 22050 and audio3.shape == (66150,) and not audio3[22050 + 64:].any()
-    with pytest.raises(ValueError):
-        open(os.path.join(tmp_path, "bad.wav"), "wb").write(b"not a wav")
+    # not a WAVE file (an mp3 / ogg upload, reference config.py:49): decoded through soundfile / audioread when importable,
+    # else a ValueError subclass that names the missing decoder
+    open(os.path.join(tmp_path, "bad.wav"), "wb").write(b"not a wav")
+    with pytest.raises(ValueError) as ei:
         ap.load_audio(os.path.join(tmp_path, "bad.wav"))
+    try:
+        import soundfile  # noqa: F401
+    except ImportError:
+        try:
+            import audioread  # noqa: F401
+        except ImportError:
+            assert isinstance(ei.value, ap.UnsupportedAudioFormat) and "soundfile" in str(ei.value)
 
 
 def test_raw_pcm16_reader_selects_only_16_bit_mono_or_stereo(tmp_path):
