@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         }
         const long long fprof_t0 = clock64();
 #endif
-        clip_tail<kDebug, kUmma>(p, tb, cs, sl, clip, T, out, bank_parity, tid, lane, warp, &us);
+        clip_tail<kDebug, kUmma, true>(p, tb, cs, sl, clip, T, out, bank_parity, tid, lane, warp, &us);
 #ifdef SFX_FUSED_DIAG
         if (tid == 0) atomicAdd(&g_fprof[6], static_cast<unsigned long long>(clock64() - fprof_t0));
 #endif

@@ -609,7 +609,9 @@ static __device__ __noinline__ int peak_bin_exact(float pitch, const double* s_e
 // ------------------------------------------------------------------------------------------------ phases 2-3
 // Expects (set up by the caller, followed by __syncthreads): cs.s_i[20 + w] = peak records in segment w, cs.s_i[17] = cs.s_i[18] = 0, cs.s_i[19] = ~0, cs.s_f[w] = per-warp log-mel
 // max, cs.s_wacc[w*16 + 0/1] = per-warp centroid / roll-off sums, cs.s_i[8+w] = per-warp weighted zero-crossing counts.
-template <bool kDebug, bool kUmmaTail = false>
+// kWarpSegs (fused kernel): the per-peak loop gives segment w to warp w (every warp filled one in phase 1, all about the same
+// size) instead of walking one dense index over the segments: no boundary search per record, warp-contiguous loads.
+template <bool kDebug, bool kUmmaTail = false, bool kWarpSegs = false>
 __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, const ClipSmem& cs, const ClipSlice& sl,
                                           const int clip, const int T, float* __restrict__ out, unsigned& bank_parity,
                                           const int tid, const int lane, const int warp, UmmaState* us = nullptr) {
@@ -649,27 +651,42 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         auto peaks = [&](auto SM) {
             constexpr bool kSmem = decltype(SM)::value;
             const float4 kDummy = make_float4(0.f, 1.f, 1.f, __int_as_float(64));      // harmless stand-in past the end
-            // dense peak index -> record: a thread's indices only grow, so it walks the segment boundaries once
+            // index -> record.  Dense form: one index over all segments, a thread's indices only grow, so it walks the
+            // segment boundaries once.  kWarpSegs: index within the warp's own segment, keys land behind those of the
+            // segments before it.
+            const int first = kWarpSegs ? lane : tid, stride = kWarpSegs ? 32 : kThreads;
+            const int count = kWarpSegs ? cs.s_i[20 + warp] : np;
+            int off = 0;
+            if constexpr (kWarpSegs) {
+#pragma unroll
+                for (int v = 0; v < kWarps; ++v) off += (v < warp) ? cs.s_i[20 + v] : 0;
+            }
+            const float4* seg = sl.gRec + static_cast<size_t>(warp) * sl.seg_cap;
             int seg_w = 0, seg_end = cs.s_i[20], seg_adj = 0;          // record of index i sits at gRec[i + seg_adj]
             auto fetch = [&](int i) -> float4 {
-                if (i >= np) return kDummy;
-                while (i >= seg_end) {
-                    ++seg_w;
-                    seg_adj += sl.seg_cap - cs.s_i[20 + seg_w - 1];
-                    seg_end += cs.s_i[20 + seg_w];
+                if (i >= count) return kDummy;
+                if constexpr (kWarpSegs) {
+                    return seg[i];
+                } else {
+                    while (i >= seg_end) {
+                        ++seg_w;
+                        seg_adj += sl.seg_cap - cs.s_i[20 + seg_w - 1];
+                        seg_end += cs.s_i[20 + seg_w];
+                    }
+                    return sl.gRec[i + seg_adj];
                 }
-                return sl.gRec[i + seg_adj];
             };
+            (void)seg; (void)seg_w; (void)seg_end; (void)seg_adj;
             unsigned kor = 0u, kand = 0xffffffffu;
             float4 nxt[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) nxt[u] = fetch(tid + u * kThreads);
-            for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
+            for (int u = 0; u < 4; ++u) nxt[u] = fetch(first + u * stride);
+            for (int i0 = first; i0 < count; i0 += 4 * stride) {
                 float4 recs[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     recs[u] = nxt[u];
-                    nxt[u] = fetch(i0 + (4 + u) * kThreads);                              // next step's records
+                    nxt[u] = fetch(i0 + (4 + u) * stride);                                // next step's records
                 }
                 float shift[4];
                 bool redo = false;
@@ -718,15 +735,15 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
                     const float fl = floorf(uf);
                     const float fr = uf - fl;
                     int bin = max(0, min(kTunings - 1, static_cast<int>(fl)));
-                    const int i = i0 + u * kThreads;
+                    const int j = i0 + u * stride, i = off + j;       // index in the segment / dense index, key slot
                     // normal positive pitch and clear of the bin edges, else redo (NaN-safe: comparisons false -> redo)
                     const bool sure = (fr > 0.0025f) & (fr < 0.9975f) & ((pb - 0x00800000u) < 0x7f000000u);
-                    if (!sure && i < np) {
+                    if (!sure && j < count) {
                         const int slot = atomicAdd(&cs.s_i[17], 1);
                         if (slot < kRedoCap) redo_list[slot] = make_uint2(static_cast<unsigned>(i), pb);
                         else bin = peak_bin_exact(pitch, cs.s_edges);
                     }
-                    if (i < np) {
+                    if (j < count) {
                         kor |= key;
                         kand &= key;
                         if constexpr (kSmem) {
