@@ -115,7 +115,9 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
             } else if (lane == 0) {
                 fo.gE[t] = 0.0f;
                 fo.gNy[t] = 0.0f;
-                fo.gInvS[t] = 0.0f;
+                // split pipeline: -1 marks the all-zero frame for the clips kernel (a non-zero frame below 2^-113 also has
+                // 1/scale = 0); where the chroma normalisation meets it, 0 * -1 = -0 adds nothing, like the fused kernel's 0
+                fo.gInvS[t] = kFrameVals ? -1.0f : 0.0f;
                 if constexpr (kFrameVals) { fo.gCent[t] = 0.0f; fo.gRoll[t] = 0.0f; fo.gLmax[t] = lm0; fo.gZc[t] = 0; }
                 else { fo.s_f[warp] = fmaxf(fo.s_f[warp], lm0); fo.s_f[16 + warp] += 1.0f; }
             }

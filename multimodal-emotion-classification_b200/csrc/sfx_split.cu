@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_clips_kernel(const SplitParam
                 sr += static_cast<double>(sl.gRoll[t]);
                 sz += sl.gZc[t];
                 lm = fmaxf(lm, sl.gLmax[t]);
-                if (sl.gInvS[t] != 0.0f) lastnz = static_cast<float>(t);     // 1/scale is 0 exactly for the all-zero frames
+                if (sl.gInvS[t] >= 0.0f) lastnz = static_cast<float>(t);     // the frames kernel marks all-zero frames with -1
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {

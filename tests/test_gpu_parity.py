@@ -597,3 +597,17 @@ def test_fused_and_split_pipelines_agree(ex):
     small = ex.extract(w[:8]).cpu().numpy()                               # auto mode: B <= 256 takes the split pipeline
     assert ex.lib.sfx_launches_per_extract() == 3
     assert np.array_equal(small, res["split"][0][:8])
+
+
+def test_bench_mix_host_path_equals_fused_kernel(ex):
+    """bench.py's pool (noise / harmonic, full length and zero-tailed) through the fused kernel (4 096 clips, device-resident)
+    and through the chunked host path (split pipeline): the same bits.  The pool holds clips whose last non-zero frame is
+    fainter than 2^-113 -- their 1/scale is 0 like an all-zero frame's, which once moved the end of the chroma projection
+    by a frame in the split pipeline only (bench.py's e2e_f32_bitwise_equal_device_path caught it)."""
+    import bench
+    pool = bench.synth_pool(4096, N3S, seed=1234, device=torch.device("cuda", 0))
+    fused = ex.extract(pool).cpu().numpy()
+    assert ex.lib.sfx_launches_per_extract() == 1
+    host = ex.extract_host(pool.cpu().numpy())
+    assert np.array_equal(fused[:, :53], host[:, :53]) and np.array_equal(fused[:, 55], host[:, 55])
+    np.testing.assert_allclose(fused[:, 53:55], host[:, 53:55], rtol=3e-7)
