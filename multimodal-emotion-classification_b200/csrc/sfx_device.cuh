@@ -199,7 +199,9 @@ __device__ __forceinline__ int pidx(int k) { return k + 4 * (k >> 5); }   // pad
 // ------------------------------------------------------------------------------------------------
 // CTA-wide radix select over the clip's peak magnitudes: key of the element of ascending rank r.
 // count_le = number of elements <= that key; has_next / next = the key of rank r + 1 when the select determined it on the
-// way (the median of an even count needs both).  All threads must call.  h0, h1, h2 = three 256-int histograms.
+// way (the median of an even count needs both).  All threads must call.  h0, h1, h2 = three 256-int histograms; h0 must be
+// all zero and visible to every thread on entry (the caller clears it before its last barrier); `clean` returns one of the
+// three, all zero and visible again on return, for the caller's next histogram.
 // kor / kand = OR / AND of all keys: only the bits in which the keys differ are examined, 8 per pass from the top, so
 // the first pass already spreads over up to 256 bins (keys are order-preserving float bits and a clip's peak
 // magnitudes share their leading exponent bits) instead of piling shared-memory atomics onto a handful of bins.
@@ -209,7 +211,7 @@ __device__ __forceinline__ int pidx(int k) { return k + 4 * (k >> 5); }   // pad
 // every warp for itself -- typically after one or two of the four passes.
 constexpr int kSelCand = 64;
 static __device__ unsigned radix_select(const unsigned* keys, int np, int r, int* h0, int* h1, int* h2, int& count_le,
-                                        unsigned kor, unsigned kand, unsigned& next, bool& has_next) {
+                                        unsigned kor, unsigned kand, unsigned& next, bool& has_next, int*& clean) {
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned diff = kor ^ kand;
     int remaining = 32 - __clz(diff);                       // differing bits are [0, remaining)
@@ -217,8 +219,6 @@ static __device__ unsigned radix_select(const unsigned* keys, int np, int r, int
     unsigned prefix = kand & mask;
     int less = 0, equal = np;
     int* cur = h0; int* nxt = h1; int* third = h2;
-    for (int i = tid; i < 256; i += kThreads) cur[i] = 0;
-    __syncthreads();
     while (remaining > 0 && equal > kSelCand) {
         const int width = min(8, remaining);
         const int shift = remaining - width;
@@ -269,12 +269,16 @@ static __device__ unsigned radix_select(const unsigned* keys, int np, int r, int
         int* t = cur; cur = nxt; nxt = third; third = t;
     }
     if (remaining == 0) {                                  // every differing bit consumed: `equal` copies of one key
+        clean = cur;                                       // cleared during the last pass (or by the caller), never used
         count_le = less + equal;
         next = prefix;
         has_next = r + 1 < equal;
         return prefix;
     }
-    // candidate stage: cur is cleared and unused; cur[0] = count, cur[1 ..] = the bucket's keys in arrival order
+    // candidate stage: cur is cleared and unused; cur[0] = count, cur[1 ..] = the bucket's keys in arrival order.  nxt (last
+    // read before the previous barrier, if ever) is cleared for the caller meanwhile.
+    for (int i = tid; i < 256; i += kThreads) nxt[i] = 0;
+    clean = nxt;
     for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
         unsigned k4[4];
 #pragma unroll

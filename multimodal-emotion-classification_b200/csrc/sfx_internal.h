@@ -22,7 +22,8 @@ constexpr int kExFloats = 32 * 33 * 2;   // per-warp float2[32][33] exchange til
 constexpr int kP16Stride = 1056;         // halves per FP16 |X|^2 row (2112 B = 64 mod 128: conflict-free LDS.128 of the bank rows)
 constexpr int kChromaTiles = 16;         // full 8-frame tiles per pass: 32 units = 4 per warp; their K-half partial sums
                                          // (2 x 16 slots of 96 floats) fit beside the bank in the warp tiles
-constexpr int kRedoCap = 256;            // peaks per clip queued for the reference-form bin (overflow is handled inline)
+constexpr int kRedoCap = 128;            // peaks per clip queued for the reference-form bin (overflow is handled inline); the
+                                         // list sits in the 1 KB of the warp tiles behind the key and bin arrays
 constexpr int kPRow = 36;                // floats per 32 bins of the |X|^2 tile (4 pad: 128-bit conflict-free rows)
 constexpr int kPartOff = 1156;           // offset of the mel partial-sum slots inside a warp's tile
 constexpr int kKeyCap = 13312;           // peak keys (u32) + bins (u8) kept in shared memory during the median select

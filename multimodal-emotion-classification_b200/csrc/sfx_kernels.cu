@@ -115,18 +115,24 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
     const ClipSmem cs{s_ex, s_pool, s_wacc, s_edges, s_mbar, s_hist, s_i, s_f, s_lm, s_lmin, s_ubar, kUmma ? *s_tmem : 0u};
     const ClipSlice sl{gP16, gL, gRec, gKey, gE, gNy, gInvS, gBin, seg_cap};
 
+    // The clip queue: s_i[1] = queue index of the CTA's next clip.  Thread 0 draws it while the tail of the current clip runs
+    // (the global atomic's round trip used to sit between two barriers at the top of the loop, with 255 threads waiting) and
+    // publishes it behind the tail; one barrier per clip separates the clips.
+    if (tid == 0) s_i[1] = atomicAdd(counter, 1);
     for (;;) {
-        __syncthreads();
-        if (tid == 0) { s_i[0] = atomicAdd(counter, 1); s_i[17] = 0; s_i[18] = 0; s_i[19] = -1; }
-        __syncthreads();
-        if (s_i[0] >= p.B) break;
-        const int clip = p.order ? p.order[s_i[0]] : s_i[0];
+        __syncthreads();                           // the previous clip's tail is done with the shared state; s_i[1] is visible
+        const int qi = s_i[1];
+        if (qi >= p.B) break;
+        const int clip = p.order ? p.order[qi] : qi;
         const long long n = clip_samples(p, clip);
         float* out = p.out + static_cast<long long>(clip) * p.out_stride;
         if (n <= 0) {
             for (int i = tid; i < p.n_mfcc + 16; i += kThreads) out[i] = __int_as_float(0x7fc00000);
+            __syncthreads();                       // every thread has read s_i[1]
+            if (tid == 0) s_i[1] = atomicAdd(counter, 1);
             continue;
         }
+        if (tid == 0) { s_i[17] = 0; s_i[18] = 0; s_i[19] = -1; }      // (published by the barrier behind the frames)
         const int T = 1 + static_cast<int>(n / kHop);
         const float* x = p.wave + static_cast<long long>(clip) * p.row_stride;
 
@@ -160,7 +166,10 @@ __global__ void __launch_bounds__(kThreads, 2) sfx_extract_kernel(const Params p
         }
         const long long fprof_t0 = clock64();
 #endif
+        int next_q = 0;
+        if (tid == 0) next_q = atomicAdd(counter, 1);                  // every thread has read s_i[1]; stored behind the tail
         clip_tail<kDebug, kUmma, true>(p, tb, cs, sl, clip, T, out, bank_parity, tid, lane, warp, &us);
+        if (tid == 0) s_i[1] = next_q;
 #ifdef SFX_FUSED_DIAG
         if (tid == 0) atomicAdd(&g_fprof[6], static_cast<unsigned long long>(clock64() - fprof_t0));
 #endif

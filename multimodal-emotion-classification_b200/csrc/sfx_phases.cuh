@@ -649,7 +649,8 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         const bool in_smem = np <= kKeyCap;
         unsigned* keys = in_smem ? reinterpret_cast<unsigned*>(cs.s_ex) : sl.gKey;
         unsigned char* bins = in_smem ? reinterpret_cast<unsigned char*>(cs.s_ex + kKeyCap) : sl.gBin;
-        uint2* redo_list = reinterpret_cast<uint2*>(cs.s_pool);              // (peak index, pitch bits), kRedoCap entries
+        // (peak index, pitch bits), kRedoCap entries, in the 1 KB of the warp tiles behind the shared-memory key and bin arrays
+        uint2* redo_list = reinterpret_cast<uint2*>(cs.s_ex + kKeyCap + kKeyCap / 4);
         auto peaks = [&](auto SM) {
             constexpr bool kSmem = decltype(SM)::value;
             const float4 kDummy = make_float4(0.f, 1.f, 1.f, __int_as_float(64));      // harmless stand-in past the end
@@ -766,6 +767,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             }
         };
         if (in_smem) peaks(std::true_type{}); else peaks(std::false_type{});
+        for (int i = tid; i < 256; i += kThreads) cs.s_hist[i] = 0;          // the select's first histogram
         __syncthreads();
         FPROF_MARK(1);
         {
@@ -797,15 +799,17 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             }
             if (diff) atomicAdd(&cs.s_i[16], diff);
         }
-        __syncthreads();
+        // (no barrier: the redo loop above writes bins, which nothing reads before the barriers of the select)
         FPROF_MARK(8);
         int cle = 0;
         const int r0 = (np - 1) >> 1;
         unsigned knext = 0u;
         bool has_next = false;
         // (histograms 1 and 2 of the select live in s_pool, free between the redo list above and the MFCC pooling)
+        int* thist = nullptr;                            // a cleared histogram for the tuning bins, handed back by the select
         const unsigned ka = radix_select(keys, np, r0, cs.s_hist, reinterpret_cast<int*>(cs.s_pool), reinterpret_cast<int*>(cs.s_pool) + 256,
-                                         cle, static_cast<unsigned>(cs.s_i[18]), static_cast<unsigned>(cs.s_i[19]), knext, has_next);
+                                         cle, static_cast<unsigned>(cs.s_i[18]), static_cast<unsigned>(cs.s_i[19]), knext, has_next,
+                                         thist);
         unsigned kb = ka;
         FPROF_MARK(9);
         if ((np & 1) == 0) {
@@ -834,9 +838,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         const float fa = fkey_inv(ka), fb = fkey_inv(kb);
         thr = ((np & 1) == 0) ? __fmul_rn(__fadd_rn(fa, fb), 0.5f) : fa;
         const unsigned kthr = fkey(thr);
-        // histogram of the residual bins of peaks with mag >= median
-        for (int i = tid; i < 128; i += kThreads) cs.s_hist[i] = 0;
-        __syncthreads();
+        // histogram of the residual bins of peaks with mag >= median, into the cleared histogram the select handed back
         for (int i0 = tid; i0 < np; i0 += 4 * kThreads) {
             unsigned k4[4];
             int b4[4];
@@ -848,16 +850,18 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (i0 + u * kThreads < np && k4[u] >= kthr) atomicAdd(&cs.s_hist[b4[u]], 1);
+                if (i0 + u * kThreads < np && k4[u] >= kthr) atomicAdd(&thist[b4[u]], 1);
         }
+        fence_proxy_async_smem();       // last generic-proxy accesses of the tiles (keys, bins): the bank's async copy follows
         __syncthreads();
-        if (warp == 0) {
+        {
+            // first arg-max, by every warp for itself (no second barrier to publish one warp's answer)
             int bc = -1, bi = 1 << 20, tot = 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int b = lane * 4 + q;
                 if (b < kTunings) {
-                    const int c = cs.s_hist[b];
+                    const int c = thist[b];
                     tot += c;
                     if (c > bc) { bc = c; bi = b; }
                 }
@@ -868,12 +872,12 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (oc > bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
             }
-            tot = warp_sum_i(tot);
-            if (lane == 0) { cs.s_i[2] = bi; cs.s_i[3] = tot; }
+            tuning_idx = bi;
+            nsel = warp_sum_i(tot);
         }
+    } else {
+        fence_proxy_async_smem();       // phase 1's generic-proxy accesses of the tiles precede the bank's async copy
         __syncthreads();
-        tuning_idx = cs.s_i[2];
-        nsel = cs.s_i[3];
     }
     if (kDebug) {
         if (p.dbg.clip_info && tid == 0) {
@@ -889,14 +893,13 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
     // ===================================== phase 3a: MFCC ======================================
     // The tuning's FP16 hi/lo chroma bank (50 688 B) is staged into the now-free warp tiles by one TMA bulk copy
     // (cp.async.bulk, completes on an mbarrier) that runs underneath the MFCC pooling.
-    __half* sW = reinterpret_cast<__half*>(cs.s_ex);       // [2][12][kP16Stride]
-    fence_proxy_async_smem();                           // generic-proxy accesses of the tiles precede the async write
-    __syncthreads();
+    __half* sW = reinterpret_cast<__half*>(cs.s_ex);       // [2][12][kP16Stride]  (fenced and behind a barrier: see above)
     if constexpr (!kUmmaTail) {
         if (tid == 0)
             bulk_copy_g2s(sW, tb.chroma16 + static_cast<size_t>(tuning_idx) * 2 * kChroma * kP16Stride,
                           2 * kChroma * kP16Stride * 2, cs.s_mbar);
     }
+    FPROF_MARK(11);
     {
         const float clampv = __fsub_rn(gmx, 80.0f);
         // power_to_db's clamp max(L, gmax - 80) is the identity on every non-zero frame of most clips (it exists for the
@@ -916,6 +919,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             for (int w = 1; w < kWarps; ++w) lmin = fminf(lmin, cs.s_f[24 + w]);
             fast = lmin >= clampv;
         }
+        FPROF_MARK(12);
         if (fast) {
             if (tid < 128) {
                 float nz = cs.s_f[16];
@@ -938,6 +942,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             if (tid < 128) cs.s_pool[tid] = (cs.s_pool[tid] + cs.s_pool[128 + tid]) / static_cast<double>(T);
         }
         __syncthreads();
+        FPROF_MARK(13);
         {
             // DCT-II of the pooled log-mel vector: coefficient k by a pair of threads (bands 0..63 and 64..127, the two
             // partial sums added in that order), which halves the dependent float64 FMA chain on the tail's critical path
@@ -1264,7 +1269,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
                         csum6[c] += static_cast<double>(small ? raw[c] * inv_s : __fdiv_rn(raw[c], mx));
                 }
             }
-            __syncthreads();
+            if (pass + 1 < npass) __syncthreads();          // every reader is done before the next pass overwrites the partials
         }
 #pragma unroll
         for (int c = 0; c < 6; ++c) {

@@ -35,5 +35,6 @@ for kind, w in [("mix", pool)] + [(bench.KINDS[k], pool[k::4].contiguous()) for 
     print(f"{kind}: {w.shape[0] / e0.elapsed_time(e1) / 1e3:.3f} M clips/s; cycles per clip per CTA: " +
           ", ".join(f"{nm} {float(buf[i]) / n:.0f}" for i, nm in enumerate(names[:7])) +
           f"; inside select+hist: redo {float(buf[8]) / n:.0f}, radix select {float(buf[9]) / n:.0f}, upper median "
-          f"{float(buf[10]) / n:.0f}, (select+hist above = histogram + argmax only)", flush=True)
+          f"{float(buf[10]) / n:.0f}, (select+hist above = histogram + argmax only); inside mfcc: fence+barrier+bank copy issue "
+          f"{float(buf[11]) / n:.0f}, minimum + barrier {float(buf[12]) / n:.0f}, pooling + barrier {float(buf[13]) / n:.0f} (mfcc above = the DCT only)", flush=True)
 ex.set_pipeline("auto")
