@@ -58,7 +58,8 @@ typedef struct {
     int32_t       pip_kmax;
     int32_t       mel_ps;        /* row stride of the per-lane mel partial-sum slots (odd, <= 31) */
     int32_t       mel_flush32;   /* 1 if the Slaney interval index advances at the Nyquist bin */
-    const float  *hann;          /* [2048] */
+    const float  *hann;          /* [2048] periodic Hann window; uploaded and validated, but since round 2 the kernels build the
+                                  * window from cos/sin of the sample phase (within 1 ulp(0.5) of these values) instead of reading it */
     const float  *tw1;           /* [32][32][2] */
     const float  *tw2;           /* [32][32][2] */
     const float  *mel_ab;        /* [33][32][2] (falling, rising) weights of bin 32*lane + j at [j][lane] */
