@@ -611,3 +611,41 @@ def test_bench_mix_host_path_equals_fused_kernel(ex):
     host = ex.extract_host(pool.cpu().numpy())
     assert np.array_equal(fused[:, :53], host[:, :53]) and np.array_equal(fused[:, 55], host[:, 55])
     np.testing.assert_allclose(fused[:, 53:55], host[:, 53:55], rtol=3e-7)
+
+
+def test_median_select_with_massive_duplicates_and_tiny_peak_lists(ex):
+    """The median of the peak magnitudes (librosa.pitch_tuning's threshold) on inputs that drive the CTA-wide select through
+    all of its exits: hop-periodic signals make every interior frame identical, so thousands of peaks share a handful of
+    magnitudes (the surviving bucket never shrinks below the candidate limit and every differing bit is consumed); clips of
+    two to five frames hold fewer peaks than the candidate limit from the start.  Fused, split and stream pipelines (the
+    stream tail has a select of its own) against the oracle, fused and split bit for bit."""
+    sr, n = 22050, N3S
+    t = np.arange(n, dtype=np.float64)
+    i512 = np.arange(512, dtype=np.float64)
+
+    def tiled(block):                    # one hop of float32 samples repeated: interior frames are identical bit for bit
+        return np.tile(block.astype(np.float32), n // 512 + 1)[:n]
+
+    sig = [tiled(0.5 * np.sin(2 * np.pi * 10 * i512 / 512)),
+           tiled(0.3 * np.sin(2 * np.pi * 7 * i512 / 512) + 0.2 * np.sin(2 * np.pi * 23 * i512 / 512 + 1.0)),
+           tiled(0.4 * np.sign(np.sin(2 * np.pi * i512 / 64.0 + 0.1))),
+           0.25 * np.sin(2 * np.pi * (33 * sr / 512) * t / sr) ** 3]
+    w = np.stack(sig).astype(np.float32)
+    ref = lp.features_batch(w)
+    lens = np.array([600, 1100, 2048, 2600], dtype=np.int32)
+    rng = np.random.default_rng(5)
+    ws = (0.2 * rng.standard_normal((4, 2600))).astype(np.float32)
+    ws[0] += (0.3 * np.sin(2 * np.pi * 440.0 * np.arange(2600) / sr)).astype(np.float32)
+    ref_s = np.stack([lp.features_batch(ws[i:i + 1, :lens[i]])[0] for i in range(4)])
+    res = {}
+    try:
+        for mode, name in ((1, "fused"), (2, "split"), (3, "stream")):
+            assert ex.lib.sfx_set_pipeline(mode) == 0
+            res[name] = (ex.extract(dev(w)).cpu().numpy(), ex.extract(dev(ws), dev(lens)).cpu().numpy())
+    finally:
+        ex.lib.sfx_set_pipeline(0)
+    for name, (a, b) in res.items():
+        assert_parity(a, ref)
+        assert_parity(b, ref_s)
+    for a, b in zip(res["fused"], res["split"]):
+        assert np.array_equal(a[:, :53], b[:, :53]) and np.array_equal(a[:, 55], b[:, 55])
