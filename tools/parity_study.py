@@ -29,15 +29,21 @@ def main():
     chunk = 16
     seeds = [5000 + i for i in range(n // chunk)]
     cores = len(os.sched_getaffinity(0))
-    t0 = time.time()
-    with mp.get_context("fork").Pool(cores) as pool:          # before CUDA is initialised
-        res = pool.map(oracle_chunk, [(s, chunk) for s in seeds])
-    t_oracle = time.time() - t0
+    cache = f"/tmp/parity_oracle_{n}.npz"                  # a second library (SFX_B200_LIB=...) in the same job reuses the oracle rows
+    if os.path.exists(cache):
+        z = np.load(cache)
+        ref, ref_tun, t_oracle = z["ref"], z["ref_tun"], float(z["t"])
+    else:
+        t0 = time.time()
+        with mp.get_context("fork").Pool(cores) as pool:          # before CUDA is initialised
+            res = pool.map(oracle_chunk, [(s, chunk) for s in seeds])
+        t_oracle = time.time() - t0
+        ref = np.concatenate([r[1] for r in res])
+        ref_tun = np.concatenate([r[2] for r in res])
+        np.savez(cache, ref=ref, ref_tun=ref_tun, t=t_oracle)
     import torch
     from sfx_b200 import get_extractor
     ex = get_extractor(torch.device("cuda", 0))
-    ref = np.concatenate([r[1] for r in res])
-    ref_tun = np.concatenate([r[2] for r in res])
     got, tun = [], []
     for s in seeds:
         w = synth.make_batch(chunk, 66150, seed=s)
@@ -48,7 +54,7 @@ def main():
     flips = np.abs(tun - ref_tun) > 1e-6
     ok, report = synth.compare(got[~flips], ref[~flips])
     kinds = np.array([synth.KINDS[i % 4] for i in range(chunk)] * len(seeds))
-    summary = {"clips": int(n), "oracle_seconds": t_oracle, "host_cores": cores,
+    summary = {"library": os.environ.get("SFX_B200_LIB", "installed"), "clips": int(n), "oracle_seconds": t_oracle, "host_cores": cores,
                "tuning_flips": int(flips.sum()), "tuning_flips_by_kind": {k: int(flips[kinds == k].sum()) for k in synth.KINDS},
                "all_within_tolerance_excluding_flips": bool(ok), "report": report.split("\n"),
                "rolloff_differs": int((np.abs(got[:, 54] - ref[:, 54]) > 1e-3).sum()),
@@ -57,6 +63,21 @@ def main():
         rel = np.abs(got[flips, 40:52] - ref[flips, 40:52]) / np.maximum(np.abs(ref[flips, 40:52]), 1e-9)
         summary["chroma_rel_err_on_flipped_clips_max"] = float(rel.max())
         summary["flip_deltas"] = [float(x) for x in (tun[flips] - ref_tun[flips])[:16]]
+        # how close the oracle's own arg-max was: the two largest counts of its 100-bin residual histogram
+        margins = []
+        for i in np.nonzero(flips)[0][:16]:
+            w = synth.make_batch(chunk, 66150, seed=seeds[i // chunk])[i % chunk]
+            S = lp.spectrogram(w, power=2)
+            pitch, mag = lp.piptrack(S)
+            m = pitch > 0
+            sel = pitch[(mag >= np.median(mag[m])) & m]
+            res_ = np.mod(12 * lp.hz_to_octs(sel), 1.0)
+            res_[res_ >= 0.5] -= 1.0
+            counts, edges = np.histogram(res_, np.linspace(-0.5, 0.5, 101))
+            top = np.argsort(counts)[::-1][:3]
+            margins.append({"clip": int(i), "kind": str(kinds[i]), "gpu_tuning": float(tun[i]), "oracle_tuning": float(ref_tun[i]),
+                            "oracle_top_bins": [[float(edges[b]), int(counts[b])] for b in top]})
+        summary["flipped_clips"] = margins
     print(json.dumps(summary, indent=1))
     if out_path:
         json.dump(summary, open(out_path, "w"), indent=1)
