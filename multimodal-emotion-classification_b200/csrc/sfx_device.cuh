@@ -330,6 +330,16 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* ptr, unsigned bytes
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
 }
 
+// Tell L2 that a range of scratch is dead: the 128-byte lines that lie entirely inside [ptr, ptr + bytes) are discarded
+// (discard.global.L2), i.e. dropped without a write-back if they are still resident and dirty.  All kThreads threads of the
+// CTA call it; the range must not be read again before it is rewritten.
+__device__ __forceinline__ void discard_l2_range(const void* ptr, size_t bytes, int tid) {
+    const unsigned long long a0 = (reinterpret_cast<unsigned long long>(ptr) + 127ull) & ~127ull;
+    const unsigned long long a1 = (reinterpret_cast<unsigned long long>(ptr) + bytes) & ~127ull;
+    for (unsigned long long a = a0 + 128ull * tid; a < a1; a += 128ull * kThreads)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(a) : "memory");
+}
+
 // ---- TMA bulk copy (global -> shared) completing on an mbarrier
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {

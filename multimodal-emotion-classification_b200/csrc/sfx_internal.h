@@ -20,6 +20,8 @@ constexpr int kStreamWarps = 16;         // warps per CTA of the stream kernel (
 constexpr int kThreads = kWarps * 32;
 constexpr int kExFloats = 32 * 33 * 2;   // per-warp float2[32][33] exchange tile, reused as the padded |X|^2 tile
 constexpr int kP16Stride = 1056;         // halves per FP16 |X|^2 row (2112 B = 64 mod 128: conflict-free LDS.128 of the bank rows)
+constexpr int kP16Row = 1024;            // halves per FP16 |X|^2 row in the scratch (bins 0..1023; the Nyquist bin travels apart): 2 KB, so that
+                                         // the rows of all 296 CTAs of a 3 s batch (78.8 MB) fit the 79 MB persisting-L2 set-aside whole
 constexpr int kChromaTiles = 16;         // full 8-frame tiles per pass: 32 units = 4 per warp; their K-half partial sums
                                          // (2 x 16 slots of 96 floats) fit beside the bank in the warp tiles
 constexpr int kRedoCap = 128;            // peaks per clip queued for the reference-form bin (overflow is handled inline); the
@@ -88,7 +90,7 @@ __host__ __device__ inline int rec_frames(int Tmax) { return (Tmax + kWarps - 1)
 //  16 K blocks per atom row group: ceil(Tmax / 8) * 16 KB)
 inline size_t cta_p16_bytes(int Tmax, bool umma = false) {
     if (umma) return static_cast<size_t>((Tmax + 7) / 8) * 16 * 1024;
-    return (static_cast<size_t>(Tmax) * kP16Stride * 2 + 255) & ~static_cast<size_t>(255);
+    return (static_cast<size_t>(Tmax) * kP16Row * 2 + 255) & ~static_cast<size_t>(255);
 }
 inline size_t cta_lm_bytes(int Tmax) { return (static_cast<size_t>(Tmax) * kMels * 4 + 255) & ~static_cast<size_t>(255); }
 // bytes of the rest of a CTA's scratch for clips of up to Tmax frames (multiple of 256)
@@ -118,7 +120,7 @@ struct SplitParams {
 
 // bytes of one clip's slice in the split pipeline (multiple of 256)
 inline size_t split_slice_bytes(int Tmax, int max_pk) {
-    size_t b = static_cast<size_t>(Tmax) * (kP16Stride * 2 + kMels * 4 + 12 + 16 + static_cast<size_t>(max_pk) * (16 + 4 + 1));
+    size_t b = static_cast<size_t>(Tmax) * (kP16Row * 2 + kMels * 4 + 12 + 16 + static_cast<size_t>(max_pk) * (16 + 4 + 1));
     return (b + 255) & ~static_cast<size_t>(255);
 }
 
@@ -126,7 +128,7 @@ inline size_t split_slice_bytes(int Tmax, int max_pk) {
 inline size_t stream_slot_bytes(int Tmax, int max_pk) {
     // per frame: FP16 |X|^2 row, log-mel row, the record of per-frame values, max_pk peak records (float4: every frame owns
     // a fixed segment, its fill level is part of the per-frame record), peak keys (u32) + bins (u8) of the overflow path
-    size_t b = static_cast<size_t>(Tmax) * (kP16Stride * 2 + kMels * 4 + 8 * 4 + static_cast<size_t>(max_pk) * (16 + 4 + 1));
+    size_t b = static_cast<size_t>(Tmax) * (kP16Row * 2 + kMels * 4 + 8 * 4 + static_cast<size_t>(max_pk) * (16 + 4 + 1));
     return (b + 255) & ~static_cast<size_t>(255);
 }
 size_t smem_stream();

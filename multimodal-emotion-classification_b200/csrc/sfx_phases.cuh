@@ -9,6 +9,15 @@
 #pragma once
 #include "sfx_device.cuh"
 
+// Which dead scratch the fused tail drops from L2 (discard_l2_range: discard.global.L2, SASS CCTL.E.RML2, one per 128-byte line):
+// 1 peak records (after the per-peak loop), 2 log-mel rows (after the pooling), 4 FP16 |X|^2 rows (after the chroma projection).
+// Measured on the bench mix (tools/dram_ab.sh, tools/ab_probe.py): 4 takes the DRAM traffic from 549 to 485 KB per clip (7 takes
+// it to 450) but costs 1.3 % of the throughput (2 145 cache-control instructions per clip through the LSU), 1 and 2 save ~10 KB
+// for 1 %: HBM is at 12 % utilisation, so the default is 0 (off).
+#ifndef SFX_DISCARD
+#define SFX_DISCARD 0
+#endif
+
 namespace sfx {
 
 // Cycle accounting of the fused kernel (library built with -DSFX_FUSED_DIAG, tools/fused_prof.py): thread 0 of every CTA adds
@@ -106,7 +115,7 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
                 for (int q4 = 0; q4 < 4; ++q4)
                     *reinterpret_cast<uint4*>(img + umma_p16_offset(p.Tmax, t, lane >> 1, (lane & 1) * 4 + q4)) = make_uint4(0u, 0u, 0u, 0u);
             } else {
-                uint4* dst = reinterpret_cast<uint4*>(fo.gP16 + static_cast<size_t>(t) * kP16Stride + 32 * lane);
+                uint4* dst = reinterpret_cast<uint4*>(fo.gP16 + static_cast<size_t>(t) * kP16Row + 32 * lane);
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(0u, 0u, 0u, 0u);
             }
@@ -352,7 +361,7 @@ __device__ __forceinline__ void process_frame(const Params& p, const DevTables& 
                     *reinterpret_cast<uint4*>(img + umma_p16_offset(p.Tmax, t, lane >> 1, (lane & 1) * 4 + q4)) =
                         make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
             } else {
-                uint4* dst = reinterpret_cast<uint4*>(fo.gP16 + static_cast<size_t>(t) * kP16Stride + 32 * lane);
+                uint4* dst = reinterpret_cast<uint4*>(fo.gP16 + static_cast<size_t>(t) * kP16Row + 32 * lane);
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
             }
@@ -769,6 +778,12 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
         if (in_smem) peaks(std::true_type{}); else peaks(std::false_type{});
         for (int i = tid; i < 256; i += kThreads) cs.s_hist[i] = 0;          // the select's first histogram
         __syncthreads();
+        if constexpr (kWarpSegs && !kDebug && (SFX_DISCARD & 1)) {
+            // the records are dead: drop their lines from L2 instead of letting them be written back to HBM (16 B per peak)
+#pragma unroll 1
+            for (int w = 0; w < kWarps; ++w)
+                discard_l2_range(sl.gRec + static_cast<size_t>(w) * sl.seg_cap, static_cast<size_t>(cs.s_i[20 + w]) * sizeof(float4), tid);
+        }
         FPROF_MARK(1);
         {
             const int nredo = min(cs.s_i[17], kRedoCap);
@@ -942,6 +957,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
             if (tid < 128) cs.s_pool[tid] = (cs.s_pool[tid] + cs.s_pool[128 + tid]) / static_cast<double>(T);
         }
         __syncthreads();
+        if constexpr (kWarpSegs && (SFX_DISCARD & 2)) discard_l2_range(sl.gL, static_cast<size_t>(T) * kMels * sizeof(float), tid);   // rows pooled: dead
         FPROF_MARK(13);
         {
             // DCT-II of the pooled log-mel vector: coefficient k by a pair of threads (bands 0..63 and 64..127, the two
@@ -1151,8 +1167,8 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
                 const int pr = u >> 1, kh = u & 1;
                 const bool vB = 2 * pr + 1 < nt;                      // an odd tile count leaves the last pair half empty
                 const int fA = (tile0 + 2 * pr) * 8 + g, fB = fA + (vB ? 8 : 0);
-                const __half* prowA = sl.gP16 + static_cast<size_t>(fA) * kP16Stride + kh * 512 + 8 * t4;
-                const __half* prowB = sl.gP16 + static_cast<size_t>(fB) * kP16Stride + kh * 512 + 8 * t4;
+                const __half* prowA = sl.gP16 + static_cast<size_t>(fA) * kP16Row + kh * 512 + 8 * t4;
+                const __half* prowB = sl.gP16 + static_cast<size_t>(fB) * kP16Row + kh * 512 + 8 * t4;
                 const int r1 = (g < 4) ? g + 8 : g;                  // bank rows 12..15 do not exist
                 const __half* whi0 = sW + g * kP16Stride + kh * 512 + 8 * t4;
                 const __half* whi1 = sW + r1 * kP16Stride + kh * 512 + 8 * t4;
@@ -1203,7 +1219,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
                 const int f = nfull * 8 + g;
                 const bool valid = f < Tc;
                 const int k0 = warp * 128 + 8 * t4;                      // steps 4*warp .. 4*warp+3
-                const __half* prow = sl.gP16 + static_cast<size_t>(valid ? f : 0) * kP16Stride + k0;
+                const __half* prow = sl.gP16 + static_cast<size_t>(valid ? f : 0) * kP16Row + k0;
                 const int r1 = (g < 4) ? g + 8 : g;
                 const __half* whi0 = sW + g * kP16Stride + k0;
                 const __half* whi1 = sW + r1 * kP16Stride + k0;
@@ -1290,6 +1306,7 @@ __device__ __forceinline__ void clip_tail(const Params& p, const DevTables& tb, 
       }
     }
     __syncthreads();
+    if constexpr (kWarpSegs && !kUmmaTail && (SFX_DISCARD & 4)) discard_l2_range(sl.gP16, static_cast<size_t>(T) * kP16Row * sizeof(__half), tid);   // projected: dead
 
     FPROF_MARK(5);
     // ===================================== epilogue: pooled row ================================

@@ -18,7 +18,7 @@ struct Slice {
 __device__ __forceinline__ Slice slice_of(unsigned char* base, int Tmax, int max_pk) {
     Slice s;
     s.gP16 = reinterpret_cast<__half*>(base);
-    s.gL = reinterpret_cast<float*>(s.gP16 + static_cast<size_t>(Tmax) * kP16Stride);
+    s.gL = reinterpret_cast<float*>(s.gP16 + static_cast<size_t>(Tmax) * kP16Row);
     s.gRec = reinterpret_cast<float4*>(s.gL + static_cast<size_t>(Tmax) * kMels);
     s.gKey = reinterpret_cast<unsigned*>(s.gRec + static_cast<size_t>(Tmax) * max_pk);
     s.gE = reinterpret_cast<float*>(s.gKey + static_cast<size_t>(Tmax) * max_pk);

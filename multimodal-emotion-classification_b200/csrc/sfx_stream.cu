@@ -100,7 +100,7 @@ struct StreamSlice {
 __device__ __forceinline__ StreamSlice stream_slice(unsigned char* base, int Tmax, int max_pk) {
     StreamSlice s;
     s.gP16 = reinterpret_cast<__half*>(base);
-    s.gL = reinterpret_cast<float*>(s.gP16 + static_cast<size_t>(Tmax) * kP16Stride);
+    s.gL = reinterpret_cast<float*>(s.gP16 + static_cast<size_t>(Tmax) * kP16Row);
     s.gFv = s.gL + static_cast<size_t>(Tmax) * kMels;
     s.gRec = reinterpret_cast<float4*>(s.gFv + static_cast<size_t>(Tmax) * kFvStride);
     s.gKey = reinterpret_cast<unsigned*>(s.gRec + static_cast<size_t>(Tmax) * max_pk);
@@ -223,7 +223,7 @@ static __device__ __forceinline__ void chroma_group(const ChromaLane& cl, const 
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
         const int f = min(f0 + 8 * j + cl.g, T - 1);                // rows past the clip repeat its last frame, never used
-        prow[j] = reinterpret_cast<const uint4*>(sl.gP16 + static_cast<size_t>(f) * kP16Stride + 8 * cl.t4);
+        prow[j] = reinterpret_cast<const uint4*>(sl.gP16 + static_cast<size_t>(f) * kP16Row + 8 * cl.t4);
     }
     float acc[NT][4], acl[NT][4];
 #pragma unroll
@@ -307,7 +307,7 @@ static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned cha
                 bulk_prefetch_l2(sl.gRec + off, static_cast<unsigned>(min(4096, np - off)) * 16u);
         }
         for (int t0 = 0; t0 < T; t0 += 64) bulk_prefetch_l2(sl.gL + static_cast<size_t>(t0) * kMels, static_cast<unsigned>(min(64, T - t0)) * kMels * 4u);
-        bulk_prefetch_l2(sl.gP16, static_cast<unsigned>(min(32, T)) * kP16Stride * 2u);
+        bulk_prefetch_l2(sl.gP16, static_cast<unsigned>(min(32, T)) * kP16Row * 2u);
     }
 #ifdef SFX_STREAM_DIAG
     long long tp0 = clock64();
@@ -585,7 +585,7 @@ static __device__ __noinline__ void clip_tail_warp(const Params& p, unsigned cha
         const ChromaLane cl{tb.chroma_frag + static_cast<size_t>(tuning_idx) * (32 * 128) + lane, wny0, wny1, g, t4};
         for (int f0 = 0; f0 < T; f0 += 32) {
             if (lane == 0 && f0 + 32 < T)                           // next group's rows on their way to L2
-                bulk_prefetch_l2(sl.gP16 + static_cast<size_t>(f0 + 32) * kP16Stride, static_cast<unsigned>(min(32, T - f0 - 32)) * kP16Stride * 2u);
+                bulk_prefetch_l2(sl.gP16 + static_cast<size_t>(f0 + 32) * kP16Row, static_cast<unsigned>(min(32, T - f0 - 32)) * kP16Row * 2u);
             // always four 8-frame tiles (one instantiation: code size): tiles past the clip repeat its last frame, are
             // multiplied for nothing (the tensor pipe is otherwise idle) and ignored
             chroma_group<4>(cl, sl, f0, T, cs0, cs1);
