@@ -111,12 +111,13 @@ int         sfx_launches_per_extract(void);
 /* Pipeline selection: 0 = auto (default), 1 = fused, 2 = split, 3 = stream, 4 = fused_umma.  One arithmetic:
  *   stream  one persistent 16-warp CTA per SM; every warp pulls STFT frames or whole per-clip tails (tuning estimate,
  *           MFCC, chroma, pooled row) from a CTA-local scheduler, so a tail occupies one warp while 15 keep transforming
- *           frames.  Highest throughput on large batches.
+ *           frames.  Built and measured (1.42 M clips/s against the fused kernel's 2.03 M on the bench mix); kept as an A/B.
  *   fused   persistent 8-warp CTAs, two per SM, one clip per CTA at a time (frames, barrier, tail by all 8 warps).
+ *           Highest throughput on large batches: the kernel bench.py times.
  *   split   frame-parallel two-kernel pipeline per chunk of <= 1024 clips: lowest latency for small batches.
  *   fused_umma  the fused kernel with its chroma projection on tcgen05 (UMMA, accumulator in tensor memory) instead of
  *           mma.sync: same throughput (measured), kept as the A/B of the two tensor paths.
- * auto = split for batches that fit one chunk of at most 1024 clips (256 when ragged), stream above that.  Also settable
+ * auto = split for batches that fit one chunk of at most 1024 clips (256 when ragged), fused above that.  Also settable
  * through the environment variable SFX_PIPELINE=auto|fused|split|stream|fused_umma before the first call.  The mode is read once per
  * call (atomically); call sfx_workspace_bytes again after changing it. */
 int         sfx_set_pipeline(int mode);
