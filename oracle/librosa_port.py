@@ -13,7 +13,9 @@ torchaudio's librosa-compatible Slaney mel bank / ortho DCT / MFCC, transformers
 bin-centred sinusoid).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
-legs may import this module -- as the checker or the reported CPU baseline, never as the product.
+legs may import this module -- as the checker or the reported CPU baseline, never as the product
+(the study scripts under ``tools/`` -- parity_study.py, pin_against_librosa.py, eq_check*.py -- are checkers of the same
+kind: they ship no code path and nothing under the package imports them).
 
 Each function cites the reference line it stands behind and the librosa 0.10.0 routine it restates.
 dtype trail (SURVEY App. A.1): float32 audio -> float64 window*frames -> float64 rfft -> complex64;
